@@ -1,0 +1,97 @@
+// Sequence of passes of one FFT convolution (host logic, backend independent).
+//
+// Replaces imglib2-algorithm FFTConvolution.convolve() as called from
+// S/SimulateMultiViewDataset.java:257-261 (mirror-single image (x) zero-extended kernel, kernel
+// element kdim/2 at the origin, no conjugation, same-size output).  The padded transforms are
+// "pruned": each pass reads only rows that carry data and writes only rows the next pass needs.
+//
+//   PSF:    xfwd(zero ext) -> P1[KZ][KY][KXc] -> y fwd -> P2[KZ][Ny][KXc] -> z fwd (scaled) -> H[Nz][Ny][KXc]
+//   image:  xfwd(mirror)   -> U1[Z][Y][KXc]  -> y fwd -> U2[Z][Ny][KXc]  -> z fwd * H, z inv (in place)
+//           -> y inv -> U1[Z][Y][KXc] -> x inv + crop (+ per-block sums) -> out[Z][Y][X]
+//
+// `L` is the launcher: the CUDA one enqueues kernels on a stream, the emulation one (tests/emu)
+// executes the same phase functions on the CPU.
+#pragma once
+#include "conv_plan.h"
+#include "line_fft.cuh"
+
+namespace mvsim {
+
+struct ConvWorkspace {
+    float2* u1;     // u1_elems
+    float2* u2;     // u2_elems
+    float2* h;      // h_elems
+    float2* p1;     // p1_elems
+    float2* p2;     // p2_elems
+    const float2 *tw_x, *tw_y, *tw_z, *twist_x;   // tables for sx.n, sy.n, sz.n
+};
+
+// PSF (already normalised to sum 1) -> scaled spectrum ws.h
+template <class L> int conv_psf_spectrum(L& l, const ConvPlan& pl, const ConvWorkspace& ws, const float* psf)
+{
+    const long long kxc = pl.kxc();
+    XParams xp = {};
+    xp.rin = psf; xp.cout = ws.p1; xp.tw = ws.tw_x; xp.twist = ws.twist_x;
+    xp.X = pl.kdims[0]; xp.n_rows = pl.kdims[1] * pl.kdims[2]; xp.left = 0; xp.zero_ext = 1;
+    int err = l.launch_x(false, pl.sx, xp);
+    if (err) return err;
+
+    StridedParams sp = {};
+    sp.in = ws.p1; sp.out = ws.p2; sp.tw = ws.tw_y; sp.kx_count = (int)kxc;
+    sp.n_src = pl.kdims[1]; sp.left = 0; sp.zero_ext = 1;
+    sp.in_estride = kxc; sp.in_ostride = (long long)pl.kdims[1] * kxc;
+    sp.out_estride = kxc; sp.out_ostride = (long long)pl.sy.n * kxc;
+    sp.scale = 1.0f;
+    err = l.launch_strided(false, pl.sy, sp, pl.kdims[2]);
+    if (err) return err;
+
+    sp.in = ws.p2; sp.out = ws.h; sp.tw = ws.tw_z;
+    sp.n_src = pl.kdims[2];
+    sp.in_estride = (long long)pl.sy.n * kxc; sp.in_ostride = kxc;
+    sp.out_estride = (long long)pl.sy.n * kxc; sp.out_ostride = kxc;
+    sp.scale = (float)pl.scale;
+    return l.launch_strided(false, pl.sz, sp, pl.sy.n);
+}
+
+// image -> out, using the spectrum in ws.h.  partials (nullable): one double per x-inverse block.
+template <class L> int conv_apply(L& l, const ConvPlan& pl, const ConvWorkspace& ws, const float* img, float* out, double* partials)
+{
+    const long long kxc = pl.kxc();
+    XParams xp = {};
+    xp.rin = img; xp.cout = ws.u1; xp.tw = ws.tw_x; xp.twist = ws.twist_x;
+    xp.X = pl.dims[0]; xp.n_rows = pl.dims[1] * pl.dims[2]; xp.left = pl.left[0]; xp.zero_ext = 0;
+    int err = l.launch_x(false, pl.sx, xp);
+    if (err) return err;
+
+    StridedParams sp = {};
+    sp.in = ws.u1; sp.out = ws.u2; sp.tw = ws.tw_y; sp.kx_count = (int)kxc;
+    sp.n_src = pl.dims[1]; sp.left = pl.left[1]; sp.zero_ext = 0;
+    sp.in_estride = kxc; sp.in_ostride = (long long)pl.dims[1] * kxc;
+    sp.out_estride = kxc; sp.out_ostride = (long long)pl.sy.n * kxc;
+    sp.scale = 1.0f;
+    err = l.launch_strided(false, pl.sy, sp, pl.dims[2]);
+    if (err) return err;
+
+    ZFusedParams zp = {};
+    zp.u = ws.u2; zp.h = ws.h; zp.tw = ws.tw_z; zp.kx_count = (int)kxc;
+    zp.n_src = pl.dims[2]; zp.left = pl.left[2]; zp.crop0 = pl.crop0[2];
+    zp.estride = (long long)pl.sy.n * kxc; zp.ostride = kxc; zp.h_estride = (long long)pl.sy.n * kxc;
+    err = l.launch_zfused(pl.sz, zp, pl.sy.n);
+    if (err) return err;
+
+    StridedParams ip = {};
+    ip.in = ws.u2; ip.out = ws.u1; ip.tw = ws.tw_y; ip.kx_count = (int)kxc;
+    ip.crop0 = pl.crop0[1]; ip.n_out = pl.dims[1];
+    ip.in_estride = kxc; ip.in_ostride = (long long)pl.sy.n * kxc;
+    ip.out_estride = kxc; ip.out_ostride = (long long)pl.dims[1] * kxc;
+    ip.scale = 1.0f;
+    err = l.launch_strided(true, pl.sy, ip, pl.dims[2]);
+    if (err) return err;
+
+    XParams ix = {};
+    ix.cin = ws.u1; ix.rout = out; ix.tw = ws.tw_x; ix.twist = ws.twist_x; ix.partials = partials;
+    ix.X = pl.dims[0]; ix.n_rows = pl.dims[1] * pl.dims[2]; ix.crop0 = pl.crop0[0];
+    return l.launch_x(true, pl.sx, ix);
+}
+
+}  // namespace mvsim

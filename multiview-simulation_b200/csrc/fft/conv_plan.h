@@ -1,0 +1,109 @@
+// Host-side planning of the FFT convolution: padded sizes, the (A, B) split of every line length,
+// margins and crop offsets.  Pure C++ (shared by the CUDA driver and the CPU emulation tests).
+//
+// Replaces the size/padding logic of imglib2-algorithm FFTConvolution.convolve()
+// (FFTMethods.dimensionsRealToComplexFast + paddingIntervalCentered; reference call site
+// S/SimulateMultiViewDataset.java:257-261).  The result inside the original interval does not
+// depend on the padded size as long as it is >= dim + kdim - 1, so the
+// sizes here are chosen for the GPU: products A*B with A, B <= 40 held in registers.
+#pragma once
+#include <stdint.h>
+
+namespace mvsim {
+
+struct FftSize { int n, a, b; };
+
+// X(n, a, b): supported complex line lengths, ascending, gaps <= 12.5 %.
+#define MVSIM_FFT_SIZES_SMALL(X) \
+    X(16, 4, 4) X(20, 4, 5) X(24, 4, 6) X(32, 4, 8) X(40, 5, 8) X(48, 6, 8) X(64, 8, 8) X(72, 8, 9) \
+    X(80, 8, 10) X(96, 8, 12)
+#define MVSIM_FFT_SIZES_G1(X) \
+    X(108, 9, 12) X(128, 8, 16) X(144, 12, 12) X(160, 10, 16) X(192, 12, 16) X(216, 12, 18) X(240, 15, 16) \
+    X(256, 16, 16) X(288, 16, 18)
+#define MVSIM_FFT_SIZES_G2(X) \
+    X(320, 16, 20) X(360, 18, 20) X(384, 16, 24) X(432, 18, 24) X(480, 20, 24) X(512, 16, 32) X(576, 24, 24)
+#define MVSIM_FFT_SIZES_G3(X) \
+    X(640, 20, 32) X(720, 24, 30) X(768, 24, 32) X(864, 27, 32) X(960, 30, 32) X(1024, 32, 32)
+#define MVSIM_FFT_SIZES_G4(X) \
+    X(1152, 32, 36) X(1280, 32, 40) X(1440, 36, 40) X(1600, 40, 40)
+
+#ifdef MVSIM_EMU_SMALL_ONLY
+#define MVSIM_FFT_SIZES(X) MVSIM_FFT_SIZES_SMALL(X)
+#else
+#define MVSIM_FFT_SIZES(X) \
+    MVSIM_FFT_SIZES_SMALL(X) MVSIM_FFT_SIZES_G1(X) MVSIM_FFT_SIZES_G2(X) MVSIM_FFT_SIZES_G3(X) MVSIM_FFT_SIZES_G4(X)
+#endif
+
+inline const FftSize* fft_size_table(int* count)
+{
+#define MVSIM_X(n, a, b) { n, a, b },
+    static const FftSize t[] = { MVSIM_FFT_SIZES(MVSIM_X) };
+#undef MVSIM_X
+    *count = (int)(sizeof(t) / sizeof(t[0]));
+    return t;
+}
+
+// smallest supported size >= min_n, or nullptr
+inline const FftSize* pick_fft_size(int64_t min_n)
+{
+    int c;
+    const FftSize* t = fft_size_table(&c);
+    for (int i = 0; i < c; ++i)
+        if (t[i].n >= min_n) return &t[i];
+    return nullptr;
+}
+
+struct ConvPlan {
+    int dims[3], kdims[3];
+    FftSize sx, sy, sz;     // sx.n = complex length of the folded x rows (padded real length 2*sx.n)
+    int left[3];            // padded index p holds source index p - left   (left = kdim - 1 - kdim/2)
+    int crop0[3];           // output voxel o lives at padded index o + crop0 (crop0 = kdim - 1)
+    double scale;           // 1 / (sx.n * sy.n * sz.n)
+
+    int64_t kxc() const { return sx.n; }
+    int64_t u1_elems() const { return (int64_t)dims[2] * dims[1] * sx.n; }          // [Z][Y][KXc]
+    int64_t u2_elems() const { return (int64_t)dims[2] * sy.n * sx.n; }             // [Z][Ny][KXc]
+    int64_t h_elems() const { return (int64_t)sz.n * sy.n * sx.n; }                 // [Nz][Ny][KXc]
+    int64_t p1_elems() const { return (int64_t)kdims[2] * kdims[1] * sx.n; }        // [KZ][KY][KXc]
+    int64_t p2_elems() const { return (int64_t)kdims[2] * sy.n * sx.n; }            // [KZ][Ny][KXc]
+};
+
+// 0 ok, 1 invalid dims, 5 unsupported (too large for the size table)
+inline int make_conv_plan(const int64_t dims[3], const int64_t kdims[3], ConvPlan* p)
+{
+    for (int d = 0; d < 3; ++d) {
+        if (dims[d] < 1 || kdims[d] < 1 || dims[d] > (1 << 30) || kdims[d] > (1 << 30)) return 1;
+        p->dims[d] = (int)dims[d];
+        p->kdims[d] = (int)kdims[d];
+        p->left[d] = (int)(kdims[d] - 1 - kdims[d] / 2);
+        p->crop0[d] = (int)(kdims[d] - 1);
+    }
+    const FftSize* sx = pick_fft_size((dims[0] + kdims[0] - 1 + 1) / 2);
+    const FftSize* sy = pick_fft_size(dims[1] + kdims[1] - 1);
+    const FftSize* sz = pick_fft_size(dims[2] + kdims[2] - 1);
+    if (!sx || !sy || !sz) return 5;
+    p->sx = *sx; p->sy = *sy; p->sz = *sz;
+    p->scale = 1.0 / ((double)sx->n * (double)sy->n * (double)sz->n);
+    return 0;
+}
+
+// exp(-2 pi i m / n), m < n  (double-built, float-stored) -- table for the inter-level twiddles
+inline void fill_twiddles(int n, float* re_im /* 2n floats */)
+{
+    for (int m = 0; m < n; ++m) {
+        const double a = -2.0 * 3.14159265358979323846 * (double)m / (double)n;
+        re_im[2 * m] = (float)__builtin_cos(a);
+        re_im[2 * m + 1] = (float)__builtin_sin(a);
+    }
+}
+// exp(-i pi m / (2n)), m < n -- the twist of the folded real transform of padded length 2n
+inline void fill_twist(int n, float* re_im)
+{
+    for (int m = 0; m < n; ++m) {
+        const double a = -3.14159265358979323846 * (double)m / (2.0 * (double)n);
+        re_im[2 * m] = (float)__builtin_cos(a);
+        re_im[2 * m + 1] = (float)__builtin_sin(a);
+    }
+}
+
+}  // namespace mvsim

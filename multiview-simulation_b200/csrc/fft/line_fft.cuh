@@ -1,0 +1,374 @@
+// Two-level (N = A*B) line FFTs held in registers, one shared-memory exchange per direction.
+//
+// Replaces the 1-D float32 FFT lines that imglib2-algorithm fft2.FFTConvolution hands to Mines JTK
+// (reference call site S/SimulateMultiViewDataset.java:257-261; S = src/main/java/net/preibisch/simulation).
+//
+// Decomposition (n = n1*B + n2, k = k1 + A*k2):
+//   forward : thread n2 (<B) runs an A-point FFT over n1, multiplies by W_N^{n2 k1}, writes smem[k1][n2];
+//             thread k1 (<A) runs a B-point FFT over n2 and ends up holding X[k1 + A*k2], k2 = 0..B-1.
+//   inverse : the mirror image: thread k1 starts from X[k1 + A*k2] in registers, B-point inverse,
+//             twiddle, smem[k1][n2]; thread n2 runs the A-point inverse and holds x[n1*B + n2].
+// so a forward transform followed by an inverse one (the fused z pass) never needs a reordering.
+//
+// Shared-memory layout: element (k1, n2) of a line lives at base + (k1*BP + n2)*LS with BP = B|1 (odd
+// pitch => both the row-wise writes and the column-wise reads are bank-conflict free for 8-byte
+// accesses), LS = lane stride (T interleaved lines for the strided passes, 1 for the x passes).
+//
+// Every kernel is written as a sequence of `phase<k>` functions separated by block barriers.  The
+// phases are __host__ __device__: tests/emu runs the very same code on the CPU, thread by thread.
+#pragma once
+#include "fft_defs.cuh"
+#include "regfft_gen.cuh"
+
+namespace mvsim {
+
+template <int A_, int B_> struct LineShape {
+    static constexpr int A = A_, B = B_;
+    static constexpr int N = A * B;
+    static constexpr int P = A > B ? A : B;   // threads per line
+    static constexpr int BP = B | 1;          // odd pitch
+    static constexpr int ELEMS = A * BP;      // float2 per line in shared memory
+};
+
+// ---- forward halves ---------------------------------------------------------------------------
+// thread p < B.  x[n1] = line[p + n1*B] on entry.
+template <int A, int B> MVSIM_HD void fwd_first(int p, float2 (&x)[A], float2* sm, int base, int ls, const float2* __restrict__ tw)
+{
+    constexpr int BP = B | 1;
+    RegFFT<A, -1>::run(x);
+    MVSIM_UNROLL
+    for (int k1 = 0; k1 < A; ++k1) {
+        const float2 v = k1 == 0 ? x[0] : cmul(x[k1], tw[k1 * p]);
+        sm[base + (k1 * BP + p) * ls] = v;
+    }
+}
+// thread p < A.  On exit y[k2] = X[p + A*k2].
+template <int A, int B> MVSIM_HD void fwd_second(int p, float2 (&y)[B], const float2* sm, int base, int ls)
+{
+    constexpr int BP = B | 1;
+    MVSIM_UNROLL
+    for (int n2 = 0; n2 < B; ++n2) y[n2] = sm[base + (p * BP + n2) * ls];
+    RegFFT<B, -1>::run(y);
+}
+
+// ---- inverse halves (unscaled) ----------------------------------------------------------------
+// thread p < A.  y[k2] = X[p + A*k2] on entry.
+template <int A, int B> MVSIM_HD void inv_first(int p, float2 (&y)[B], float2* sm, int base, int ls, const float2* __restrict__ tw)
+{
+    constexpr int BP = B | 1;
+    RegFFT<B, 1>::run(y);
+    MVSIM_UNROLL
+    for (int n2 = 0; n2 < B; ++n2) {
+        const float2 v = n2 == 0 ? y[0] : cmulc(y[n2], tw[n2 * p]);
+        sm[base + (p * BP + n2) * ls] = v;
+    }
+}
+// thread p < B.  On exit x[n1] = line[p + n1*B].
+template <int A, int B> MVSIM_HD void inv_second(int p, float2 (&x)[A], const float2* sm, int base, int ls)
+{
+    constexpr int BP = B | 1;
+    MVSIM_UNROLL
+    for (int k1 = 0; k1 < A; ++k1) x[k1] = sm[base + (k1 * BP + p) * ls];
+    RegFFT<A, 1>::run(x);
+}
+
+// ==============================================================================================
+// Strided forward pass (y pass, and the z pass of the PSF spectrum).  A CTA owns T neighbouring
+// kx columns (contiguous in memory) of one `outer` slab and transforms them along the strided axis.
+// The source line (length n_src) is extended on the fly: mirror-single (image; imglib2
+// Views.extendMirrorSingle) or zero (kernel; Views.extendValue(kernel, 0)); `left` = kdim-1-kdim/2.
+// ==============================================================================================
+struct StridedParams {
+    const float2* in;
+    float2* out;
+    const float2* tw;       // exp(-2 pi i m / N), m < N
+    int kx_count;           // complex columns per row
+    int n_src;              // valid source samples along the line
+    int left;               // padded index p holds source p - left
+    int zero_ext;           // 0 mirror-single, 1 zero extension
+    int crop0, n_out;       // inverse: store padded indices [crop0, crop0 + n_out)
+    long long in_estride, in_ostride, out_estride, out_ostride;   // in float2 units
+    float scale;            // forward: multiplied into the output (folds 1/N and PSF scaling)
+};
+
+struct NoState {};
+
+template <int A_, int B_, int T_> struct StridedFwd : LineShape<A_, B_> {
+    using S = LineShape<A_, B_>;
+    static constexpr int A = A_, B = B_, T = T_;
+    static constexpr int THREADS = T * S::P;
+    static constexpr int SMEM_BYTES = S::ELEMS * T * (int)sizeof(float2);
+    static constexpr int NPH = 2;
+    using Params = StridedParams;
+    using State = NoState;
+
+    template <int PH> static MVSIM_HD void phase(const Params& q, int bx, int by, int tid, float2* sm, State&)
+    {
+        const int lane = tid % T, p = tid / T;
+        const int kx = bx * T + lane;
+        const bool active = kx < q.kx_count;
+        if (PH == 0) {
+            if (p < B && active) {
+                float2 x[A];
+                const float2* src = q.in + by * q.in_ostride + kx;
+                MVSIM_UNROLL
+                for (int n1 = 0; n1 < A; ++n1) {
+                    const int n = p + n1 * B - q.left;
+                    if (q.zero_ext) {
+                        x[n1] = (unsigned)n < (unsigned)q.n_src ? src[n * q.in_estride] : make_float2(0.f, 0.f);
+                    } else {
+                        x[n1] = src[mirror_single(n, q.n_src) * q.in_estride];
+                    }
+                }
+                fwd_first<A, B>(p, x, sm, lane, T, q.tw);
+            }
+        } else {
+            if (p < A && active) {
+                float2 y[B];
+                fwd_second<A, B>(p, y, sm, lane, T);
+                float2* dst = q.out + by * q.out_ostride + kx;
+                MVSIM_UNROLL
+                for (int k2 = 0; k2 < B; ++k2)
+                    dst[(p + A * k2) * q.out_estride] = make_float2(y[k2].x * q.scale, y[k2].y * q.scale);
+            }
+        }
+    }
+};
+
+// Strided inverse pass (y inverse): natural-order spectrum in, padded indices [crop0, crop0+n_out) out.
+template <int A_, int B_, int T_> struct StridedInv : LineShape<A_, B_> {
+    using S = LineShape<A_, B_>;
+    static constexpr int A = A_, B = B_, T = T_;
+    static constexpr int THREADS = T * S::P;
+    static constexpr int SMEM_BYTES = S::ELEMS * T * (int)sizeof(float2);
+    static constexpr int NPH = 2;
+    using Params = StridedParams;
+    using State = NoState;
+
+    template <int PH> static MVSIM_HD void phase(const Params& q, int bx, int by, int tid, float2* sm, State&)
+    {
+        const int lane = tid % T, p = tid / T;
+        const int kx = bx * T + lane;
+        const bool active = kx < q.kx_count;
+        if (PH == 0) {
+            if (p < A && active) {
+                float2 y[B];
+                const float2* src = q.in + by * q.in_ostride + kx;
+                MVSIM_UNROLL
+                for (int k2 = 0; k2 < B; ++k2) y[k2] = src[(p + A * k2) * q.in_estride];
+                inv_first<A, B>(p, y, sm, lane, T, q.tw);
+            }
+        } else {
+            if (p < B && active) {
+                float2 x[A];
+                inv_second<A, B>(p, x, sm, lane, T);
+                float2* dst = q.out + by * q.out_ostride + kx;
+                MVSIM_UNROLL
+                for (int n1 = 0; n1 < A; ++n1) {
+                    const int o = p + n1 * B - q.crop0;
+                    if ((unsigned)o < (unsigned)q.n_out) dst[o * q.out_estride] = x[n1];
+                }
+            }
+        }
+    }
+};
+
+// ==============================================================================================
+// Fused z pass: mirror-extended forward FFT along z, multiply by the PSF spectrum H (the complex
+// multiply of FFTConvolution.multiplyComplex), inverse FFT along z, store only the cropped range.
+// In place: a CTA reads its T lines completely before it writes them.
+// ==============================================================================================
+struct ZFusedParams {
+    float2* u;              // [Z][Ny][KXc] in place
+    const float2* h;        // [Nz][Ny][KXc], already scaled by 1/(N*Ny*Nz)
+    const float2* tw;
+    int kx_count, n_src, left, crop0;
+    long long estride;      // z stride of u (= Ny*KXc)
+    long long ostride;      // ky stride (= KXc), same for u and h
+    long long h_estride;    // kz stride of h (= Ny*KXc)
+};
+
+template <int B> struct RegState { float2 y[B]; };
+
+template <int A_, int B_, int T_> struct ZFused : LineShape<A_, B_> {
+    using S = LineShape<A_, B_>;
+    static constexpr int A = A_, B = B_, T = T_;
+    static constexpr int THREADS = T * S::P;
+    static constexpr int SMEM_BYTES = S::ELEMS * T * (int)sizeof(float2);
+    static constexpr int NPH = 4;
+    using Params = ZFusedParams;
+    using State = RegState<B>;
+
+    template <int PH> static MVSIM_HD void phase(const Params& q, int bx, int by, int tid, float2* sm, State& st)
+    {
+        const int lane = tid % T, p = tid / T;
+        const int kx = bx * T + lane;
+        const bool active = kx < q.kx_count;
+        if (PH == 0) {
+            if (p < B && active) {
+                float2 x[A];
+                const float2* src = q.u + by * q.ostride + kx;
+                MVSIM_UNROLL
+                for (int n1 = 0; n1 < A; ++n1)
+                    x[n1] = src[mirror_single(p + n1 * B - q.left, q.n_src) * q.estride];
+                fwd_first<A, B>(p, x, sm, lane, T, q.tw);
+            }
+        } else if (PH == 1) {
+            if (p < A && active) {
+                fwd_second<A, B>(p, st.y, sm, lane, T);
+                const float2* hs = q.h + by * q.ostride + kx;
+                MVSIM_UNROLL
+                for (int k2 = 0; k2 < B; ++k2) st.y[k2] = cmul(st.y[k2], hs[(p + A * k2) * q.h_estride]);
+            }
+        } else if (PH == 2) {
+            if (p < A && active) inv_first<A, B>(p, st.y, sm, lane, T, q.tw);
+        } else {
+            if (p < B && active) {
+                float2 x[A];
+                inv_second<A, B>(p, x, sm, lane, T);
+                float2* dst = q.u + by * q.ostride + kx;
+                MVSIM_UNROLL
+                for (int n1 = 0; n1 < A; ++n1) {
+                    const int o = p + n1 * B - q.crop0;
+                    if ((unsigned)o < (unsigned)q.n_src) dst[o * q.estride] = x[n1];
+                }
+            }
+        }
+    }
+};
+
+// ==============================================================================================
+// x passes.  A real row of padded length 2N is transformed with ONE N-point complex FFT:
+//   z[m] = (r[m] - i r[m+N]) * exp(-i pi m / 2N)      (fold + twist)
+// gives the even bins of the odd-frequency DFT  X[k] = sum_n r[n] exp(-2 pi i (k+1/2) n / 2N),
+// which diagonalises negacyclic convolution.  The padded length is >= dim + kdim - 1, so no
+// wrapped term reaches the cropped output and the result equals the reference's cyclic
+// FFTConvolution inside the original interval -- with exactly N complex bins per row (no Nyquist
+// column, no real-to-complex post-processing pass).
+// ==============================================================================================
+struct XParams {
+    const float* rin;       // forward: real rows [n_rows][X]
+    float* rout;            // inverse: real rows [n_rows][X]
+    const float2* cin;      // inverse: spectrum rows [n_rows][N]
+    float2* cout;           // forward: spectrum rows [n_rows][N]
+    const float2* tw;       // exp(-2 pi i m / N)
+    const float2* twist;    // exp(-i pi m / 2N)
+    double* partials;       // inverse: per-block sums of the stored voxels (may be null)
+    int X, n_rows, left, zero_ext, crop0;
+};
+
+template <int A_, int B_, int R_> struct XFwd : LineShape<A_, B_> {
+    using S = LineShape<A_, B_>;
+    static constexpr int A = A_, B = B_, R = R_;
+    static constexpr int THREADS = R * S::P;
+    static constexpr int SMEM_BYTES = S::ELEMS * R * (int)sizeof(float2);
+    static constexpr int NPH = 2;
+    using Params = XParams;
+    using State = NoState;
+
+    static MVSIM_HD float fetch(const float* row, int i, int n, int zero_ext)
+    {
+        if (zero_ext) return (unsigned)i < (unsigned)n ? row[i] : 0.f;
+        return row[mirror_single(i, n)];
+    }
+
+    template <int PH> static MVSIM_HD void phase(const Params& q, int bx, int, int tid, float2* sm, State&)
+    {
+        constexpr int N = S::N;
+        const int r = tid / S::P, p = tid % S::P;
+        const long long row = (long long)bx * R + r;
+        const bool active = row < q.n_rows;
+        if (PH == 0) {
+            if (p < B && active) {
+                float2 x[A];
+                const float* src = q.rin + row * q.X;
+                MVSIM_UNROLL
+                for (int n1 = 0; n1 < A; ++n1) {
+                    const int m = p + n1 * B;
+                    const float a = fetch(src, m - q.left, q.X, q.zero_ext);
+                    const float b = fetch(src, m + N - q.left, q.X, q.zero_ext);
+                    const float2 t = q.twist[m];
+                    x[n1] = make_float2(a * t.x + b * t.y, a * t.y - b * t.x);   // (a - i b) * t
+                }
+                fwd_first<A, B>(p, x, sm, r * S::ELEMS, 1, q.tw);
+            }
+        } else {
+            if (p < A && active) {
+                float2 y[B];
+                fwd_second<A, B>(p, y, sm, r * S::ELEMS, 1);
+                float2* dst = q.cout + row * N;
+                MVSIM_UNROLL
+                for (int k2 = 0; k2 < B; ++k2) dst[p + A * k2] = y[k2];
+            }
+        }
+    }
+};
+
+template <int A_, int B_, int R_> struct XInv : LineShape<A_, B_> {
+    using S = LineShape<A_, B_>;
+    static constexpr int A = A_, B = B_, R = R_;
+    static constexpr int THREADS = R * S::P;
+    // exchange area + per-thread float partials + 32 double partials
+    static constexpr int EXCH = S::ELEMS * R;
+    static constexpr int SMEM_BYTES = EXCH * (int)sizeof(float2) + THREADS * (int)sizeof(float) + 32 * (int)sizeof(double) + 8;
+    static constexpr int NPH = 4;
+    using Params = XParams;
+    using State = NoState;
+
+    static MVSIM_HD float* psum(float2* sm) { return reinterpret_cast<float*>(sm + EXCH); }
+    static MVSIM_HD double* dsum(float2* sm)
+    {
+        // 8-byte aligned: EXCH float2 (8 B each) then THREADS floats rounded up to an even count
+        return reinterpret_cast<double*>(sm + EXCH + (THREADS + 1) / 2);
+    }
+
+    template <int PH> static MVSIM_HD void phase(const Params& q, int bx, int, int tid, float2* sm, State&)
+    {
+        constexpr int N = S::N;
+        const int r = tid / S::P, p = tid % S::P;
+        const long long row = (long long)bx * R + r;
+        const bool active = row < q.n_rows;
+        if (PH == 0) {
+            if (p < A && active) {
+                float2 y[B];
+                const float2* src = q.cin + row * N;
+                MVSIM_UNROLL
+                for (int k2 = 0; k2 < B; ++k2) y[k2] = src[p + A * k2];
+                inv_first<A, B>(p, y, sm, r * S::ELEMS, 1, q.tw);
+            }
+        } else if (PH == 1) {
+            float acc = 0.f;
+            if (p < B && active) {
+                float2 x[A];
+                inv_second<A, B>(p, x, sm, r * S::ELEMS, 1);
+                float* dst = q.rout + row * q.X;
+                MVSIM_UNROLL
+                for (int n1 = 0; n1 < A; ++n1) {
+                    const int m = p + n1 * B;
+                    const float2 t = q.twist[m];
+                    // x * conj(t): real part -> padded m, minus imaginary part -> padded m + N
+                    const float re = x[n1].x * t.x + x[n1].y * t.y;
+                    const float mi = x[n1].x * t.y - x[n1].y * t.x;
+                    const int o1 = m - q.crop0, o2 = m + N - q.crop0;
+                    if ((unsigned)o1 < (unsigned)q.X) { dst[o1] = re; acc += re; }
+                    if ((unsigned)o2 < (unsigned)q.X) { dst[o2] = mi; acc += mi; }
+                }
+            }
+            if (q.partials) psum(sm)[tid] = acc;
+        } else if (PH == 2) {
+            if (q.partials && tid < 32) {
+                double s = 0.0;
+                for (int j = tid; j < THREADS; j += 32) s += (double)psum(sm)[j];
+                dsum(sm)[tid] = s;
+            }
+        } else {
+            if (q.partials && tid == 0) {
+                double s = 0.0;
+                for (int j = 0; j < 32; ++j) s += dsum(sm)[j];
+                q.partials[bx] = s;
+            }
+        }
+    }
+};
+
+}  // namespace mvsim
