@@ -1,0 +1,358 @@
+#!/usr/bin/env python3
+"""Benchmark of the per-view acquisition pipeline (BASELINE.json: simulated voxels/s and views/s,
+achieved HBM GB/s vs peak).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3|cfg1|small]
+
+One "step" = one pass of the hot path over one batch: the 6 views of BASELINE config 3
+(1024x1024x512 float32 ground truth, 6 views 60 deg apart (+15), one 128^3 PSF per view, delta 0.01,
+every 5th slice, Poisson SNR 25).  With N > 1 (torchrun, one rank per GPU) every rank simulates its
+own batch of 6 views (weak scaling, no data-path collective; views are independent units).
+
+`value`  : voxels/s, inputs resident in HBM, CUDA-event timed on the stream the kernels run on.
+`e2e`    : same metric through the host-buffer C-ABI call (mvsim_simulate_views) from pinned host
+           memory, ground truth H2D + results D2H inside the timed region.
+`roofline`: the dominant kernel (fused z pass) timed live with CUDA events inside the timed region.
+`cpu_baseline`: the CPU oracle (restatement of the reference; no JVM in this image) on a bounded sample.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (shape_zyx, kshape_zyx, sigma_zyx, degrees, inc, snr)
+    "cfg3": ((512, 1024, 1024), (128, 128, 128), (17.5, 5.5, 5.0), [15, 75, 135, 195, 255, 315], 5, 25.0),
+    "cfg1": ((256, 512, 512), (51, 51, 51), (7.0, 2.2, 2.0), [15, 105, 195, 285], 3, 25.0),
+    "small": ((64, 128, 128), (16, 16, 16), (3.0, 1.2, 1.1), [15, 75, 135, 195, 255, 315], 5, 25.0),
+}
+CPU_SAMPLE = {"cfg3": ((128, 256, 256), (32, 32, 32), (4.4, 1.4, 1.25)), "cfg1": ((64, 128, 128), (25, 25, 25), (3.5, 1.1, 1.0)),
+              "small": ((32, 64, 64), (8, 8, 8), (1.5, 0.8, 0.8))}
+
+
+def _periodic_sphere_tile(t, n_spheres, rng):
+    """t^3 tile of max-composited spheres, radius U{1..20}/2 px, intensity U(0,1), periodic wrap."""
+    tile = np.zeros((t, t, t), dtype=np.float32)
+    ax = np.arange(t, dtype=np.float32)
+    for _ in range(n_spheres):
+        c = rng.uniform(0, t, 3)
+        r = rng.integers(1, 21) / 2.0
+        v = np.float32(rng.random())
+        d = [np.minimum(np.abs(ax - c[i]), t - np.abs(ax - c[i])) ** 2 for i in range(3)]
+        m = (d[0][:, None, None] + d[1][None, :, None] + d[2][None, None, :]) <= r * r
+        tile[m] = np.maximum(tile[m], v)
+    return tile
+
+
+def make_ground_truth(shape, seed=464232194):
+    """Sphere-phantom statistics of the reference's simulate() (S/SimulateMultiViewDataset.java:366-522):
+    a centred body with semi-axes 0.337*dim (16 % of the volume, background exactly 0) filled with small
+    max-composited random spheres of intensity U(0,1).  Own generator: one periodic 64^3 tile repeated
+    over the volume (cheap for 0.5 G voxels), masked by the body."""
+    z, y, x = shape
+    t = 64
+    tile = _periodic_sphere_tile(t, 80, np.random.default_rng(seed))
+    reps = (math.ceil(z / t), math.ceil(y / t), math.ceil(x / t))
+    vol = np.tile(tile, reps)[:z, :y, :x]
+    zz = ((np.arange(z, dtype=np.float32) - (z - 1) / 2.0) / (0.337 * z)) ** 2
+    yy = ((np.arange(y, dtype=np.float32) - (y - 1) / 2.0) / (0.337 * y)) ** 2
+    xx = ((np.arange(x, dtype=np.float32) - (x - 1) / 2.0) / (0.337 * x)) ** 2
+    out = np.empty(shape, dtype=np.float32)
+    for k in range(z):          # slab-wise to keep the temporary small
+        out[k] = vol[k] * ((zz[k] + yy[:, None] + xx[None, :]) <= 1.0)
+    return out
+
+
+def make_psfs(kshape, sigma, n):
+    from helpers import gaussian_psf
+    return [gaussian_psf(kshape, (sigma[0] * (1 + 0.03 * v), sigma[1] * (1 - 0.02 * v), sigma[2] * (1 + 0.01 * v)), threshold=1e-3)
+            for v in range(n)]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [c.strip() for c in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); power.append(float(f[2]))
+            except ValueError:
+                continue
+            for nme, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_reference_sample(workload, steps=1, warmup=0):
+    """The reference's loop body on the host cores: CPU oracle (C restatement; kind 'port'), shaped like
+    the reference -- single-threaded stages, FFT lines on all cores, O(lambda) Poisson loop."""
+    from helpers import gaussian_psf
+    from oracle import oracle as orc
+    shape, kshape, sigma = CPU_SAMPLE[workload]
+    _, _, _, degrees, inc, snr = WORKLOADS[workload]
+    gt = make_ground_truth(shape)
+    psf = gaussian_psf(kshape, sigma, threshold=1e-3)
+    cores = orc.lib().orc_max_threads()
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        _, _, st = orc.simulate_view(gt, psf, degrees=degrees[i % len(degrees)], inc=inc, snr=snr, use_fft=True,
+                                     fft_threads=cores, stage_threads=1)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append((dt, st))
+    dt = float(np.mean([t for t, _ in times]))
+    stages = np.mean([s for _, s in times], axis=0)
+    vox = int(np.prod(shape))
+    return {"value": vox / dt, "unit": "voxels/s", "cores": cores, "kind": "port",
+            "sample": (f"1 view of a {shape[2]}x{shape[1]}x{shape[0]} sub-volume, PSF {kshape[2]}^3, inc {inc}, SNR {snr}: C oracle of the reference "
+                       f"(no JVM in the image), stages on 1 thread, FFT lines on {cores} threads, reference O(lambda) Poisson loop"),
+            "seconds_per_view": dt, "views_per_s": 1.0 / dt,
+            "stage_seconds": dict(zip(["rotate", "attenuate", "convolve", "adjust", "extract_poisson"], [float(s) for s in stages]))}, dt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    base, dt = cpu_reference_sample(args.workload, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+    shape, kshape, _, degrees, inc, snr = WORKLOADS[args.workload]
+    line = {"impl": "reference", "metric": "simulated voxels/s (per-view acquisition pipeline)", "value": base["value"], "unit": "voxels/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.workload), "views_per_s": base["views_per_s"], "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(name):
+    shape, kshape, _, degrees, inc, snr = WORKLOADS[name]
+    return {"workload": f"BASELINE config 3 (configs[2])" if name == "cfg3" else name,
+            "volume_xyz": [shape[2], shape[1], shape[0]], "psf_xyz": [kshape[2], kshape[1], kshape[0]],
+            "views_per_gpu_per_step": len(degrees), "degrees": degrees, "axis": 0, "delta": 0.01, "inc": inc, "snr": snr,
+            "l2": "inputs exceed L2 (2.1 GB ground truth, 2.4-3.4 GB spectra per pass vs 126 MB L2)",
+            "parallelism": "view-sharded, one batch of views per GPU, no collective"}
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import mvsim_b200 as mv
+    from mvsim_b200._lib import check
+    import ctypes as C
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the CUDA path is the only implementation (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    shape, kshape, sigma, degrees, inc, snr = WORKLOADS[args.workload]
+    degrees = [d + 7 * rank for d in degrees]          # every rank owns different views
+    nv = len(degrees)
+    vox_per_view = int(np.prod(shape))
+    oshape = ((shape[0] - 1) // inc + 1, shape[1], shape[2])
+
+    stream = torch.cuda.current_stream()
+    ctx = mv.Context(local_rank, cuda_stream=stream.cuda_stream)
+    lib = ctx._lib
+
+    # ---- inputs: pinned host buffers (e2e) and device-resident volumes (value) ----------------------
+    gt_pin = mv.PinnedBuffer(shape)
+    gt_pin.array[...] = make_ground_truth(shape)
+    psf_raw = make_psfs(kshape, sigma, nv)
+    psf_pin = [mv.PinnedBuffer(kshape) for _ in range(nv)]
+    out_pin = [mv.PinnedBuffer(oshape) for _ in range(nv)]
+    d_gt = mv.DeviceVolume(ctx, shape, gt_pin.array)
+    d_psf = [mv.DeviceVolume(ctx, kshape, p) for p in psf_raw]
+    d_out = [mv.DeviceVolume(ctx, oshape) for _ in range(nv)]
+    params = [mv.make_view_params(shape, kshape, 0, degrees[v], 0.01, 0.0001, 1.0, inc, snr, seed=464232194, stream=rank * nv + v)
+              for v in range(nv)]
+
+    def step_device():
+        for v in range(nv):
+            check(lib.mvsim_dev_simulate_view(ctx.h, C.byref(params[v]), d_gt.h, d_psf[v].h, d_out[v].h), ctx.h)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if dist is None:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident arm -------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    ctx.profile(True)
+    launches0 = ctx.kernel_launches
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    e1.record(stream)
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clk = clocks.stop() if clocks else None
+    launches = ctx.kernel_launches - launches0
+    stage = ctx.stage_times()
+    ctx.profile(False)
+    if dist is not None:
+        t = torch.tensor([launches], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t)
+        launches = int(t.item())
+    ms_step = ms_total / args.steps
+    value = world * nv * vox_per_view / (ms_step * 1e-3)
+
+    # ---- end-to-end arm: host buffers through the C ABI ------------------------------------------------
+    S = mv.SimulateMultiViewDataset
+    e2e_steps = max(1, min(args.steps, 3))
+
+    def step_e2e():
+        for v in range(nv):
+            psf_pin[v].array[...] = psf_raw[v]          # the call normalises the PSF in place
+        S.simulateViews(gt_pin.array, [p.array for p in psf_pin], degrees, inc=inc, poissonSNR=snr, rnd=464232194, ctx=ctx,
+                        outs=[o.array for o in out_pin], first_stream=rank * nv)
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(e2e_steps):
+        step_e2e()
+    e1.record(stream)
+    barrier()
+    wall = (time.perf_counter() - t0) / e2e_steps
+    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1) / e2e_steps, wall * 1e3))
+    h2d = 4 * vox_per_view + nv * 4 * int(np.prod(kshape))
+    d2h = nv * 4 * (int(np.prod(oshape)) + int(np.prod(kshape)))
+    result_checksum = float(out_pin[0].array[::7, ::31, ::29].astype(np.float64).mean())
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ------------------------------------------------------------------
+    nfft = (C.c_int64 * 3)()
+    check(lib.mvsim_conv_padded_dims(mv._lib.dims3(shape), mv._lib.dims3(kshape), nfft))
+    kxc, ny, nz = nfft[0] // 2, nfft[1], nfft[2]
+    z_ms, z_n = stage["fft_zfused"]
+    bytes_zfused = 8 * kxc * ny * (2 * shape[0] + nz)       # pruned: read Z planes, read H (Nz), write Z planes
+    S_model = 8 * (nfft[0] // 2 + 1) * ny * nz
+    peak, peak_src = measured_peak_gbs()
+    per_launch_ms = z_ms / max(z_n, 1)
+    achieved = bytes_zfused / (per_launch_ms * 1e-3) / 1e9
+    fft_passes = {k: stage[k][0] / max(stage[k][1], 1) for k in ("fft_xfwd", "fft_yfwd", "fft_zfused", "fft_yinv", "fft_xinv")}
+    N = vox_per_view
+    O = int(np.prod(oshape))
+    b_fused_model = 8 * N + 9 * S_model + 8 * O
+    b_stage_model = 32 * N + 11 * S_model + 8 * O
+    view_ms = ms_step / nv
+    roofline = {"bound": "hbm", "kernel": "fft_zfused (z-forward * PSF spectrum * z-inverse, in place)", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "bytes_per_launch": bytes_zfused, "bytes_per_launch_model_3S": 3 * S_model, "ms_per_launch": per_launch_ms,
+                "launches_timed": z_n,
+                "whole_view": {"ms": view_ms, "B_fused_model_GB": b_fused_model / 1e9, "B_stage_model_GB": b_stage_model / 1e9,
+                               "frac_of_peak_fused_model": b_fused_model / (view_ms * 1e-3) / 1e9 / peak,
+                               "frac_of_peak_stage_model": b_stage_model / (view_ms * 1e-3) / 1e9 / peak}}
+    stages_ms = {k: {"ms_per_view": v[0] / (args.steps * nv), "launches": v[1]} for k, v in stage.items() if v[1]}
+
+    cpu, _ = cpu_reference_sample(args.workload, steps=2) if not args.no_cpu else ({"value": None, "unit": "voxels/s", "cores": 0, "kind": "port", "sample": "skipped"}, 0)
+
+    line = {"metric": "simulated voxels/s (per-view acquisition pipeline)", "value": value, "unit": "voxels/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args.workload),
+            "views_per_s": world * nv / (ms_step * 1e-3), "ms_per_view": view_ms,
+            "e2e": {"value": world * nv * vox_per_view / (e2e_ms * 1e-3), "unit": "voxels/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "views_per_s": world * nv / (e2e_ms * 1e-3),
+                    "api": "mvsim_simulate_views (pinned host buffers)", "steps": e2e_steps, "result_checksum": result_checksum},
+            "gpu_launches": launches, "roofline": roofline, "stages": stages_ms, "fft_ms_per_launch": fft_passes,
+            "fft_padded_xyz": [int(nfft[0]), int(ny), int(nz)], "cpu_baseline": cpu, "clocks": clk}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world == 1 and args.gpus > 1:
+        # plain `python bench.py --gpus N`: relaunch under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,148 @@
+/*
+ * mvsim.h -- C ABI of libmvsim.so: the B200 (sm_100a) implementation of the per-view acquisition
+ * pipeline of PreibischLab/multiview-simulation.
+ *
+ * The reference has no FFI layer; its boundary for this path is a set of public static Java
+ * methods (S = src/main/java/net/preibisch/simulation):
+ *     S/SimulateMultiViewDataset.java:80   axisRotation
+ *     S/SimulateMultiViewDataset.java:104  rotateAroundAxis
+ *     S/SimulateMultiViewDataset.java:318  attenuate3d
+ *     S/SimulateMultiViewDataset.java:253  convolve            (+ S/Tools.java:112 normImage)
+ *     S/Tools.java:143                     adjustImage
+ *     S/SimulateMultiViewDataset.java:195  extractSlices
+ *     S/SimulateMultiViewDataset.java:233  poissonProcess      (+ S/Tools.java:73)
+ * Each entry point below names the method whose body it replaces; INTEGRATION.md shows the JNI /
+ * Panama stubs a maintainer adds on the Java side.
+ *
+ * Conventions
+ *   - volumes are dense float32 in ImgLib2 ArrayImg order, x fastest: idx = x + X*(y + Y*z);
+ *     dims[3] = {X, Y, Z}.
+ *   - every function returns an mvsim_status (0 = OK); mvsim_last_error(ctx) has the text.
+ *   - host entry points (const float* / float* arguments) copy to the device, run the CUDA
+ *     kernels and copy back; they return after the result is in the caller's buffer.  Buffers from
+ *     mvsim_alloc_pinned make the copies asynchronous DMA.
+ *   - device entry points (mvsim_volume handles) keep data resident in HBM between stages and are
+ *     asynchronous on the context's stream.
+ *   - one context = one device + one stream + cached workspaces.  A context must not be used from
+ *     two threads at once; any number of contexts may exist per device (the reference's callers
+ *     run two pipelines concurrently, S/SimulateTileStitching.java:85-117).
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails with
+ *     MVSIM_ECUDA.
+ */
+#ifndef MVSIM_H
+#define MVSIM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum mvsim_status {
+    MVSIM_OK = 0,
+    MVSIM_EINVAL = 1,       /* bad argument / shape (the reference throws from imglib2) */
+    MVSIM_ENOMEM = 2,
+    MVSIM_ECUDA = 3,
+    MVSIM_ENCCL = 4,
+    MVSIM_EUNSUPPORTED = 5  /* padded size beyond the FFT size table */
+} mvsim_status;
+
+typedef struct mvsim_ctx mvsim_ctx;
+typedef struct mvsim_volume mvsim_volume;   /* device-resident float32 volume */
+
+/* Parameters of one view: loop body S/SimulateMultiViewDataset.java:570-585. */
+typedef struct mvsim_view_params {
+    int64_t dims[3];        /* ground-truth volume X, Y, Z */
+    int64_t kdims[3];       /* PSF KX, KY, KZ */
+    int32_t axis;           /* rotation axis (reference uses 0) */
+    int32_t degrees;        /* angle + angleOffset, integer degrees (:570) */
+    double delta;           /* attenuation (:573), reference 0.01 */
+    float min_value;        /* adjustImage minValue (:77), 0.0001f */
+    float target_avg;       /* adjustImage targetAverage (:78), 1 */
+    int32_t inc;            /* lightsheetSpacing (:585) */
+    float snr;              /* poissonSNR; < 0 = no noise (:211) */
+    uint64_t seed;          /* Philox key; the Java facade draws it from the caller's Random */
+    uint64_t stream;        /* Philox stream id = view id */
+    int32_t strict_reference; /* 1: attenuate loops dimension(0) steps like :345 (needs X <= Y) */
+    int32_t reserved;
+} mvsim_view_params;
+
+/* stage indices of mvsim_stage_times */
+enum {
+    MVSIM_T_H2D = 0, MVSIM_T_ROTATE, MVSIM_T_ATTENUATE, MVSIM_T_PSF, MVSIM_T_FFT_XFWD, MVSIM_T_FFT_YFWD,
+    MVSIM_T_FFT_ZFUSED, MVSIM_T_FFT_YINV, MVSIM_T_FFT_XINV, MVSIM_T_ADJUST, MVSIM_T_SAMPLE, MVSIM_T_D2H,
+    MVSIM_NSTAGES
+};
+
+/* ---- library / context ------------------------------------------------------------------- */
+int mvsim_version(void);
+int mvsim_device_count(int* count);
+int mvsim_ctx_create(int device, mvsim_ctx** ctx);
+/* same, but all work is enqueued on an existing cudaStream_t (e.g. torch's current stream) */
+int mvsim_ctx_create_on_stream(int device, void* cuda_stream, mvsim_ctx** ctx);
+int mvsim_ctx_destroy(mvsim_ctx* ctx);
+int mvsim_ctx_synchronize(mvsim_ctx* ctx);
+const char* mvsim_last_error(mvsim_ctx* ctx);      /* ctx may be NULL: last error of this thread */
+/* per-kernel CUDA-event timing: enable, run, then read accumulated milliseconds and launch counts */
+int mvsim_profile_enable(mvsim_ctx* ctx, int on);
+int mvsim_profile_reset(mvsim_ctx* ctx);
+int mvsim_stage_times(mvsim_ctx* ctx, double ms[MVSIM_NSTAGES], int64_t launches[MVSIM_NSTAGES]);
+/* number of kernels this context has launched since creation */
+int64_t mvsim_kernel_launches(mvsim_ctx* ctx);
+
+int mvsim_alloc_pinned(size_t bytes, void** ptr);
+int mvsim_free_pinned(void* ptr);
+
+/* FFT padding the convolution will use for (dims, kdims): nfft = {2*Nx/2, Ny, Nz} */
+int mvsim_conv_padded_dims(const int64_t dims[3], const int64_t kdims[3], int64_t nfft[3]);
+
+/* ---- host-buffer stage entry points ------------------------------------------------------- */
+/* axisRotation (:80-102) and its mpicbg createInverse(); pure host arithmetic, 3x4 row-major */
+int mvsim_axis_rotation(const int64_t dims[3], int axis, int degrees, double fwd[12], double inv[12]);
+/* rotateAroundAxis (:104-135) */
+int mvsim_rotate_axis(mvsim_ctx* ctx, const float* in, float* out, const int64_t dims[3], int axis, int degrees);
+/* attenuate3d (:318-364) */
+int mvsim_attenuate(mvsim_ctx* ctx, const float* in, float* out, const int64_t dims[3], double delta, int strict_reference);
+/* Tools.normImage (S/Tools.java:112-118): in place, returns the sum that was divided out */
+int mvsim_psf_normalize(mvsim_ctx* ctx, float* psf, const int64_t kdims[3], double* sum_out);
+/* convolve (:253-264): normalises psf IN PLACE like :255, then FFT convolution */
+int mvsim_convolve(mvsim_ctx* ctx, const float* img, const int64_t dims[3], float* psf, const int64_t kdims[3], float* out);
+/* Tools.adjustImage (S/Tools.java:143-159): in place, returns the correction factor */
+int mvsim_adjust(mvsim_ctx* ctx, float* img, const int64_t dims[3], float min_value, float target_avg, double* correction_out);
+/* extractSlices (:195-231): out has X*Y*((Z-1)/inc+1) floats; snr < 0 copies without noise */
+int mvsim_extract_slices(mvsim_ctx* ctx, const float* in, const int64_t dims[3], int inc, float snr,
+                         uint64_t seed, uint64_t stream, float* out);
+/* Tools.poissonProcess (S/Tools.java:73-86): in place on n floats */
+int mvsim_poisson(mvsim_ctx* ctx, float* inout, size_t n, double snr, uint64_t seed, uint64_t stream);
+/* whole loop body (:570-585) with intermediates kept on the device.  psf is normalised in place.
+ * out has X*Y*((Z-1)/inc+1) floats. */
+int mvsim_simulate_view(mvsim_ctx* ctx, const mvsim_view_params* p, const float* gt, float* psf, float* out);
+
+/* the reference's view loop (:567-613): one ground truth, n_views parameter sets / PSFs / outputs.  The
+ * ground truth is uploaded once; the download of view v overlaps the kernels of view v+1. */
+int mvsim_simulate_views(mvsim_ctx* ctx, int n_views, const mvsim_view_params* params, const float* gt,
+                         float* const* psfs, float* const* outs);
+
+/* ---- device-resident volumes (SNR sweeps a la S/SimulateTileStitching.java:131-189) ------- */
+int mvsim_volume_create(mvsim_ctx* ctx, const int64_t dims[3], mvsim_volume** vol);
+int mvsim_volume_free(mvsim_ctx* ctx, mvsim_volume* vol);
+int mvsim_volume_dims(const mvsim_volume* vol, int64_t dims[3]);
+void* mvsim_volume_device_ptr(mvsim_volume* vol);
+int mvsim_volume_upload(mvsim_ctx* ctx, mvsim_volume* vol, const float* host);       /* async if pinned */
+int mvsim_volume_download(mvsim_ctx* ctx, const mvsim_volume* vol, float* host);     /* async if pinned */
+
+int mvsim_dev_rotate_axis(mvsim_ctx* ctx, const mvsim_volume* in, mvsim_volume* out, int axis, int degrees);
+int mvsim_dev_attenuate(mvsim_ctx* ctx, const mvsim_volume* in, mvsim_volume* out, double delta, int strict_reference);
+int mvsim_dev_psf_normalize(mvsim_ctx* ctx, mvsim_volume* psf, double* sum_out /* nullable: no sync */);
+/* psf must already be normalised (mvsim_dev_psf_normalize); the spectrum is rebuilt per call like :257 */
+int mvsim_dev_convolve(mvsim_ctx* ctx, const mvsim_volume* img, const mvsim_volume* psf, mvsim_volume* out);
+int mvsim_dev_adjust(mvsim_ctx* ctx, mvsim_volume* img, float min_value, float target_avg, double* correction_out /* nullable: no sync */);
+int mvsim_dev_extract_slices(mvsim_ctx* ctx, const mvsim_volume* in, int inc, float snr, uint64_t seed, uint64_t stream, mvsim_volume* out);
+/* gt: ground truth, psf: raw PSF (normalised in place), out: X*Y*((Z-1)/inc+1) */
+int mvsim_dev_simulate_view(mvsim_ctx* ctx, const mvsim_view_params* p, const mvsim_volume* gt, mvsim_volume* psf, mvsim_volume* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVSIM_H */

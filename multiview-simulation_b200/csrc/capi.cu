@@ -1,0 +1,720 @@
+// C ABI of libmvsim.so (include/mvsim.h).  Host-side orchestration only; kernels live in stages.cu
+// and fft/.  There is deliberately no CPU path: without a CUDA device every compute call fails.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "ctx.h"
+#include "fft/conv_plan.h"
+
+namespace mvsim {
+
+static thread_local std::string tls_error;
+
+int set_error(mvsim_ctx* ctx, int status, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    tls_error = buf;
+    if (ctx) ctx->err = buf;
+    return status;
+}
+
+int cuda_fail(mvsim_ctx* ctx, cudaError_t e, const char* what)
+{
+    return set_error(ctx, e == cudaErrorMemoryAllocation ? MVSIM_ENOMEM : MVSIM_ECUDA, "CUDA error %d (%s) in %s", (int)e,
+                     cudaGetErrorString(e), what);
+}
+
+StageTimer::StageTimer(mvsim_ctx* c, int stage) : ctx(c), idx(-1)
+{
+    if (!c->profiling) return;
+    mvsim_ctx::Ev ev;
+    if (!c->pool.empty()) { ev = c->pool.back(); c->pool.pop_back(); }
+    else if (cudaEventCreate(&ev.a) != cudaSuccess || cudaEventCreate(&ev.b) != cudaSuccess) return;
+    ev.stage = stage;
+    cudaEventRecord(ev.a, c->stream);
+    c->events.push_back(ev);
+    idx = (int)c->events.size() - 1;
+}
+
+StageTimer::~StageTimer()
+{
+    if (idx >= 0) cudaEventRecord(ctx->events[idx].b, ctx->stream);
+}
+
+int dev_alloc(mvsim_ctx* ctx, void** p, size_t bytes)
+{
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMallocAsync(p, bytes, ctx->stream);
+    if (e != cudaSuccess) { *p = nullptr; return cuda_fail(ctx, e, "cudaMallocAsync"); }
+    return MVSIM_OK;
+}
+
+void dev_free(mvsim_ctx* ctx, void* p)
+{
+    if (p) cudaFreeAsync(p, ctx->stream);
+}
+
+int get_tables(mvsim_ctx* ctx, int n, mvsim_tables* t)
+{
+    auto it = ctx->tables.find(n);
+    if (it != ctx->tables.end()) { *t = it->second; return MVSIM_OK; }
+    std::vector<float> host((size_t)4 * n);
+    fill_twiddles(n, host.data());
+    fill_twist(n, host.data() + 2 * n);
+    float2* d = nullptr;
+    MVSIM_CUDA(ctx, cudaMalloc((void**)&d, sizeof(float2) * 2 * n));
+    // synchronous copy from pageable memory: the host vector may die right after
+    MVSIM_CUDA(ctx, cudaMemcpy(d, host.data(), sizeof(float2) * 2 * n, cudaMemcpyHostToDevice));
+    mvsim_tables nt = { d, d + n };
+    ctx->tables[n] = nt;
+    *t = nt;
+    return MVSIM_OK;
+}
+
+// axisRotation S/SimulateMultiViewDataset.java:80-102 and mpicbg AffineModel3D.createInverse()
+static void preconcat(double* t, const double* a)
+{
+    double r[12];
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) r[4 * i + j] = a[4 * i] * t[j] + a[4 * i + 1] * t[4 + j] + a[4 * i + 2] * t[8 + j];
+        r[4 * i + 3] = a[4 * i] * t[3] + a[4 * i + 1] * t[7] + a[4 * i + 2] * t[11] + a[4 * i + 3];
+    }
+    memcpy(t, r, sizeof(r));
+}
+
+static int axis_rotation(const int64_t dims[3], int axis, int degrees, double fwd[12], double inv[12])
+{
+    if (axis < 0 || axis > 2) return MVSIM_EINVAL;
+    double c[3];
+    for (int d = 0; d < 3; ++d) c[d] = (double)((dims[d] - 1) / 2);            // (max - min) / 2, long division
+    const double th = (double)(float)((double)degrees / 180.0 * 3.14159265358979323846);   // (float)Math.toRadians
+    const double cs = cos(th), sn = sin(th);
+    double rot[12] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0 };
+    if (axis == 0) { rot[5] = cs; rot[6] = -sn; rot[9] = sn; rot[10] = cs; }
+    else if (axis == 1) { rot[0] = cs; rot[2] = sn; rot[8] = -sn; rot[10] = cs; }
+    else { rot[0] = cs; rot[1] = -sn; rot[4] = sn; rot[5] = cs; }
+    const double t1[12] = { 1, 0, 0, -c[0], 0, 1, 0, -c[1], 0, 0, 1, -c[2] };
+    const double t2[12] = { 1, 0, 0, c[0], 0, 1, 0, c[1], 0, 0, 1, c[2] };
+    double m[12];
+    memcpy(m, t1, sizeof(m));
+    preconcat(m, rot);
+    preconcat(m, t2);
+    const double det = m[0] * m[5] * m[10] + m[4] * m[9] * m[2] + m[8] * m[1] * m[6] - m[2] * m[5] * m[8] - m[6] * m[9] * m[0] - m[10] * m[1] * m[4];
+    if (det == 0) return MVSIM_EINVAL;
+    const double id = 1.0 / det;
+    double i[12];
+    i[0] = (m[5] * m[10] - m[6] * m[9]) * id;  i[1] = (m[2] * m[9] - m[1] * m[10]) * id;  i[2] = (m[1] * m[6] - m[2] * m[5]) * id;
+    i[4] = (m[6] * m[8] - m[4] * m[10]) * id;  i[5] = (m[0] * m[10] - m[2] * m[8]) * id;  i[6] = (m[2] * m[4] - m[0] * m[6]) * id;
+    i[8] = (m[4] * m[9] - m[5] * m[8]) * id;   i[9] = (m[1] * m[8] - m[0] * m[9]) * id;   i[10] = (m[0] * m[5] - m[1] * m[4]) * id;
+    i[3] = -i[0] * m[3] - i[1] * m[7] - i[2] * m[11];
+    i[7] = -i[4] * m[3] - i[5] * m[7] - i[6] * m[11];
+    i[11] = -i[8] * m[3] - i[9] * m[7] - i[10] * m[11];
+    if (fwd) memcpy(fwd, m, sizeof(m));
+    if (inv) memcpy(inv, i, sizeof(i));
+    return MVSIM_OK;
+}
+
+static int check_dims(mvsim_ctx* ctx, const int64_t d[3], const char* what)
+{
+    if (!d || d[0] < 1 || d[1] < 1 || d[2] < 1) return set_error(ctx, MVSIM_EINVAL, "%s: dims must be >= 1", what);
+    if (d[0] > 0x7fffffff || d[1] > 0x7fffffff || d[2] > 0x7fffffff || (double)d[0] * (double)d[1] * (double)d[2] > 1.0e11)
+        return set_error(ctx, MVSIM_EINVAL, "%s: dims too large", what);
+    return MVSIM_OK;
+}
+
+static size_t elems(const int64_t d[3]) { return (size_t)(d[0] * d[1] * d[2]); }
+
+static int attenuate_steps(mvsim_ctx* ctx, const int64_t d[3], int strict, int* steps)
+{
+    if (strict && d[0] > d[1])
+        return set_error(ctx, MVSIM_EINVAL, "attenuate: strict_reference needs X <= Y (the reference loop bound is dimension(0) and walks out of bounds otherwise)");
+    *steps = (int)(strict ? d[0] : d[1]);
+    return MVSIM_OK;
+}
+
+static int h2d(mvsim_ctx* ctx, void* d, const void* h, size_t bytes)
+{
+    StageTimer t(ctx, MVSIM_T_H2D);
+    MVSIM_CUDA(ctx, cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return MVSIM_OK;
+}
+
+static int d2h(mvsim_ctx* ctx, void* h, const void* d, size_t bytes)
+{
+    StageTimer t(ctx, MVSIM_T_D2H);
+    MVSIM_CUDA(ctx, cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return MVSIM_OK;
+}
+
+static int sync(mvsim_ctx* ctx)
+{
+    MVSIM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MVSIM_OK;
+}
+
+// scoped device buffer
+struct DevBuf {
+    mvsim_ctx* ctx; void* p;
+    explicit DevBuf(mvsim_ctx* c) : ctx(c), p(nullptr) {}
+    ~DevBuf() { dev_free(ctx, p); }
+    int alloc(size_t bytes) { return dev_alloc(ctx, &p, bytes); }
+    float* f() { return static_cast<float*>(p); }
+};
+
+struct Activate {
+    int prev; bool ok;
+    explicit Activate(mvsim_ctx* ctx) : prev(-1), ok(false)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) return;
+        ok = cudaSetDevice(ctx->device) == cudaSuccess;
+    }
+    ~Activate() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+#define MVSIM_ENTER(ctx)                                                                     \
+    if (!(ctx)) return mvsim::set_error(nullptr, MVSIM_EINVAL, "null context");             \
+    mvsim::Activate act__(ctx);                                                              \
+    if (!act__.ok) return mvsim::set_error((ctx), MVSIM_ECUDA, "cannot select CUDA device %d", (ctx)->device)
+
+// ---- device-level building blocks ---------------------------------------------------------
+static int dev_rotate(mvsim_ctx* ctx, const float* in, float* out, const int64_t dims[3], int axis, int degrees)
+{
+    double inv[12];
+    if (axis_rotation(dims, axis, degrees, nullptr, inv)) return set_error(ctx, MVSIM_EINVAL, "rotate: axis must be 0, 1 or 2");
+    StageTimer t(ctx, MVSIM_T_ROTATE);
+    return k_rotate(ctx, in, out, dims, axis, inv);
+}
+
+static int dev_attenuate(mvsim_ctx* ctx, const float* in, float* out, const int64_t dims[3], double delta, int strict)
+{
+    int steps;
+    MVSIM_TRY(attenuate_steps(ctx, dims, strict, &steps));
+    StageTimer t(ctx, MVSIM_T_ATTENUATE);
+    return k_attenuate(ctx, in, out, dims, delta, steps);
+}
+
+static int dev_psf_normalize(mvsim_ctx* ctx, float* psf, size_t n)
+{
+    StageTimer t(ctx, MVSIM_T_PSF);
+    MVSIM_TRY(k_sum(ctx, psf, n, ctx->d_scalars + 0));
+    return k_divide_by_sum(ctx, psf, n, ctx->d_scalars + 0);
+}
+
+static int read_scalar(mvsim_ctx* ctx, int slot, double* out)
+{
+    MVSIM_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_scalars + slot, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    return sync(ctx);
+}
+
+static int dev_adjust(mvsim_ctx* ctx, float* img, size_t n, float min_value, float target_avg)
+{
+    StageTimer t(ctx, MVSIM_T_ADJUST);
+    MVSIM_TRY(k_sum(ctx, img, n, ctx->d_scalars + 1));
+    MVSIM_TRY(k_adjust_corr(ctx, ctx->d_scalars + 1, n, min_value, target_avg, ctx->d_scalars + 2));
+    return k_adjust_apply(ctx, img, n, ctx->d_scalars + 2, min_value);
+}
+
+static int check_view(mvsim_ctx* ctx, const mvsim_view_params* p)
+{
+    if (!p) return set_error(ctx, MVSIM_EINVAL, "null view params");
+    MVSIM_TRY(check_dims(ctx, p->dims, "simulate_view dims"));
+    MVSIM_TRY(check_dims(ctx, p->kdims, "simulate_view kdims"));
+    if (p->inc < 1) return set_error(ctx, MVSIM_EINVAL, "simulate_view: inc must be >= 1");
+    if (p->axis < 0 || p->axis > 2) return set_error(ctx, MVSIM_EINVAL, "simulate_view: axis must be 0, 1 or 2");
+    return MVSIM_OK;
+}
+
+// loop body S/SimulateMultiViewDataset.java:570-585 on device pointers
+static int dev_simulate_view(mvsim_ctx* ctx, const mvsim_view_params* p, const float* gt, float* psf, float* out)
+{
+    const size_t n = elems(p->dims);
+    DevBuf a(ctx), b(ctx);
+    MVSIM_TRY(a.alloc(n * sizeof(float)));
+    MVSIM_TRY(b.alloc(n * sizeof(float)));
+    MVSIM_TRY(dev_rotate(ctx, gt, a.f(), p->dims, p->axis, p->degrees));                       // :570
+    MVSIM_TRY(dev_attenuate(ctx, a.f(), b.f(), p->dims, p->delta, p->strict_reference));       // :573
+    MVSIM_TRY(dev_psf_normalize(ctx, psf, elems(p->kdims)));                                   // :255
+    MVSIM_TRY(conv_device(ctx, b.f(), p->dims, psf, p->kdims, a.f(), ctx->d_scalars + 1));     // :580
+    {
+        StageTimer t(ctx, MVSIM_T_ADJUST);                                                     // :582, applied inside the sampler
+        MVSIM_TRY(k_adjust_corr(ctx, ctx->d_scalars + 1, n, p->min_value, p->target_avg, ctx->d_scalars + 2));
+    }
+    StageTimer t(ctx, MVSIM_T_SAMPLE);                                                         // :585
+    return k_extract(ctx, a.f(), p->dims, p->inc, ctx->d_scalars + 2, p->min_value, p->snr, p->seed, p->stream, out);
+}
+
+}  // namespace mvsim
+
+using namespace mvsim;
+
+extern "C" {
+
+int mvsim_version(void) { return 100; }
+
+int mvsim_device_count(int* count)
+{
+    if (!count) return MVSIM_EINVAL;
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) { *count = 0; return cuda_fail(nullptr, e, "cudaGetDeviceCount"); }
+    return MVSIM_OK;
+}
+
+int mvsim_ctx_create_on_stream(int device, void* cuda_stream, mvsim_ctx** out)
+{
+    if (!out) return set_error(nullptr, MVSIM_EINVAL, "null output pointer");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n < 1)
+        return set_error(nullptr, MVSIM_ECUDA, "no CUDA device available (%s); libmvsim has no CPU fallback",
+                         e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= n) return set_error(nullptr, MVSIM_EINVAL, "device %d out of range [0,%d)", device, n);
+    mvsim_ctx* ctx = new mvsim_ctx();
+    ctx->device = device;
+    ctx->stream = nullptr;
+    ctx->own_stream = false;
+    ctx->copy_stream = nullptr;
+    ctx->d_scalars = nullptr;
+    ctx->launches = 0;
+    ctx->profiling = false;
+    memset(ctx->acc_ms, 0, sizeof(ctx->acc_ms));
+    memset(ctx->acc_n, 0, sizeof(ctx->acc_n));
+    int prev = -1;
+    cudaGetDevice(&prev);
+    int st = MVSIM_OK;
+    do {
+        if ((e = cudaSetDevice(device)) != cudaSuccess) { st = cuda_fail(nullptr, e, "cudaSetDevice"); break; }
+        if (cuda_stream) ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+        else {
+            if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) { st = cuda_fail(nullptr, e, "cudaStreamCreate"); break; }
+            ctx->own_stream = true;
+        }
+        if ((e = cudaMalloc((void**)&ctx->d_scalars, 8 * sizeof(double))) != cudaSuccess) { st = cuda_fail(nullptr, e, "cudaMalloc"); break; }
+        // keep freed workspaces cached in the stream-ordered pool (no per-call cudaMalloc)
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    } while (0);
+    if (prev >= 0) cudaSetDevice(prev);
+    if (st != MVSIM_OK) {
+        if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        return st;
+    }
+    *out = ctx;
+    return MVSIM_OK;
+}
+
+int mvsim_ctx_create(int device, mvsim_ctx** out) { return mvsim_ctx_create_on_stream(device, nullptr, out); }
+
+int mvsim_ctx_destroy(mvsim_ctx* ctx)
+{
+    if (!ctx) return MVSIM_OK;
+    Activate act(ctx);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& kv : ctx->tables) cudaFree(kv.second.tw);
+    for (auto& ev : ctx->events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
+    for (auto& ev : ctx->pool) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
+    cudaFree(ctx->d_scalars);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return MVSIM_OK;
+}
+
+int mvsim_ctx_synchronize(mvsim_ctx* ctx)
+{
+    MVSIM_ENTER(ctx);
+    return sync(ctx);
+}
+
+const char* mvsim_last_error(mvsim_ctx* ctx) { return ctx ? ctx->err.c_str() : tls_error.c_str(); }
+
+int mvsim_profile_enable(mvsim_ctx* ctx, int on)
+{
+    if (!ctx) return MVSIM_EINVAL;
+    ctx->profiling = on != 0;
+    return MVSIM_OK;
+}
+
+static int drain_events(mvsim_ctx* ctx)
+{
+    MVSIM_TRY(sync(ctx));
+    for (auto& ev : ctx->events) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ev.a, ev.b) == cudaSuccess) {
+            ctx->acc_ms[ev.stage] += ms;
+            ctx->acc_n[ev.stage] += 1;
+        }
+        ctx->pool.push_back(ev);
+    }
+    ctx->events.clear();
+    return MVSIM_OK;
+}
+
+int mvsim_profile_reset(mvsim_ctx* ctx)
+{
+    MVSIM_ENTER(ctx);
+    MVSIM_TRY(drain_events(ctx));
+    memset(ctx->acc_ms, 0, sizeof(ctx->acc_ms));
+    memset(ctx->acc_n, 0, sizeof(ctx->acc_n));
+    return MVSIM_OK;
+}
+
+int mvsim_stage_times(mvsim_ctx* ctx, double ms[MVSIM_NSTAGES], int64_t launches[MVSIM_NSTAGES])
+{
+    MVSIM_ENTER(ctx);
+    MVSIM_TRY(drain_events(ctx));
+    for (int i = 0; i < MVSIM_NSTAGES; ++i) {
+        if (ms) ms[i] = ctx->acc_ms[i];
+        if (launches) launches[i] = ctx->acc_n[i];
+    }
+    return MVSIM_OK;
+}
+
+int64_t mvsim_kernel_launches(mvsim_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int mvsim_alloc_pinned(size_t bytes, void** ptr)
+{
+    if (!ptr) return MVSIM_EINVAL;
+    cudaError_t e = cudaHostAlloc(ptr, bytes ? bytes : 16, cudaHostAllocPortable);
+    if (e != cudaSuccess) { *ptr = nullptr; return cuda_fail(nullptr, e, "cudaHostAlloc"); }
+    return MVSIM_OK;
+}
+
+int mvsim_free_pinned(void* ptr)
+{
+    if (!ptr) return MVSIM_OK;
+    cudaError_t e = cudaFreeHost(ptr);
+    return e == cudaSuccess ? MVSIM_OK : cuda_fail(nullptr, e, "cudaFreeHost");
+}
+
+int mvsim_conv_padded_dims(const int64_t dims[3], const int64_t kdims[3], int64_t nfft[3])
+{
+    if (!dims || !kdims || !nfft) return MVSIM_EINVAL;
+    ConvPlan pl;
+    const int e = make_conv_plan(dims, kdims, &pl);
+    if (e) return e == 1 ? MVSIM_EINVAL : MVSIM_EUNSUPPORTED;
+    nfft[0] = 2 * pl.sx.n; nfft[1] = pl.sy.n; nfft[2] = pl.sz.n;
+    return MVSIM_OK;
+}
+
+int mvsim_axis_rotation(const int64_t dims[3], int axis, int degrees, double fwd[12], double inv[12])
+{
+    if (!dims) return MVSIM_EINVAL;
+    return axis_rotation(dims, axis, degrees, fwd, inv);
+}
+
+// ---- host-buffer entry points ---------------------------------------------------------------
+int mvsim_rotate_axis(mvsim_ctx* ctx, const float* in, float* out, const int64_t dims[3], int axis, int degrees)
+{
+    MVSIM_ENTER(ctx);
+    if (!in || !out) return set_error(ctx, MVSIM_EINVAL, "rotate: null buffer");
+    MVSIM_TRY(check_dims(ctx, dims, "rotate"));
+    const size_t bytes = elems(dims) * sizeof(float);
+    DevBuf a(ctx), b(ctx);
+    MVSIM_TRY(a.alloc(bytes));
+    MVSIM_TRY(b.alloc(bytes));
+    MVSIM_TRY(h2d(ctx, a.p, in, bytes));
+    MVSIM_TRY(dev_rotate(ctx, a.f(), b.f(), dims, axis, degrees));
+    MVSIM_TRY(d2h(ctx, out, b.p, bytes));
+    return sync(ctx);
+}
+
+int mvsim_attenuate(mvsim_ctx* ctx, const float* in, float* out, const int64_t dims[3], double delta, int strict_reference)
+{
+    MVSIM_ENTER(ctx);
+    if (!in || !out) return set_error(ctx, MVSIM_EINVAL, "attenuate: null buffer");
+    MVSIM_TRY(check_dims(ctx, dims, "attenuate"));
+    const size_t bytes = elems(dims) * sizeof(float);
+    DevBuf a(ctx), b(ctx);
+    MVSIM_TRY(a.alloc(bytes));
+    MVSIM_TRY(b.alloc(bytes));
+    MVSIM_TRY(h2d(ctx, a.p, in, bytes));
+    MVSIM_TRY(dev_attenuate(ctx, a.f(), b.f(), dims, delta, strict_reference));
+    MVSIM_TRY(d2h(ctx, out, b.p, bytes));
+    return sync(ctx);
+}
+
+int mvsim_psf_normalize(mvsim_ctx* ctx, float* psf, const int64_t kdims[3], double* sum_out)
+{
+    MVSIM_ENTER(ctx);
+    if (!psf) return set_error(ctx, MVSIM_EINVAL, "psf_normalize: null buffer");
+    MVSIM_TRY(check_dims(ctx, kdims, "psf_normalize"));
+    const size_t bytes = elems(kdims) * sizeof(float);
+    DevBuf a(ctx);
+    MVSIM_TRY(a.alloc(bytes));
+    MVSIM_TRY(h2d(ctx, a.p, psf, bytes));
+    MVSIM_TRY(dev_psf_normalize(ctx, a.f(), elems(kdims)));
+    MVSIM_TRY(d2h(ctx, psf, a.p, bytes));
+    double s = 0;
+    MVSIM_TRY(read_scalar(ctx, 0, &s));
+    if (sum_out) *sum_out = s;
+    return MVSIM_OK;
+}
+
+int mvsim_convolve(mvsim_ctx* ctx, const float* img, const int64_t dims[3], float* psf, const int64_t kdims[3], float* out)
+{
+    MVSIM_ENTER(ctx);
+    if (!img || !psf || !out) return set_error(ctx, MVSIM_EINVAL, "convolve: null buffer");
+    MVSIM_TRY(check_dims(ctx, dims, "convolve dims"));
+    MVSIM_TRY(check_dims(ctx, kdims, "convolve kdims"));
+    const size_t bytes = elems(dims) * sizeof(float), kbytes = elems(kdims) * sizeof(float);
+    DevBuf a(ctx), b(ctx), k(ctx);
+    MVSIM_TRY(a.alloc(bytes));
+    MVSIM_TRY(b.alloc(bytes));
+    MVSIM_TRY(k.alloc(kbytes));
+    MVSIM_TRY(h2d(ctx, a.p, img, bytes));
+    MVSIM_TRY(h2d(ctx, k.p, psf, kbytes));
+    MVSIM_TRY(dev_psf_normalize(ctx, k.f(), elems(kdims)));
+    MVSIM_TRY(conv_device(ctx, a.f(), dims, k.f(), kdims, b.f(), nullptr));
+    MVSIM_TRY(d2h(ctx, psf, k.p, kbytes));          // in-place normalisation is part of the contract (:255)
+    MVSIM_TRY(d2h(ctx, out, b.p, bytes));
+    return sync(ctx);
+}
+
+int mvsim_adjust(mvsim_ctx* ctx, float* img, const int64_t dims[3], float min_value, float target_avg, double* correction_out)
+{
+    MVSIM_ENTER(ctx);
+    if (!img) return set_error(ctx, MVSIM_EINVAL, "adjust: null buffer");
+    MVSIM_TRY(check_dims(ctx, dims, "adjust"));
+    const size_t bytes = elems(dims) * sizeof(float);
+    DevBuf a(ctx);
+    MVSIM_TRY(a.alloc(bytes));
+    MVSIM_TRY(h2d(ctx, a.p, img, bytes));
+    MVSIM_TRY(dev_adjust(ctx, a.f(), elems(dims), min_value, target_avg));
+    MVSIM_TRY(d2h(ctx, img, a.p, bytes));
+    double c = 0;
+    MVSIM_TRY(read_scalar(ctx, 2, &c));
+    if (correction_out) *correction_out = c;
+    return MVSIM_OK;
+}
+
+int mvsim_extract_slices(mvsim_ctx* ctx, const float* in, const int64_t dims[3], int inc, float snr, uint64_t seed, uint64_t stream, float* out)
+{
+    MVSIM_ENTER(ctx);
+    if (!in || !out) return set_error(ctx, MVSIM_EINVAL, "extract_slices: null buffer");
+    MVSIM_TRY(check_dims(ctx, dims, "extract_slices"));
+    if (inc < 1) return set_error(ctx, MVSIM_EINVAL, "extract_slices: inc must be >= 1");
+    const size_t bytes = elems(dims) * sizeof(float);
+    const size_t obytes = (size_t)(dims[0] * dims[1] * ((dims[2] - 1) / inc + 1)) * sizeof(float);
+    DevBuf a(ctx), b(ctx);
+    MVSIM_TRY(a.alloc(bytes));
+    MVSIM_TRY(b.alloc(obytes));
+    MVSIM_TRY(h2d(ctx, a.p, in, bytes));
+    {
+        StageTimer t(ctx, MVSIM_T_SAMPLE);
+        MVSIM_TRY(k_extract(ctx, a.f(), dims, inc, nullptr, 0.f, snr, seed, stream, b.f()));
+    }
+    MVSIM_TRY(d2h(ctx, out, b.p, obytes));
+    return sync(ctx);
+}
+
+int mvsim_poisson(mvsim_ctx* ctx, float* inout, size_t n, double snr, uint64_t seed, uint64_t stream)
+{
+    MVSIM_ENTER(ctx);
+    if (!inout && n) return set_error(ctx, MVSIM_EINVAL, "poisson: null buffer");
+    if (n == 0) return MVSIM_OK;
+    DevBuf a(ctx);
+    MVSIM_TRY(a.alloc(n * sizeof(float)));
+    MVSIM_TRY(h2d(ctx, a.p, inout, n * sizeof(float)));
+    {
+        StageTimer t(ctx, MVSIM_T_SAMPLE);
+        MVSIM_TRY(k_poisson(ctx, a.f(), n, snr, seed, stream));
+    }
+    MVSIM_TRY(d2h(ctx, inout, a.p, n * sizeof(float)));
+    return sync(ctx);
+}
+
+int mvsim_simulate_view(mvsim_ctx* ctx, const mvsim_view_params* p, const float* gt, float* psf, float* out)
+{
+    MVSIM_ENTER(ctx);
+    MVSIM_TRY(check_view(ctx, p));
+    if (!gt || !psf || !out) return set_error(ctx, MVSIM_EINVAL, "simulate_view: null buffer");
+    const size_t bytes = elems(p->dims) * sizeof(float), kbytes = elems(p->kdims) * sizeof(float);
+    const size_t obytes = (size_t)(p->dims[0] * p->dims[1] * ((p->dims[2] - 1) / p->inc + 1)) * sizeof(float);
+    DevBuf g(ctx), k(ctx), o(ctx);
+    MVSIM_TRY(g.alloc(bytes));
+    MVSIM_TRY(k.alloc(kbytes));
+    MVSIM_TRY(o.alloc(obytes));
+    MVSIM_TRY(h2d(ctx, g.p, gt, bytes));
+    MVSIM_TRY(h2d(ctx, k.p, psf, kbytes));
+    MVSIM_TRY(dev_simulate_view(ctx, p, g.f(), k.f(), o.f()));
+    MVSIM_TRY(d2h(ctx, psf, k.p, kbytes));
+    MVSIM_TRY(d2h(ctx, out, o.p, obytes));
+    return sync(ctx);
+}
+
+int mvsim_simulate_views(mvsim_ctx* ctx, int n_views, const mvsim_view_params* params, const float* gt,
+                         float* const* psfs, float* const* outs)
+{
+    MVSIM_ENTER(ctx);
+    if (n_views < 0 || (n_views > 0 && (!params || !gt || !psfs || !outs))) return set_error(ctx, MVSIM_EINVAL, "simulate_views: null argument");
+    if (n_views == 0) return MVSIM_OK;
+    for (int v = 0; v < n_views; ++v) {
+        MVSIM_TRY(check_view(ctx, &params[v]));
+        if (!psfs[v] || !outs[v]) return set_error(ctx, MVSIM_EINVAL, "simulate_views: null buffer for view %d", v);
+        for (int d = 0; d < 3; ++d)
+            if (params[v].dims[d] != params[0].dims[d]) return set_error(ctx, MVSIM_EINVAL, "simulate_views: all views share the ground truth dims");
+    }
+    if (!ctx->copy_stream) MVSIM_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    const size_t bytes = elems(params[0].dims) * sizeof(float);
+    DevBuf g(ctx);
+    MVSIM_TRY(g.alloc(bytes));
+    MVSIM_TRY(h2d(ctx, g.p, gt, bytes));
+    std::vector<void*> held;            // per-view device buffers stay alive until their download is done
+    cudaEvent_t done = nullptr, copied = nullptr;
+    int st = MVSIM_OK;
+    if (cudaEventCreateWithFlags(&done, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&copied, cudaEventDisableTiming) != cudaSuccess)
+        st = set_error(ctx, MVSIM_ECUDA, "simulate_views: cannot create events");
+    for (int v = 0; v < n_views && st == MVSIM_OK; ++v) {
+        const mvsim_view_params* p = &params[v];
+        const size_t kbytes = elems(p->kdims) * sizeof(float);
+        const size_t obytes = (size_t)(p->dims[0] * p->dims[1] * ((p->dims[2] - 1) / p->inc + 1)) * sizeof(float);
+        void *k = nullptr, *o = nullptr;
+        if ((st = dev_alloc(ctx, &k, kbytes)) != MVSIM_OK) break;
+        held.push_back(k);
+        if ((st = dev_alloc(ctx, &o, obytes)) != MVSIM_OK) break;
+        held.push_back(o);
+        if ((st = h2d(ctx, k, psfs[v], kbytes)) != MVSIM_OK) break;
+        if ((st = dev_simulate_view(ctx, p, g.f(), static_cast<float*>(k), static_cast<float*>(o))) != MVSIM_OK) break;
+        cudaError_t e = cudaEventRecord(done, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, done, 0);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(psfs[v], k, kbytes, cudaMemcpyDeviceToHost, ctx->copy_stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(outs[v], o, obytes, cudaMemcpyDeviceToHost, ctx->copy_stream);
+        if (e != cudaSuccess) st = cuda_fail(ctx, e, "simulate_views: download");
+    }
+    // the main stream waits for the copy stream before the buffers go back to the pool
+    if (copied && cudaEventRecord(copied, ctx->copy_stream) == cudaSuccess) cudaStreamWaitEvent(ctx->stream, copied, 0);
+    for (void* q : held) dev_free(ctx, q);
+    const int st2 = sync(ctx);
+    if (done) cudaEventDestroy(done);
+    if (copied) cudaEventDestroy(copied);
+    return st != MVSIM_OK ? st : st2;
+}
+
+// ---- device-resident volumes ------------------------------------------------------------------
+int mvsim_volume_create(mvsim_ctx* ctx, const int64_t dims[3], mvsim_volume** vol)
+{
+    MVSIM_ENTER(ctx);
+    if (!vol) return set_error(ctx, MVSIM_EINVAL, "volume_create: null output pointer");
+    *vol = nullptr;
+    MVSIM_TRY(check_dims(ctx, dims, "volume_create"));
+    mvsim_volume* v = new mvsim_volume();
+    v->device = ctx->device;
+    memcpy(v->dims, dims, sizeof(v->dims));
+    cudaError_t e = cudaMalloc((void**)&v->d, v->elems() * sizeof(float));
+    if (e != cudaSuccess) { delete v; return cuda_fail(ctx, e, "cudaMalloc(volume)"); }
+    *vol = v;
+    return MVSIM_OK;
+}
+
+int mvsim_volume_free(mvsim_ctx* ctx, mvsim_volume* vol)
+{
+    if (!vol) return MVSIM_OK;
+    MVSIM_ENTER(ctx);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(vol->d);
+    delete vol;
+    return MVSIM_OK;
+}
+
+int mvsim_volume_dims(const mvsim_volume* vol, int64_t dims[3])
+{
+    if (!vol || !dims) return MVSIM_EINVAL;
+    memcpy(dims, vol->dims, sizeof(vol->dims));
+    return MVSIM_OK;
+}
+
+void* mvsim_volume_device_ptr(mvsim_volume* vol) { return vol ? vol->d : nullptr; }
+
+int mvsim_volume_upload(mvsim_ctx* ctx, mvsim_volume* vol, const float* host)
+{
+    MVSIM_ENTER(ctx);
+    if (!vol || !host) return set_error(ctx, MVSIM_EINVAL, "volume_upload: null argument");
+    return h2d(ctx, vol->d, host, vol->elems() * sizeof(float));
+}
+
+int mvsim_volume_download(mvsim_ctx* ctx, const mvsim_volume* vol, float* host)
+{
+    MVSIM_ENTER(ctx);
+    if (!vol || !host) return set_error(ctx, MVSIM_EINVAL, "volume_download: null argument");
+    return d2h(ctx, host, vol->d, vol->elems() * sizeof(float));
+}
+
+static bool same_dims(const mvsim_volume* a, const mvsim_volume* b)
+{
+    return a->dims[0] == b->dims[0] && a->dims[1] == b->dims[1] && a->dims[2] == b->dims[2];
+}
+
+int mvsim_dev_rotate_axis(mvsim_ctx* ctx, const mvsim_volume* in, mvsim_volume* out, int axis, int degrees)
+{
+    MVSIM_ENTER(ctx);
+    if (!in || !out || in == out || !same_dims(in, out)) return set_error(ctx, MVSIM_EINVAL, "dev_rotate: need two distinct volumes of equal dims");
+    return dev_rotate(ctx, in->d, out->d, in->dims, axis, degrees);
+}
+
+int mvsim_dev_attenuate(mvsim_ctx* ctx, const mvsim_volume* in, mvsim_volume* out, double delta, int strict_reference)
+{
+    MVSIM_ENTER(ctx);
+    if (!in || !out || in == out || !same_dims(in, out)) return set_error(ctx, MVSIM_EINVAL, "dev_attenuate: need two distinct volumes of equal dims");
+    return dev_attenuate(ctx, in->d, out->d, in->dims, delta, strict_reference);
+}
+
+int mvsim_dev_psf_normalize(mvsim_ctx* ctx, mvsim_volume* psf, double* sum_out)
+{
+    MVSIM_ENTER(ctx);
+    if (!psf) return set_error(ctx, MVSIM_EINVAL, "dev_psf_normalize: null volume");
+    MVSIM_TRY(dev_psf_normalize(ctx, psf->d, psf->elems()));
+    if (sum_out) MVSIM_TRY(read_scalar(ctx, 0, sum_out));
+    return MVSIM_OK;
+}
+
+int mvsim_dev_convolve(mvsim_ctx* ctx, const mvsim_volume* img, const mvsim_volume* psf, mvsim_volume* out)
+{
+    MVSIM_ENTER(ctx);
+    if (!img || !psf || !out || img == out || !same_dims(img, out)) return set_error(ctx, MVSIM_EINVAL, "dev_convolve: need img/out of equal dims, distinct");
+    return conv_device(ctx, img->d, img->dims, psf->d, psf->dims, out->d, nullptr);
+}
+
+int mvsim_dev_adjust(mvsim_ctx* ctx, mvsim_volume* img, float min_value, float target_avg, double* correction_out)
+{
+    MVSIM_ENTER(ctx);
+    if (!img) return set_error(ctx, MVSIM_EINVAL, "dev_adjust: null volume");
+    MVSIM_TRY(dev_adjust(ctx, img->d, img->elems(), min_value, target_avg));
+    if (correction_out) MVSIM_TRY(read_scalar(ctx, 2, correction_out));
+    return MVSIM_OK;
+}
+
+int mvsim_dev_extract_slices(mvsim_ctx* ctx, const mvsim_volume* in, int inc, float snr, uint64_t seed, uint64_t stream, mvsim_volume* out)
+{
+    MVSIM_ENTER(ctx);
+    if (!in || !out || inc < 1) return set_error(ctx, MVSIM_EINVAL, "dev_extract_slices: bad argument");
+    if (out->dims[0] != in->dims[0] || out->dims[1] != in->dims[1] || out->dims[2] != (in->dims[2] - 1) / inc + 1)
+        return set_error(ctx, MVSIM_EINVAL, "dev_extract_slices: out dims must be (X, Y, (Z-1)/inc+1)");
+    StageTimer t(ctx, MVSIM_T_SAMPLE);
+    return k_extract(ctx, in->d, in->dims, inc, nullptr, 0.f, snr, seed, stream, out->d);
+}
+
+int mvsim_dev_simulate_view(mvsim_ctx* ctx, const mvsim_view_params* p, const mvsim_volume* gt, mvsim_volume* psf, mvsim_volume* out)
+{
+    MVSIM_ENTER(ctx);
+    MVSIM_TRY(check_view(ctx, p));
+    if (!gt || !psf || !out) return set_error(ctx, MVSIM_EINVAL, "dev_simulate_view: null volume");
+    for (int d = 0; d < 3; ++d)
+        if (gt->dims[d] != p->dims[d] || psf->dims[d] != p->kdims[d]) return set_error(ctx, MVSIM_EINVAL, "dev_simulate_view: params do not match the volumes");
+    if (out->dims[0] != p->dims[0] || out->dims[1] != p->dims[1] || out->dims[2] != (p->dims[2] - 1) / p->inc + 1)
+        return set_error(ctx, MVSIM_EINVAL, "dev_simulate_view: out dims must be (X, Y, (Z-1)/inc+1)");
+    return dev_simulate_view(ctx, p, gt->d, psf->d, out->d);
+}
+
+}  // extern "C"

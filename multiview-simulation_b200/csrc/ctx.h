@@ -1,0 +1,83 @@
+// Context of libmvsim.so: device, stream, error text, cached tables, event profiling.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/mvsim.h"
+
+struct mvsim_volume {
+    float* d;
+    int64_t dims[3];
+    int device;
+    size_t elems() const { return (size_t)(dims[0] * dims[1] * dims[2]); }
+};
+
+struct mvsim_tables { float2 *tw, *twist; };
+
+struct mvsim_ctx {
+    int device;
+    cudaStream_t stream;
+    bool own_stream;
+    cudaStream_t copy_stream;                // lazily created: result downloads overlapping the next view
+    std::string err;
+    double* d_scalars;                       // [8] device doubles: sums, corrections
+    std::map<int, mvsim_tables> tables;      // by complex line length
+    int64_t launches;
+    // profiling
+    bool profiling;
+    struct Ev { cudaEvent_t a, b; int stage; };
+    std::vector<Ev> events;                  // recorded since last reset
+    std::vector<Ev> pool;                    // reusable
+    double acc_ms[MVSIM_NSTAGES];
+    int64_t acc_n[MVSIM_NSTAGES];
+};
+
+namespace mvsim {
+
+int set_error(mvsim_ctx* ctx, int status, const char* fmt, ...);
+int cuda_fail(mvsim_ctx* ctx, cudaError_t e, const char* what);
+
+#define MVSIM_CUDA(ctx, call)                                             \
+    do {                                                                  \
+        cudaError_t e__ = (call);                                         \
+        if (e__ != cudaSuccess) return mvsim::cuda_fail((ctx), e__, #call); \
+    } while (0)
+#define MVSIM_TRY(call)                    \
+    do {                                   \
+        int s__ = (call);                  \
+        if (s__ != MVSIM_OK) return s__;   \
+    } while (0)
+
+// RAII-less scoped stage timer: begin() before the launches of a stage, end() after.
+struct StageTimer {
+    mvsim_ctx* ctx; int idx;
+    StageTimer(mvsim_ctx* c, int stage);
+    ~StageTimer();
+};
+
+int dev_alloc(mvsim_ctx* ctx, void** p, size_t bytes);      // stream-ordered (cudaMallocAsync)
+void dev_free(mvsim_ctx* ctx, void* p);
+int get_tables(mvsim_ctx* ctx, int n, mvsim_tables* t);
+
+// stage kernels (stages.cu); all enqueue on ctx->stream
+int k_rotate(mvsim_ctx* ctx, const float* in, float* out, const int64_t dims[3], int axis, const double inv[12]);
+int k_attenuate(mvsim_ctx* ctx, const float* in, float* out, const int64_t dims[3], double delta, int steps);
+int k_sum(mvsim_ctx* ctx, const float* in, size_t n, double* d_sum);                 // deterministic double sum
+int k_sum_partials(mvsim_ctx* ctx, const double* partials, size_t n, double* d_sum);
+int k_divide_by_sum(mvsim_ctx* ctx, float* inout, size_t n, const double* d_sum);     // (float)((double)v / sum)
+int k_adjust_corr(mvsim_ctx* ctx, const double* d_sum, size_t n, float min_value, float target_avg, double* d_corr);
+int k_adjust_apply(mvsim_ctx* ctx, float* inout, size_t n, const double* d_corr, float min_value);
+// out[x,y,cz] = f(in[x,y,cz*inc]); d_corr != null fuses adjustImage; snr >= 0 adds Poisson noise
+int k_extract(mvsim_ctx* ctx, const float* in, const int64_t dims[3], int inc, const double* d_corr, float min_value,
+              float snr, uint64_t seed, uint64_t stream, float* out);
+int k_poisson(mvsim_ctx* ctx, float* inout, size_t n, double snr, uint64_t seed, uint64_t stream);
+
+// convolution driver (conv.cu): psf normalised, device pointers; partial sums -> d_sum when non-null
+int conv_device(mvsim_ctx* ctx, const float* img, const int64_t dims[3], const float* psf, const int64_t kdims[3],
+                float* out, double* d_sum);
+
+}  // namespace mvsim

@@ -1,0 +1,72 @@
+// Instantiates the line-FFT kernels (line_fft.cuh) for one group of sizes: -DMVSIM_GROUP=0..4.
+#include "fft_launch.h"
+
+#ifndef MVSIM_GROUP
+#error "compile with -DMVSIM_GROUP=<0..4>"
+#endif
+
+namespace mvsim {
+
+template <class K> __global__ void __launch_bounds__(K::THREADS) fft_kernel(const typename K::Params q)
+{
+    extern __shared__ __align__(16) unsigned char smraw[];
+    float2* sm = reinterpret_cast<float2*>(smraw);
+    typename K::State st;
+    K::template phase<0>(q, blockIdx.x, blockIdx.y, threadIdx.x, sm, st);
+    if constexpr (K::NPH > 1) { __syncthreads(); K::template phase<1>(q, blockIdx.x, blockIdx.y, threadIdx.x, sm, st); }
+    if constexpr (K::NPH > 2) { __syncthreads(); K::template phase<2>(q, blockIdx.x, blockIdx.y, threadIdx.x, sm, st); }
+    if constexpr (K::NPH > 3) { __syncthreads(); K::template phase<3>(q, blockIdx.x, blockIdx.y, threadIdx.x, sm, st); }
+}
+
+template <class K> static int launch(const void* params, unsigned gx, unsigned gy, cudaStream_t s)
+{
+    static bool configured = false;     // per instantiation; idempotent, so a race only repeats the call
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(fft_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    fft_kernel<K><<<dim3(gx, gy), K::THREADS, K::SMEM_BYTES, s>>>(*static_cast<const typename K::Params*>(params));
+    return (int)cudaGetLastError();
+}
+
+template <int A, int B> static int launch_size(int kind, const void* params, unsigned gx, unsigned gy, cudaStream_t s)
+{
+    constexpr int R = x_rows_per_block(A, B);
+    constexpr int T = kStridedLanes;
+    switch (kind) {
+    case FFT_XFWD: return launch<XFwd<A, B, R>>(params, gx, gy, s);
+    case FFT_XINV: return launch<XInv<A, B, R>>(params, gx, gy, s);
+    case FFT_SFWD: return launch<StridedFwd<A, B, T>>(params, gx, gy, s);
+    case FFT_SINV: return launch<StridedInv<A, B, T>>(params, gx, gy, s);
+    case FFT_ZFUSED: return launch<ZFused<A, B, T>>(params, gx, gy, s);
+    }
+    return (int)cudaErrorInvalidValue;
+}
+
+#define MVSIM_CAT_(a, b) a##b
+#define MVSIM_CAT(a, b) MVSIM_CAT_(a, b)
+
+#if MVSIM_GROUP == 0
+#define MVSIM_GROUP_SIZES(X) MVSIM_FFT_SIZES_SMALL(X)
+#elif MVSIM_GROUP == 1
+#define MVSIM_GROUP_SIZES(X) MVSIM_FFT_SIZES_G1(X)
+#elif MVSIM_GROUP == 2
+#define MVSIM_GROUP_SIZES(X) MVSIM_FFT_SIZES_G2(X)
+#elif MVSIM_GROUP == 3
+#define MVSIM_GROUP_SIZES(X) MVSIM_FFT_SIZES_G3(X)
+#else
+#define MVSIM_GROUP_SIZES(X) MVSIM_FFT_SIZES_G4(X)
+#endif
+
+int MVSIM_CAT(fft_launch_g, MVSIM_GROUP)(int kind, int n, const void* params, unsigned gx, unsigned gy, cudaStream_t s)
+{
+    switch (n) {
+#define MVSIM_X(n_, a_, b_) case n_: return launch_size<a_, b_>(kind, params, gx, gy, s);
+        MVSIM_GROUP_SIZES(MVSIM_X)
+#undef MVSIM_X
+    }
+    return -1;
+}
+
+}  // namespace mvsim

@@ -1,0 +1,345 @@
+// Streaming stage kernels of the per-view pipeline (everything except the FFT passes).
+// Reference bodies replaced (S = src/main/java/net/preibisch/simulation):
+//   rotate     S/SimulateMultiViewDataset.java:104-135   (single-threaded cursor loop, 8 virtual gets/voxel)
+//   attenuate  S/SimulateMultiViewDataset.java:318-364   (single-threaded, stride-X walk along y)
+//   sums       S/Tools.java:112-132 (normImage / sumImage, mpicbg RealSum)
+//   adjust     S/Tools.java:143-159
+//   extract    S/SimulateMultiViewDataset.java:195-231 + Poisson S/Tools.java:73-86
+// All of them are HBM-bound; threads map to x (the contiguous axis) so every warp access is a
+// full 128-byte line (float4 where the row length allows).
+#include "ctx.h"
+#include "sampler.cuh"
+
+namespace mvsim {
+
+static inline unsigned blocks_for(size_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
+
+#define MVSIM_LAUNCH_CHECK(ctx)                                                     \
+    do {                                                                            \
+        (ctx)->launches++;                                                          \
+        cudaError_t e__ = cudaGetLastError();                                       \
+        if (e__ != cudaSuccess) return cuda_fail((ctx), e__, "kernel launch");      \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// rotate.  Inverse affine applied in FP64 in mpicbg's evaluation order, floor + fractional weights in
+// FP64, blend in FP32 in imglib2's tap order (000,100,110,010,011,111,101,001), zero outside.
+// ---------------------------------------------------------------------------------------------
+struct Affine { double m[12]; };
+
+// axis 0: x_src == x (row 0 of the inverse is the identity), so the source coordinates are constant
+// along a row and the gather is bilinear in (y,z): VEC contiguous voxels per thread, 4 coalesced loads.
+template <int VEC> __global__ void __launch_bounds__(256) rotate_axis0_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                                            int X, int Y, int Z, Affine a)
+{
+    const int XV = (X + VEC - 1) / VEC;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)XV * Y * Z;
+    if (idx >= total) return;
+    const int xv = (int)(idx % XV);
+    const long long yz = idx / XV;
+    const int y = (int)(yz % Y), z = (int)(yz / Y);
+    const double ly = (double)y, lz = (double)z;
+    // l0*m10 + l1*m11 + l2*m12 + m13 with m10 == 0
+    const double py = __dadd_rn(__dadd_rn(__dmul_rn(ly, a.m[5]), __dmul_rn(lz, a.m[6])), a.m[7]);
+    const double pz = __dadd_rn(__dadd_rn(__dmul_rn(ly, a.m[9]), __dmul_rn(lz, a.m[10])), a.m[11]);
+    const double fy = floor(py), fz = floor(pz);
+    const double wy = py - fy, wz = pz - fz;
+    const double wyi = 1.0 - wy, wzi = 1.0 - wz;
+    // clamp before the int conversion: far outside is simply "no tap"
+    const int iy = (int)fmax(fmin(fy, 2.0e9), -2.0e9), iz = (int)fmax(fmin(fz, 2.0e9), -2.0e9);
+    const float w00 = (float)(wyi * wzi), w10 = (float)(wy * wzi), w11 = (float)(wy * wz), w01 = (float)(wyi * wz);
+    const bool y0 = (unsigned)iy < (unsigned)Y, y1 = (unsigned)(iy + 1) < (unsigned)Y;
+    const bool z0 = (unsigned)iz < (unsigned)Z, z1 = (unsigned)(iz + 1) < (unsigned)Z;
+    const long long x0 = (long long)xv * VEC;
+    const long long r00 = x0 + (long long)X * (iy + (long long)Y * iz);
+    const long long sy = X, sz = (long long)X * Y;
+    float* o = out + x0 + (long long)X * (y + (long long)Y * z);
+    if (VEC == 4) {
+        const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 t00 = (y0 && z0) ? __ldg(reinterpret_cast<const float4*>(in + r00)) : zero;
+        const float4 t10 = (y1 && z0) ? __ldg(reinterpret_cast<const float4*>(in + r00 + sy)) : zero;
+        const float4 t11 = (y1 && z1) ? __ldg(reinterpret_cast<const float4*>(in + r00 + sy + sz)) : zero;
+        const float4 t01 = (y0 && z1) ? __ldg(reinterpret_cast<const float4*>(in + r00 + sz)) : zero;
+        float4 r;
+        r.x = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(t00.x, w00), __fmul_rn(t10.x, w10)), __fmul_rn(t11.x, w11)), __fmul_rn(t01.x, w01));
+        r.y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(t00.y, w00), __fmul_rn(t10.y, w10)), __fmul_rn(t11.y, w11)), __fmul_rn(t01.y, w01));
+        r.z = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(t00.z, w00), __fmul_rn(t10.z, w10)), __fmul_rn(t11.z, w11)), __fmul_rn(t01.z, w01));
+        r.w = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(t00.w, w00), __fmul_rn(t10.w, w10)), __fmul_rn(t11.w, w11)), __fmul_rn(t01.w, w01));
+        *reinterpret_cast<float4*>(o) = r;
+    } else {
+        const float t00 = (y0 && z0) ? __ldg(in + r00) : 0.f;
+        const float t10 = (y1 && z0) ? __ldg(in + r00 + sy) : 0.f;
+        const float t11 = (y1 && z1) ? __ldg(in + r00 + sy + sz) : 0.f;
+        const float t01 = (y0 && z1) ? __ldg(in + r00 + sz) : 0.f;
+        *o = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(t00, w00), __fmul_rn(t10, w10)), __fmul_rn(t11, w11)), __fmul_rn(t01, w01));
+    }
+}
+
+__global__ void __launch_bounds__(256) rotate_general_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                            int X, int Y, int Z, Affine a)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)X * Y * Z;
+    if (idx >= total) return;
+    const int x = (int)(idx % X);
+    const long long yz = idx / X;
+    const int y = (int)(yz % Y), z = (int)(yz / Y);
+    const double l0 = x, l1 = y, l2 = z;
+    double p[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+        p[r] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(l0, a.m[4 * r]), __dmul_rn(l1, a.m[4 * r + 1])), __dmul_rn(l2, a.m[4 * r + 2])), a.m[4 * r + 3]);
+    const double f0 = floor(p[0]), f1 = floor(p[1]), f2 = floor(p[2]);
+    const double w0 = p[0] - f0, w1 = p[1] - f1, w2 = p[2] - f2;
+    const double w0i = 1.0 - w0, w1i = 1.0 - w1, w2i = 1.0 - w2;
+    const int ix = (int)fmax(fmin(f0, 2.0e9), -2.0e9), iy = (int)fmax(fmin(f1, 2.0e9), -2.0e9), iz = (int)fmax(fmin(f2, 2.0e9), -2.0e9);
+    auto tap = [&](int dx, int dy, int dz) -> float {
+        const int xx = ix + dx, yy = iy + dy, zz = iz + dz;
+        if ((unsigned)xx >= (unsigned)X || (unsigned)yy >= (unsigned)Y || (unsigned)zz >= (unsigned)Z) return 0.f;
+        return __ldg(in + xx + (long long)X * (yy + (long long)Y * zz));
+    };
+    float acc = __fmul_rn(tap(0, 0, 0), (float)(w0i * w1i * w2i));
+    acc = __fadd_rn(acc, __fmul_rn(tap(1, 0, 0), (float)(w0 * w1i * w2i)));
+    acc = __fadd_rn(acc, __fmul_rn(tap(1, 1, 0), (float)(w0 * w1 * w2i)));
+    acc = __fadd_rn(acc, __fmul_rn(tap(0, 1, 0), (float)(w0i * w1 * w2i)));
+    acc = __fadd_rn(acc, __fmul_rn(tap(0, 1, 1), (float)(w0i * w1 * w2)));
+    acc = __fadd_rn(acc, __fmul_rn(tap(1, 1, 1), (float)(w0 * w1 * w2)));
+    acc = __fadd_rn(acc, __fmul_rn(tap(1, 0, 1), (float)(w0 * w1i * w2)));
+    acc = __fadd_rn(acc, __fmul_rn(tap(0, 0, 1), (float)(w0i * w1i * w2)));
+    out[idx] = acc;
+}
+
+int k_rotate(mvsim_ctx* ctx, const float* in, float* out, const int64_t dims[3], int axis, const double inv[12])
+{
+    Affine a;
+    for (int i = 0; i < 12; ++i) a.m[i] = inv[i];
+    const int X = (int)dims[0], Y = (int)dims[1], Z = (int)dims[2];
+    // row 0 == identity (up to the rounding of (c^2+s^2) * 1/(c^2+s^2), < 1e-15): bilinear fast path
+    const bool x_identity = axis == 0 && fabs(inv[0] - 1.0) < 1e-12 && inv[1] == 0.0 && inv[2] == 0.0 && inv[3] == 0.0 &&
+                            inv[4] == 0.0 && inv[8] == 0.0;
+    if (x_identity) {
+        const bool vec4 = (X % 4 == 0) && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) % 16 == 0);
+        if (vec4) {
+            const size_t total = (size_t)(X / 4) * Y * Z;
+            rotate_axis0_kernel<4><<<blocks_for(total, 256), 256, 0, ctx->stream>>>(in, out, X, Y, Z, a);
+        } else {
+            const size_t total = (size_t)X * Y * Z;
+            rotate_axis0_kernel<1><<<blocks_for(total, 256), 256, 0, ctx->stream>>>(in, out, X, Y, Z, a);
+        }
+    } else {
+        const size_t total = (size_t)X * Y * Z;
+        rotate_general_kernel<<<blocks_for(total, 256), 256, 0, ctx->stream>>>(in, out, X, Y, Z, a);
+    }
+    MVSIM_LAUNCH_CHECK(ctx);
+    return MVSIM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// attenuate.  One (x,z) column per thread (lanes along x: coalesced), marching from y = Y-1 down;
+// the FP64 recurrence of :343-357 is reproduced operation by operation (no FMA contraction).  The
+// loads do not depend on the recurrence, so they are issued 8 rows ahead.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) attenuate_kernel(const float* __restrict__ in, float* __restrict__ out, int X, int Y, int Z,
+                                                        double delta, int steps)
+{
+    const long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= (long long)X * Z) return;
+    const int x = (int)(col % X), z = (int)(col / X);
+    const long long base = x + (long long)X * Y * z;
+    const float* p = in + base;
+    float* o = out + base;
+    double n = 1.0;
+    int y = Y - 1, s = 0;
+    for (; s + 8 <= steps; s += 8, y -= 8) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __ldg(p + (long long)(y - j) * X);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const double dv = (double)v[j];
+            const double phi = __dmul_rn(__dmul_rn(dv, delta), n);
+            n = fmax(__dsub_rn(n, phi), 0.0);
+            o[(long long)(y - j) * X] = (float)__dmul_rn(dv, n);
+        }
+    }
+    for (; s < steps; ++s, --y) {
+        const double dv = (double)__ldg(p + (long long)y * X);
+        const double phi = __dmul_rn(__dmul_rn(dv, delta), n);
+        n = fmax(__dsub_rn(n, phi), 0.0);
+        o[(long long)y * X] = (float)__dmul_rn(dv, n);
+    }
+    for (; y >= 0; --y) o[(long long)y * X] = 0.f;      // rows the reference loop never reaches stay 0 (:321)
+}
+
+int k_attenuate(mvsim_ctx* ctx, const float* in, float* out, const int64_t dims[3], double delta, int steps)
+{
+    const size_t cols = (size_t)dims[0] * dims[2];
+    attenuate_kernel<<<blocks_for(cols, 128), 128, 0, ctx->stream>>>(in, out, (int)dims[0], (int)dims[1], (int)dims[2], delta, steps);
+    MVSIM_LAUNCH_CHECK(ctx);
+    return MVSIM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// deterministic double sums (RealSum replacement): fixed thread -> element assignment, fixed-order
+// tree in shared memory, fixed-order second stage.  The result depends only on n.
+// ---------------------------------------------------------------------------------------------
+constexpr int kSumThreads = 256;
+constexpr int kSumMaxBlocks = 1184;     // 8 CTAs per SM on 148 SMs
+
+__device__ __forceinline__ double block_tree_sum(double v, double* sm)
+{
+    sm[threadIdx.x] = v;
+    __syncthreads();
+    for (int s = kSumThreads / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) sm[threadIdx.x] += sm[threadIdx.x + s];
+        __syncthreads();
+    }
+    return sm[0];
+}
+
+__global__ void __launch_bounds__(kSumThreads) sum_stage1_kernel(const float* __restrict__ in, size_t n, double* __restrict__ partials)
+{
+    __shared__ double sm[kSumThreads];
+    double acc = 0.0;
+    const size_t stride = (size_t)gridDim.x * kSumThreads;
+    for (size_t i = (size_t)blockIdx.x * kSumThreads + threadIdx.x; i < n; i += stride) acc += (double)__ldg(in + i);
+    const double s = block_tree_sum(acc, sm);
+    if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(kSumThreads) sum_stage2_kernel(const double* __restrict__ partials, size_t n, double* __restrict__ out)
+{
+    __shared__ double sm[kSumThreads];
+    double acc = 0.0;
+    for (size_t i = threadIdx.x; i < n; i += kSumThreads) acc += partials[i];
+    const double s = block_tree_sum(acc, sm);
+    if (threadIdx.x == 0) *out = s;
+}
+
+int k_sum_partials(mvsim_ctx* ctx, const double* partials, size_t n, double* d_sum)
+{
+    sum_stage2_kernel<<<1, kSumThreads, 0, ctx->stream>>>(partials, n, d_sum);
+    MVSIM_LAUNCH_CHECK(ctx);
+    return MVSIM_OK;
+}
+
+int k_sum(mvsim_ctx* ctx, const float* in, size_t n, double* d_sum)
+{
+    unsigned blocks = blocks_for(n, kSumThreads * 16);
+    if (blocks > kSumMaxBlocks) blocks = kSumMaxBlocks;
+    if (blocks < 1) blocks = 1;
+    double* partials = nullptr;
+    MVSIM_TRY(dev_alloc(ctx, (void**)&partials, sizeof(double) * blocks));
+    sum_stage1_kernel<<<blocks, kSumThreads, 0, ctx->stream>>>(in, n, partials);
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    int st = e == cudaSuccess ? k_sum_partials(ctx, partials, blocks, d_sum) : cuda_fail(ctx, e, "sum_stage1_kernel");
+    dev_free(ctx, partials);
+    return st;
+}
+
+// normImage: t = (float)((double)t / sum)   S/Tools.java:116-117
+__global__ void __launch_bounds__(256) divide_by_sum_kernel(float* __restrict__ a, size_t n, const double* __restrict__ d_sum)
+{
+    const double sum = *d_sum;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = (float)((double)a[i] / sum);
+}
+
+int k_divide_by_sum(mvsim_ctx* ctx, float* inout, size_t n, const double* d_sum)
+{
+    divide_by_sum_kernel<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(inout, n, d_sum);
+    MVSIM_LAUNCH_CHECK(ctx);
+    return MVSIM_OK;
+}
+
+// adjustImage: correction = (targetAverage - minValue) / (sum / size)   S/Tools.java:146-147
+__global__ void adjust_corr_kernel(const double* __restrict__ d_sum, double n, float min_value, float target_avg, double* __restrict__ d_corr)
+{
+    const double avg = *d_sum / n;
+    *d_corr = (double)__fsub_rn(target_avg, min_value) / avg;
+}
+
+int k_adjust_corr(mvsim_ctx* ctx, const double* d_sum, size_t n, float min_value, float target_avg, double* d_corr)
+{
+    adjust_corr_kernel<<<1, 1, 0, ctx->stream>>>(d_sum, (double)n, min_value, target_avg, d_corr);
+    MVSIM_LAUNCH_CHECK(ctx);
+    return MVSIM_OK;
+}
+
+// t = (float)(t * correction); t = t + minValue   (two roundings, S/Tools.java:150-155)
+__device__ __forceinline__ float adjust_one(float v, double corr, float min_value)
+{
+    return __fadd_rn((float)__dmul_rn((double)v, corr), min_value);
+}
+
+__global__ void __launch_bounds__(256) adjust_apply_kernel(float* __restrict__ a, size_t n, const double* __restrict__ d_corr, float min_value)
+{
+    const double corr = *d_corr;
+    const size_t i4 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i4 + 4 <= n) {
+        float4 v = *reinterpret_cast<float4*>(a + i4);
+        v.x = adjust_one(v.x, corr, min_value); v.y = adjust_one(v.y, corr, min_value);
+        v.z = adjust_one(v.z, corr, min_value); v.w = adjust_one(v.w, corr, min_value);
+        *reinterpret_cast<float4*>(a + i4) = v;
+    } else {
+        for (size_t i = i4; i < n; ++i) a[i] = adjust_one(a[i], corr, min_value);
+    }
+}
+
+int k_adjust_apply(mvsim_ctx* ctx, float* inout, size_t n, const double* d_corr, float min_value)
+{
+    if (reinterpret_cast<uintptr_t>(inout) % 16 != 0) return set_error(ctx, MVSIM_EINVAL, "adjust: buffer not 16-byte aligned");
+    adjust_apply_kernel<<<blocks_for((n + 3) / 4, 256), 256, 0, ctx->stream>>>(inout, n, d_corr, min_value);
+    MVSIM_LAUNCH_CHECK(ctx);
+    return MVSIM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// extract + (adjust) + Poisson.  One output voxel per thread, x fastest; slice cz of the output is
+// slice cz*inc of the input (:206, integer, bit exact).  lambda = v * mul, mul = (SNR/sqrt 5)^2
+// (S/Tools.java:76); the output is the raw count (S/Tools.java:84).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) extract_kernel(const float* __restrict__ in, float* __restrict__ out, long long plane, long long n_out,
+                                                      int inc, const double* __restrict__ d_corr, float min_value, int noise, double mul,
+                                                      PoissonKey key)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_out) return;
+    const long long cz = i / plane, r = i - cz * plane;
+    float v = __ldg(in + cz * inc * plane + r);
+    if (d_corr) v = adjust_one(v, *d_corr, min_value);
+    if (noise) v = poisson_sample(__dmul_rn((double)v, mul), (uint64_t)i, key);
+    out[i] = v;
+}
+
+static double snr_to_mul(double snr) { const double q = snr / sqrt(5.0); return pow(q, 2.0); }
+
+int k_extract(mvsim_ctx* ctx, const float* in, const int64_t dims[3], int inc, const double* d_corr, float min_value,
+              float snr, uint64_t seed, uint64_t stream, float* out)
+{
+    const long long plane = (long long)dims[0] * dims[1];
+    const long long nz = (dims[2] - 1) / inc + 1;
+    const long long n_out = plane * nz;
+    const int noise = snr >= 0.0f ? 1 : 0;
+    extract_kernel<<<blocks_for((size_t)n_out, 256), 256, 0, ctx->stream>>>(in, out, plane, n_out, inc, d_corr, min_value, noise,
+                                                                         snr_to_mul((double)snr), make_poisson_key(seed, stream));
+    MVSIM_LAUNCH_CHECK(ctx);
+    return MVSIM_OK;
+}
+
+__global__ void __launch_bounds__(256) poisson_kernel(float* __restrict__ a, size_t n, double mul, PoissonKey key)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = poisson_sample(__dmul_rn((double)a[i], mul), (uint64_t)i, key);
+}
+
+int k_poisson(mvsim_ctx* ctx, float* inout, size_t n, double snr, uint64_t seed, uint64_t stream)
+{
+    poisson_kernel<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(inout, n, snr_to_mul(snr), make_poisson_key(seed, stream));
+    MVSIM_LAUNCH_CHECK(ctx);
+    return MVSIM_OK;
+}
+
+}  // namespace mvsim
