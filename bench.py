@@ -204,7 +204,8 @@ def run_ours(args, rank, world, local_rank):
     vox_per_view = int(np.prod(shape))
     oshape = ((shape[0] - 1) // inc + 1, shape[1], shape[2])
 
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()            # a real (non-default) stream shared by torch's events and the library's kernels
+    torch.cuda.set_stream(stream)
     ctx = mv.Context(local_rank, cuda_stream=stream.cuda_stream)
     lib = ctx._lib
 

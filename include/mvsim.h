@@ -79,7 +79,8 @@ enum {
 int mvsim_version(void);
 int mvsim_device_count(int* count);
 int mvsim_ctx_create(int device, mvsim_ctx** ctx);
-/* same, but all work is enqueued on an existing cudaStream_t (e.g. torch's current stream) */
+/* same, but all work is enqueued on an existing cudaStream_t (e.g. torch's current stream; NULL = the
+ * legacy default stream) */
 int mvsim_ctx_create_on_stream(int device, void* cuda_stream, mvsim_ctx** ctx);
 int mvsim_ctx_destroy(mvsim_ctx* ctx);
 int mvsim_ctx_synchronize(mvsim_ctx* ctx);

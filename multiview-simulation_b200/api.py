@@ -51,6 +51,7 @@ class Context:
     """One CUDA device + stream + cached workspaces (mvsim_ctx).  Not shared between threads."""
 
     def __init__(self, device=0, cuda_stream=None):
+        """cuda_stream: None = own stream; an int cudaStream_t handle (0 = legacy default stream) = enqueue there."""
         self._lib = _lib.load()
         h = C.c_void_p()
         if cuda_stream is None:

@@ -265,7 +265,7 @@ int mvsim_device_count(int* count)
     return MVSIM_OK;
 }
 
-int mvsim_ctx_create_on_stream(int device, void* cuda_stream, mvsim_ctx** out)
+static int ctx_create(int device, bool own, void* cuda_stream, mvsim_ctx** out)
 {
     if (!out) return set_error(nullptr, MVSIM_EINVAL, "null output pointer");
     *out = nullptr;
@@ -290,7 +290,7 @@ int mvsim_ctx_create_on_stream(int device, void* cuda_stream, mvsim_ctx** out)
     int st = MVSIM_OK;
     do {
         if ((e = cudaSetDevice(device)) != cudaSuccess) { st = cuda_fail(nullptr, e, "cudaSetDevice"); break; }
-        if (cuda_stream) ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+        if (!own) ctx->stream = static_cast<cudaStream_t>(cuda_stream);     // NULL = the legacy default stream
         else {
             if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) { st = cuda_fail(nullptr, e, "cudaStreamCreate"); break; }
             ctx->own_stream = true;
@@ -313,7 +313,8 @@ int mvsim_ctx_create_on_stream(int device, void* cuda_stream, mvsim_ctx** out)
     return MVSIM_OK;
 }
 
-int mvsim_ctx_create(int device, mvsim_ctx** out) { return mvsim_ctx_create_on_stream(device, nullptr, out); }
+int mvsim_ctx_create(int device, mvsim_ctx** out) { return ctx_create(device, true, nullptr, out); }
+int mvsim_ctx_create_on_stream(int device, void* cuda_stream, mvsim_ctx** out) { return ctx_create(device, false, cuda_stream, out); }
 
 int mvsim_ctx_destroy(mvsim_ctx* ctx)
 {

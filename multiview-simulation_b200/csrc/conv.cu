@@ -1,5 +1,7 @@
 // CUDA backend of the FFT convolution (host logic in fft/conv_driver.h, kernels in fft/line_fft.cuh).
 // Replaces convolve() S/SimulateMultiViewDataset.java:253-264 (FFTConvolution on an ExecutorService).
+#include <stdlib.h>
+
 #include "ctx.h"
 #include "fft/conv_driver.h"
 #include "fft/fft_launch.h"
@@ -11,6 +13,7 @@ namespace {
 struct CudaLauncher {
     mvsim_ctx* ctx;
     bool psf_phase;
+    int lanes;
 
     static int x_blocks(const FftSize& s, int n_rows)
     {
@@ -27,19 +30,20 @@ struct CudaLauncher {
     int launch_x(bool inverse, const FftSize& s, const XParams& q)
     {
         StageTimer t(ctx, psf_phase ? MVSIM_T_PSF : (inverse ? MVSIM_T_FFT_XINV : MVSIM_T_FFT_XFWD));
-        return finish(fft_launch(inverse ? FFT_XINV : FFT_XFWD, s.n, &q, (unsigned)x_blocks(s, q.n_rows), 1, ctx->stream), "x pass");
+        return finish(fft_launch(inverse ? FFT_XINV : FFT_XFWD, lanes, s.n, &q, (unsigned)x_blocks(s, q.n_rows), 1, ctx->stream), "x pass");
     }
     int launch_strided(bool inverse, const FftSize& s, const StridedParams& q, int n_outer)
     {
         StageTimer t(ctx, psf_phase ? MVSIM_T_PSF : (inverse ? MVSIM_T_FFT_YINV : MVSIM_T_FFT_YFWD));
-        const unsigned gx = (unsigned)((q.kx_count + kStridedLanes - 1) / kStridedLanes);
-        return finish(fft_launch(inverse ? FFT_SINV : FFT_SFWD, s.n, &q, gx, (unsigned)n_outer, ctx->stream), "strided pass");
+        const unsigned tiles = (unsigned)((q.kx_count + lanes - 1) / lanes);
+        const unsigned gx = q.swap_grid ? (unsigned)n_outer : tiles, gy = q.swap_grid ? tiles : (unsigned)n_outer;
+        return finish(fft_launch(inverse ? FFT_SINV : FFT_SFWD, lanes, s.n, &q, gx, gy, ctx->stream), "strided pass");
     }
     int launch_zfused(const FftSize& s, const ZFusedParams& q, int n_outer)
     {
         StageTimer t(ctx, MVSIM_T_FFT_ZFUSED);
-        const unsigned gx = (unsigned)((q.kx_count + kStridedLanes - 1) / kStridedLanes);
-        return finish(fft_launch(FFT_ZFUSED, s.n, &q, gx, (unsigned)n_outer, ctx->stream), "fused z pass");
+        const unsigned tiles = (unsigned)((q.kx_count + lanes - 1) / lanes);
+        return finish(fft_launch(FFT_ZFUSED, lanes, s.n, &q, (unsigned)n_outer, tiles, ctx->stream), "fused z pass");
     }
 };
 
@@ -62,6 +66,15 @@ struct Buffers {
 
 }  // namespace
 
+int strided_lanes()
+{
+    static const int lanes = [] {
+        const char* e = getenv("MVSIM_LANES");
+        return (e && atoi(e) == 4) ? 4 : 8;
+    }();
+    return lanes;
+}
+
 int conv_device(mvsim_ctx* ctx, const float* img, const int64_t dims[3], const float* psf, const int64_t kdims[3],
                 float* out, double* d_sum)
 {
@@ -74,16 +87,17 @@ int conv_device(mvsim_ctx* ctx, const float* img, const int64_t dims[3], const f
     MVSIM_TRY(get_tables(ctx, pl.sy.n, &ty));
     MVSIM_TRY(get_tables(ctx, pl.sz.n, &tz));
 
+    const int lanes = strided_lanes();
     Buffers buf(ctx);
     ConvWorkspace ws = {};
     MVSIM_TRY(buf.get(&ws.u1, (size_t)pl.u1_elems()));
-    MVSIM_TRY(buf.get(&ws.u2, (size_t)pl.u2_elems()));
-    MVSIM_TRY(buf.get(&ws.h, (size_t)pl.h_elems()));
+    MVSIM_TRY(buf.get(&ws.u2, (size_t)pl.u2_elems(lanes)));
+    MVSIM_TRY(buf.get(&ws.h, (size_t)pl.h_elems(lanes)));
     MVSIM_TRY(buf.get(&ws.p1, (size_t)pl.p1_elems()));
-    MVSIM_TRY(buf.get(&ws.p2, (size_t)pl.p2_elems()));
+    MVSIM_TRY(buf.get(&ws.p2, (size_t)pl.p2_elems(lanes)));
     ws.tw_x = tx.tw; ws.twist_x = tx.twist; ws.tw_y = ty.tw; ws.tw_z = tz.tw;
 
-    CudaLauncher l = { ctx, true };
+    CudaLauncher l = { ctx, true, lanes };
     MVSIM_TRY(conv_psf_spectrum(l, pl, ws, psf));
     l.psf_phase = false;
     double* partials = nullptr;

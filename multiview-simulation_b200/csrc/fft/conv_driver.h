@@ -5,9 +5,10 @@
 // element kdim/2 at the origin, no conjugation, same-size output).  The padded transforms are
 // "pruned": each pass reads only rows that carry data and writes only rows the next pass needs.
 //
-//   PSF:    xfwd(zero ext) -> P1[KZ][KY][KXc] -> y fwd -> P2[KZ][Ny][KXc] -> z fwd (scaled) -> H[Nz][Ny][KXc]
-//   image:  xfwd(mirror)   -> U1[Z][Y][KXc]  -> y fwd -> U2[Z][Ny][KXc]  -> z fwd * H, z inv (in place)
+//   PSF:    xfwd(zero ext) -> P1[KZ][KY][KXc] -> y fwd -> P2[KT][KZ][Ny][T] -> z fwd (scaled) -> H[KT][Nz][Ny][T]
+//   image:  xfwd(mirror)   -> U1[Z][Y][KXc]  -> y fwd -> U2[KT][Z][Ny][T]  -> z fwd * H, z inv (in place)
 //           -> y inv -> U1[Z][Y][KXc] -> x inv + crop (+ per-block sums) -> out[Z][Y][X]
+// (KT = kx tiles of T columns; the tile-major layouts keep both strided passes local in memory.)
 //
 // `L` is the launcher: the CUDA one enqueues kernels on a stream, the emulation one (tests/emu)
 // executes the same phase functions on the CPU.
@@ -29,62 +30,65 @@ struct ConvWorkspace {
 // PSF (already normalised to sum 1) -> scaled spectrum ws.h
 template <class L> int conv_psf_spectrum(L& l, const ConvPlan& pl, const ConvWorkspace& ws, const float* psf)
 {
-    const long long kxc = pl.kxc();
+    const long long kxc = pl.kxc(), T = l.lanes, ny = pl.sy.n;
     XParams xp = {};
     xp.rin = psf; xp.cout = ws.p1; xp.tw = ws.tw_x; xp.twist = ws.twist_x;
-    xp.X = pl.kdims[0]; xp.n_rows = pl.kdims[1] * pl.kdims[2]; xp.left = 0; xp.zero_ext = 1;
+    xp.X = pl.kdims[0]; xp.n_rows = pl.kdims[1] * pl.kdims[2]; xp.left = 0; xp.ext = EXT_ZERO;
     int err = l.launch_x(false, pl.sx, xp);
     if (err) return err;
 
-    StridedParams sp = {};
+    StridedParams sp = {};      // y: P1 row-major -> P2 tile-major, outer = kz
     sp.in = ws.p1; sp.out = ws.p2; sp.tw = ws.tw_y; sp.kx_count = (int)kxc;
-    sp.n_src = pl.kdims[1]; sp.left = 0; sp.zero_ext = 1;
-    sp.in_estride = kxc; sp.in_ostride = (long long)pl.kdims[1] * kxc;
-    sp.out_estride = kxc; sp.out_ostride = (long long)pl.sy.n * kxc;
-    sp.scale = 1.0f;
+    sp.n_src = pl.kdims[1]; sp.left = 0; sp.ext = EXT_ZERO;
+    sp.in_tstride = T; sp.in_estride = kxc; sp.in_ostride = (long long)pl.kdims[1] * kxc;
+    sp.out_tstride = (long long)pl.kdims[2] * ny * T; sp.out_estride = T; sp.out_ostride = ny * T;
+    sp.swap_grid = 0; sp.scale = 1.0f;
     err = l.launch_strided(false, pl.sy, sp, pl.kdims[2]);
     if (err) return err;
 
-    sp.in = ws.p2; sp.out = ws.h; sp.tw = ws.tw_z;
+    sp.in = ws.p2; sp.out = ws.h; sp.tw = ws.tw_z;   // z: P2 -> H, both tile-major, outer = ky
     sp.n_src = pl.kdims[2];
-    sp.in_estride = (long long)pl.sy.n * kxc; sp.in_ostride = kxc;
-    sp.out_estride = (long long)pl.sy.n * kxc; sp.out_ostride = kxc;
-    sp.scale = (float)pl.scale;
+    sp.in_tstride = (long long)pl.kdims[2] * ny * T; sp.in_estride = ny * T; sp.in_ostride = T;
+    sp.out_tstride = (long long)pl.sz.n * ny * T; sp.out_estride = ny * T; sp.out_ostride = T;
+    sp.swap_grid = 1; sp.scale = (float)pl.scale;
     return l.launch_strided(false, pl.sz, sp, pl.sy.n);
 }
 
 // image -> out, using the spectrum in ws.h.  partials (nullable): one double per x-inverse block.
 template <class L> int conv_apply(L& l, const ConvPlan& pl, const ConvWorkspace& ws, const float* img, float* out, double* partials)
 {
-    const long long kxc = pl.kxc();
+    const long long kxc = pl.kxc(), T = l.lanes, ny = pl.sy.n;
     XParams xp = {};
     xp.rin = img; xp.cout = ws.u1; xp.tw = ws.tw_x; xp.twist = ws.twist_x;
-    xp.X = pl.dims[0]; xp.n_rows = pl.dims[1] * pl.dims[2]; xp.left = pl.left[0]; xp.zero_ext = 0;
+    xp.X = pl.dims[0]; xp.n_rows = pl.dims[1] * pl.dims[2]; xp.left = pl.left[0];
+    xp.ext = mirror_mode(2 * pl.sx.n, pl.left[0], pl.dims[0]);
     int err = l.launch_x(false, pl.sx, xp);
     if (err) return err;
 
-    StridedParams sp = {};
+    StridedParams sp = {};      // y forward: U1 row-major -> U2 tile-major, outer = z
     sp.in = ws.u1; sp.out = ws.u2; sp.tw = ws.tw_y; sp.kx_count = (int)kxc;
-    sp.n_src = pl.dims[1]; sp.left = pl.left[1]; sp.zero_ext = 0;
-    sp.in_estride = kxc; sp.in_ostride = (long long)pl.dims[1] * kxc;
-    sp.out_estride = kxc; sp.out_ostride = (long long)pl.sy.n * kxc;
-    sp.scale = 1.0f;
+    sp.n_src = pl.dims[1]; sp.left = pl.left[1]; sp.ext = mirror_mode(pl.sy.n, pl.left[1], pl.dims[1]);
+    sp.in_tstride = T; sp.in_estride = kxc; sp.in_ostride = (long long)pl.dims[1] * kxc;
+    sp.out_tstride = (long long)pl.dims[2] * ny * T; sp.out_estride = T; sp.out_ostride = ny * T;
+    sp.swap_grid = 0; sp.scale = 1.0f;
     err = l.launch_strided(false, pl.sy, sp, pl.dims[2]);
     if (err) return err;
 
     ZFusedParams zp = {};
     zp.u = ws.u2; zp.h = ws.h; zp.tw = ws.tw_z; zp.kx_count = (int)kxc;
     zp.n_src = pl.dims[2]; zp.left = pl.left[2]; zp.crop0 = pl.crop0[2];
-    zp.estride = (long long)pl.sy.n * kxc; zp.ostride = kxc; zp.h_estride = (long long)pl.sy.n * kxc;
+    zp.ext = mirror_mode(pl.sz.n, pl.left[2], pl.dims[2]);
+    zp.estride = ny * T; zp.ostride = T;
+    zp.u_tstride = (long long)pl.dims[2] * ny * T; zp.h_tstride = (long long)pl.sz.n * ny * T;
     err = l.launch_zfused(pl.sz, zp, pl.sy.n);
     if (err) return err;
 
-    StridedParams ip = {};
+    StridedParams ip = {};      // y inverse: U2 tile-major -> U1 row-major
     ip.in = ws.u2; ip.out = ws.u1; ip.tw = ws.tw_y; ip.kx_count = (int)kxc;
     ip.crop0 = pl.crop0[1]; ip.n_out = pl.dims[1];
-    ip.in_estride = kxc; ip.in_ostride = (long long)pl.sy.n * kxc;
-    ip.out_estride = kxc; ip.out_ostride = (long long)pl.dims[1] * kxc;
-    ip.scale = 1.0f;
+    ip.in_tstride = (long long)pl.dims[2] * ny * T; ip.in_estride = T; ip.in_ostride = ny * T;
+    ip.out_tstride = T; ip.out_estride = kxc; ip.out_ostride = (long long)pl.dims[1] * kxc;
+    ip.swap_grid = 0; ip.scale = 1.0f;
     err = l.launch_strided(true, pl.sy, ip, pl.dims[2]);
     if (err) return err;
 

@@ -60,12 +60,17 @@ struct ConvPlan {
     int crop0[3];           // output voxel o lives at padded index o + crop0 (crop0 = kdim - 1)
     double scale;           // 1 / (sx.n * sy.n * sz.n)
 
+    // Workspaces.  U1/P1 are row-major in kx (written by the x pass row by row); U2/P2/H are kx-TILE-major
+    // [KT][z][ky][T] (T = lanes per CTA of the strided passes): a y line tile is one contiguous chunk
+    // and a z line tile strides by Ny*T elements (73 KB at config 3) instead of Ny*KXc (5.3 MB), which
+    // keeps the z pass inside a few 2 MB pages and DRAM rows.
     int64_t kxc() const { return sx.n; }
-    int64_t u1_elems() const { return (int64_t)dims[2] * dims[1] * sx.n; }          // [Z][Y][KXc]
-    int64_t u2_elems() const { return (int64_t)dims[2] * sy.n * sx.n; }             // [Z][Ny][KXc]
-    int64_t h_elems() const { return (int64_t)sz.n * sy.n * sx.n; }                 // [Nz][Ny][KXc]
-    int64_t p1_elems() const { return (int64_t)kdims[2] * kdims[1] * sx.n; }        // [KZ][KY][KXc]
-    int64_t p2_elems() const { return (int64_t)kdims[2] * sy.n * sx.n; }            // [KZ][Ny][KXc]
+    int64_t ktiles(int t) const { return (sx.n + t - 1) / t; }
+    int64_t u1_elems() const { return (int64_t)dims[2] * dims[1] * sx.n; }               // [Z][Y][KXc]
+    int64_t u2_elems(int t) const { return ktiles(t) * dims[2] * sy.n * t; }             // [KT][Z][Ny][T]
+    int64_t h_elems(int t) const { return ktiles(t) * sz.n * sy.n * t; }                 // [KT][Nz][Ny][T]
+    int64_t p1_elems() const { return (int64_t)kdims[2] * kdims[1] * sx.n; }             // [KZ][KY][KXc]
+    int64_t p2_elems(int t) const { return ktiles(t) * kdims[2] * sy.n * t; }            // [KT][KZ][Ny][T]
 };
 
 // 0 ok, 1 invalid dims, 5 unsupported (too large for the size table)

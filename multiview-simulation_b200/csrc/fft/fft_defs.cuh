@@ -36,4 +36,40 @@ MVSIM_HD int mirror_single(int i, int n)
     return j >= n ? p - j : j;
 }
 
+// Extension modes of the line loaders.  EXT_MIRROR1 is the common case (every padded index folds at most
+// once): branch free, so the unrolled loads of a thread are issued back to back.
+enum { EXT_MIRROR1 = 0, EXT_ZERO = 1, EXT_MIRROR_GENERAL = 2 };
+
+// valid when -(n-1) <= i <= 2(n-1)
+MVSIM_HD int mirror_once(int i, int n)
+{
+    const int a = i < 0 ? -i : i;
+    const int b = 2 * (n - 1) - a;
+    return a < b ? a : b;
+}
+
+// host side: which mode may a loader use for padded length `npad`, margin `left`, source length n?
+inline int mirror_mode(int npad, int left, int n)
+{
+    return (n > 1 && left <= n - 1 && npad - 1 - left <= 2 * (n - 1)) ? EXT_MIRROR1 : EXT_MIRROR_GENERAL;
+}
+
+// 16-byte asynchronous global->shared copy (LDGSTS); plain copy in the CPU emulation
+MVSIM_HD void cp_async16(void* smem_dst, const void* gmem_src)
+{
+#ifdef __CUDA_ARCH__
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
+#else
+    const float4* s4 = static_cast<const float4*>(gmem_src);
+    *static_cast<float4*>(smem_dst) = *s4;
+#endif
+}
+MVSIM_HD void cp_async_wait_all()
+{
+#ifdef __CUDA_ARCH__
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+#endif
+}
+
 }  // namespace mvsim

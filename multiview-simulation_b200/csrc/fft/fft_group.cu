@@ -1,13 +1,20 @@
 // Instantiates the line-FFT kernels (line_fft.cuh) for one group of sizes: -DMVSIM_GROUP=0..4.
 #include "fft_launch.h"
 
-#ifndef MVSIM_GROUP
-#error "compile with -DMVSIM_GROUP=<0..4>"
+#if !defined(MVSIM_GROUP) || !defined(MVSIM_LANES)
+#error "compile with -DMVSIM_GROUP=<0..4> -DMVSIM_LANES=<4|8>"
 #endif
 
 namespace mvsim {
 
-template <class K> __global__ void __launch_bounds__(K::THREADS) fft_kernel(const typename K::Params q)
+// resident CTAs per SM the register allocator must allow, so that the load, exchange and store phases of
+// different tiles overlap: x passes 3 (<= 85 registers at 256 threads), strided passes 2 (T=8) / 4 (T=4).
+template <class K> constexpr int min_blocks()
+{
+    return K::IS_X ? (K::THREADS <= 256 ? 3 : 1) : (K::THREADS <= 160 ? 4 : (K::THREADS <= 288 ? 2 : 1));
+}
+
+template <class K> __global__ void __launch_bounds__(K::THREADS, min_blocks<K>()) fft_kernel(const typename K::Params q)
 {
     extern __shared__ __align__(16) unsigned char smraw[];
     float2* sm = reinterpret_cast<float2*>(smraw);
@@ -33,10 +40,12 @@ template <class K> static int launch(const void* params, unsigned gx, unsigned g
 template <int A, int B> static int launch_size(int kind, const void* params, unsigned gx, unsigned gy, cudaStream_t s)
 {
     constexpr int R = x_rows_per_block(A, B);
-    constexpr int T = kStridedLanes;
+    constexpr int T = MVSIM_LANES;
     switch (kind) {
+#if MVSIM_LANES == 8
     case FFT_XFWD: return launch<XFwd<A, B, R>>(params, gx, gy, s);
     case FFT_XINV: return launch<XInv<A, B, R>>(params, gx, gy, s);
+#endif
     case FFT_SFWD: return launch<StridedFwd<A, B, T>>(params, gx, gy, s);
     case FFT_SINV: return launch<StridedInv<A, B, T>>(params, gx, gy, s);
     case FFT_ZFUSED: return launch<ZFused<A, B, T>>(params, gx, gy, s);
@@ -59,7 +68,8 @@ template <int A, int B> static int launch_size(int kind, const void* params, uns
 #define MVSIM_GROUP_SIZES(X) MVSIM_FFT_SIZES_G4(X)
 #endif
 
-int MVSIM_CAT(fft_launch_g, MVSIM_GROUP)(int kind, int n, const void* params, unsigned gx, unsigned gy, cudaStream_t s)
+#define MVSIM_FN MVSIM_CAT(MVSIM_CAT(MVSIM_CAT(fft_launch_g, MVSIM_GROUP), _t), MVSIM_LANES)
+int MVSIM_FN(int kind, int n, const void* params, unsigned gx, unsigned gy, cudaStream_t s)
 {
     switch (n) {
 #define MVSIM_X(n_, a_, b_) case n_: return launch_size<a_, b_>(kind, params, gx, gy, s);

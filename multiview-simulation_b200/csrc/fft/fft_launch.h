@@ -9,25 +9,38 @@ namespace mvsim {
 
 enum FftKind { FFT_XFWD = 0, FFT_XINV = 1, FFT_SFWD = 2, FFT_SINV = 3, FFT_ZFUSED = 4 };
 
-constexpr int kStridedLanes = 8;     // T: neighbouring kx columns per CTA (64-byte segments)
 constexpr int kXThreadsTarget = 256; // x passes: rows per CTA = kXThreadsTarget / threads-per-line
 
 constexpr int x_rows_per_block(int a, int b) { return (kXThreadsTarget / (a > b ? a : b)) > 0 ? kXThreadsTarget / (a > b ? a : b) : 1; }
 
-// returns cudaError_t as int, or -1 when `n` is not in this group
-int fft_launch_g0(int kind, int n, const void* params, unsigned gx, unsigned gy, cudaStream_t s);
-int fft_launch_g1(int kind, int n, const void* params, unsigned gx, unsigned gy, cudaStream_t s);
-int fft_launch_g2(int kind, int n, const void* params, unsigned gx, unsigned gy, cudaStream_t s);
-int fft_launch_g3(int kind, int n, const void* params, unsigned gx, unsigned gy, cudaStream_t s);
-int fft_launch_g4(int kind, int n, const void* params, unsigned gx, unsigned gy, cudaStream_t s);
+// Lanes (T) = neighbouring kx columns a CTA of the strided passes owns: 8 (64-byte segments, 2 CTAs/SM at
+// the large sizes) or 4 (32-byte sectors, 4 CTAs/SM).  Chosen per context (MVSIM_LANES, default 8); the
+// tile-major workspaces are laid out for the chosen T.
+int strided_lanes();
 
-inline int fft_launch(int kind, int n, const void* params, unsigned gx, unsigned gy, cudaStream_t s)
+// returns cudaError_t as int, or -1 when `n` is not in this group.  One translation unit per (group, lanes).
+#define MVSIM_DECL(g, t) int fft_launch_g##g##_t##t(int kind, int n, const void* params, unsigned gx, unsigned gy, cudaStream_t s);
+MVSIM_DECL(0, 4) MVSIM_DECL(1, 4) MVSIM_DECL(2, 4) MVSIM_DECL(3, 4) MVSIM_DECL(4, 4)
+MVSIM_DECL(0, 8) MVSIM_DECL(1, 8) MVSIM_DECL(2, 8) MVSIM_DECL(3, 8) MVSIM_DECL(4, 8)
+#undef MVSIM_DECL
+
+// x passes do not depend on the lane count; they live in the lanes-8 units
+inline int fft_launch(int kind, int lanes, int n, const void* params, unsigned gx, unsigned gy, cudaStream_t s)
 {
-    int r = fft_launch_g0(kind, n, params, gx, gy, s);
-    if (r == -1) r = fft_launch_g1(kind, n, params, gx, gy, s);
-    if (r == -1) r = fft_launch_g2(kind, n, params, gx, gy, s);
-    if (r == -1) r = fft_launch_g3(kind, n, params, gx, gy, s);
-    if (r == -1) r = fft_launch_g4(kind, n, params, gx, gy, s);
+    int r;
+    if (lanes == 4 && kind >= FFT_SFWD) {
+        r = fft_launch_g0_t4(kind, n, params, gx, gy, s);
+        if (r == -1) r = fft_launch_g1_t4(kind, n, params, gx, gy, s);
+        if (r == -1) r = fft_launch_g2_t4(kind, n, params, gx, gy, s);
+        if (r == -1) r = fft_launch_g3_t4(kind, n, params, gx, gy, s);
+        if (r == -1) r = fft_launch_g4_t4(kind, n, params, gx, gy, s);
+        return r;
+    }
+    r = fft_launch_g0_t8(kind, n, params, gx, gy, s);
+    if (r == -1) r = fft_launch_g1_t8(kind, n, params, gx, gy, s);
+    if (r == -1) r = fft_launch_g2_t8(kind, n, params, gx, gy, s);
+    if (r == -1) r = fft_launch_g3_t8(kind, n, params, gx, gy, s);
+    if (r == -1) r = fft_launch_g4_t8(kind, n, params, gx, gy, s);
     return r;
 }
 

@@ -24,6 +24,7 @@ namespace mvsim {
 
 template <int A_, int B_> struct LineShape {
     static constexpr int A = A_, B = B_;
+    static constexpr bool IS_X = false;
     static constexpr int N = A * B;
     static constexpr int P = A > B ? A : B;   // threads per line
     static constexpr int BP = B | 1;          // odd pitch
@@ -72,6 +73,31 @@ template <int A, int B> MVSIM_HD void inv_second(int p, float2 (&x)[A], const fl
     RegFFT<A, 1>::run(x);
 }
 
+// Gathers x[n1] = ext(line)[p + n1*B - left], n1 < A, from a strided line.  All index arithmetic is done
+// before the first load so the A loads of a thread are in flight together.
+template <int A, int B> MVSIM_HD void gather_line(float2 (&x)[A], const float2* __restrict__ src, long long estride, int p, int left,
+                                                 int n_src, int ext)
+{
+    if (ext == EXT_MIRROR1) {
+        int idx[A];
+        MVSIM_UNROLL
+        for (int n1 = 0; n1 < A; ++n1) idx[n1] = mirror_once(p + n1 * B - left, n_src);
+        MVSIM_UNROLL
+        for (int n1 = 0; n1 < A; ++n1) x[n1] = src[idx[n1] * estride];
+    } else if (ext == EXT_ZERO) {
+        MVSIM_UNROLL
+        for (int n1 = 0; n1 < A; ++n1) {
+            const int n = p + n1 * B - left;
+            const bool ok = (unsigned)n < (unsigned)n_src;
+            const float2 v = src[(ok ? n : 0) * estride];
+            x[n1] = ok ? v : make_float2(0.f, 0.f);
+        }
+    } else {
+        MVSIM_UNROLL
+        for (int n1 = 0; n1 < A; ++n1) x[n1] = src[mirror_single(p + n1 * B - left, n_src) * estride];
+    }
+}
+
 // ==============================================================================================
 // Strided forward pass (y pass, and the z pass of the PSF spectrum).  A CTA owns T neighbouring
 // kx columns (contiguous in memory) of one `outer` slab and transforms them along the strided axis.
@@ -85,9 +111,11 @@ struct StridedParams {
     int kx_count;           // complex columns per row
     int n_src;              // valid source samples along the line
     int left;               // padded index p holds source p - left
-    int zero_ext;           // 0 mirror-single, 1 zero extension
+    int ext;                // EXT_MIRROR1 / EXT_ZERO / EXT_MIRROR_GENERAL (fft_defs.cuh)
     int crop0, n_out;       // inverse: store padded indices [crop0, crop0 + n_out)
     long long in_estride, in_ostride, out_estride, out_ostride;   // in float2 units
+    long long in_tstride, out_tstride;  // stride between kx tiles: T for row-major [..][KXc], Z*N*T for tile-major [KT][..][..][T]
+    int swap_grid;          // 0: blockIdx.x = kx tile, .y = outer; 1: blockIdx.x = outer (neighbouring CTAs share DRAM pages)
     float scale;            // forward: multiplied into the output (folds 1/N and PSF scaling)
 };
 
@@ -105,28 +133,20 @@ template <int A_, int B_, int T_> struct StridedFwd : LineShape<A_, B_> {
     template <int PH> static MVSIM_HD void phase(const Params& q, int bx, int by, int tid, float2* sm, State&)
     {
         const int lane = tid % T, p = tid / T;
-        const int kx = bx * T + lane;
-        const bool active = kx < q.kx_count;
+        const int tile = q.swap_grid ? by : bx, outer = q.swap_grid ? bx : by;
+        const bool active = tile * T + lane < q.kx_count;
         if (PH == 0) {
             if (p < B && active) {
                 float2 x[A];
-                const float2* src = q.in + by * q.in_ostride + kx;
-                MVSIM_UNROLL
-                for (int n1 = 0; n1 < A; ++n1) {
-                    const int n = p + n1 * B - q.left;
-                    if (q.zero_ext) {
-                        x[n1] = (unsigned)n < (unsigned)q.n_src ? src[n * q.in_estride] : make_float2(0.f, 0.f);
-                    } else {
-                        x[n1] = src[mirror_single(n, q.n_src) * q.in_estride];
-                    }
-                }
+                const float2* src = q.in + tile * q.in_tstride + outer * q.in_ostride + lane;
+                gather_line<A, B>(x, src, q.in_estride, p, q.left, q.n_src, q.ext);
                 fwd_first<A, B>(p, x, sm, lane, T, q.tw);
             }
         } else {
             if (p < A && active) {
                 float2 y[B];
                 fwd_second<A, B>(p, y, sm, lane, T);
-                float2* dst = q.out + by * q.out_ostride + kx;
+                float2* dst = q.out + tile * q.out_tstride + outer * q.out_ostride + lane;
                 MVSIM_UNROLL
                 for (int k2 = 0; k2 < B; ++k2)
                     dst[(p + A * k2) * q.out_estride] = make_float2(y[k2].x * q.scale, y[k2].y * q.scale);
@@ -148,12 +168,12 @@ template <int A_, int B_, int T_> struct StridedInv : LineShape<A_, B_> {
     template <int PH> static MVSIM_HD void phase(const Params& q, int bx, int by, int tid, float2* sm, State&)
     {
         const int lane = tid % T, p = tid / T;
-        const int kx = bx * T + lane;
-        const bool active = kx < q.kx_count;
+        const int tile = q.swap_grid ? by : bx, outer = q.swap_grid ? bx : by;
+        const bool active = tile * T + lane < q.kx_count;
         if (PH == 0) {
             if (p < A && active) {
                 float2 y[B];
-                const float2* src = q.in + by * q.in_ostride + kx;
+                const float2* src = q.in + tile * q.in_tstride + outer * q.in_ostride + lane;
                 MVSIM_UNROLL
                 for (int k2 = 0; k2 < B; ++k2) y[k2] = src[(p + A * k2) * q.in_estride];
                 inv_first<A, B>(p, y, sm, lane, T, q.tw);
@@ -162,7 +182,7 @@ template <int A_, int B_, int T_> struct StridedInv : LineShape<A_, B_> {
             if (p < B && active) {
                 float2 x[A];
                 inv_second<A, B>(p, x, sm, lane, T);
-                float2* dst = q.out + by * q.out_ostride + kx;
+                float2* dst = q.out + tile * q.out_tstride + outer * q.out_ostride + lane;
                 MVSIM_UNROLL
                 for (int n1 = 0; n1 < A; ++n1) {
                     const int o = p + n1 * B - q.crop0;
@@ -179,13 +199,15 @@ template <int A_, int B_, int T_> struct StridedInv : LineShape<A_, B_> {
 // In place: a CTA reads its T lines completely before it writes them.
 // ==============================================================================================
 struct ZFusedParams {
-    float2* u;              // [Z][Ny][KXc] in place
-    const float2* h;        // [Nz][Ny][KXc], already scaled by 1/(N*Ny*Nz)
+    float2* u;              // tile-major [KT][Z][Ny][T], in place
+    const float2* h;        // tile-major [KT][Nz][Ny][T], already scaled by 1/(N*Ny*Nz)
     const float2* tw;
     int kx_count, n_src, left, crop0;
-    long long estride;      // z stride of u (= Ny*KXc)
-    long long ostride;      // ky stride (= KXc), same for u and h
-    long long h_estride;    // kz stride of h (= Ny*KXc)
+    int ext;                // EXT_MIRROR1 or EXT_MIRROR_GENERAL
+    long long estride;      // z stride (= Ny*T), same for u and h
+    long long ostride;      // ky stride (= T), same for u and h
+    long long u_tstride;    // kx-tile stride of u (= Z*Ny*T)
+    long long h_tstride;    // kx-tile stride of h (= Nz*Ny*T)
 };
 
 template <int B> struct RegState { float2 y[B]; };
@@ -194,31 +216,41 @@ template <int A_, int B_, int T_> struct ZFused : LineShape<A_, B_> {
     using S = LineShape<A_, B_>;
     static constexpr int A = A_, B = B_, T = T_;
     static constexpr int THREADS = T * S::P;
-    static constexpr int SMEM_BYTES = S::ELEMS * T * (int)sizeof(float2);
+    // exchange area + the H tile [N][T] (prefetched with cp.async while the forward transform runs)
+    static constexpr int SMEM_BYTES = (S::ELEMS + S::N) * T * (int)sizeof(float2);
     static constexpr int NPH = 4;
     using Params = ZFusedParams;
     using State = RegState<B>;
 
     template <int PH> static MVSIM_HD void phase(const Params& q, int bx, int by, int tid, float2* sm, State& st)
     {
+        // blockIdx.x = ky (CTAs that run together touch neighbouring 64-byte chunks of every z plane),
+        // blockIdx.y = kx tile
         const int lane = tid % T, p = tid / T;
-        const int kx = bx * T + lane;
-        const bool active = kx < q.kx_count;
+        const int tile = by, outer = bx;
+        const bool active = tile * T + lane < q.kx_count;
+        float2* smh = sm + S::ELEMS * T;
         if (PH == 0) {
+            {   // H tile -> shared memory, 16 bytes per copy, rows of T float2
+                constexpr int CH = T / 2;       // 16-byte chunks per row
+                const float2* hs = q.h + tile * q.h_tstride + outer * q.ostride;
+                for (int c = tid; c < S::N * CH; c += THREADS) {
+                    const int row = c / CH, part = c % CH;
+                    cp_async16(smh + row * T + part * 2, hs + row * q.estride + part * 2);
+                }
+            }
             if (p < B && active) {
                 float2 x[A];
-                const float2* src = q.u + by * q.ostride + kx;
-                MVSIM_UNROLL
-                for (int n1 = 0; n1 < A; ++n1)
-                    x[n1] = src[mirror_single(p + n1 * B - q.left, q.n_src) * q.estride];
+                const float2* src = q.u + tile * q.u_tstride + outer * q.ostride + lane;
+                gather_line<A, B>(x, src, q.estride, p, q.left, q.n_src, q.ext);
                 fwd_first<A, B>(p, x, sm, lane, T, q.tw);
             }
+            cp_async_wait_all();
         } else if (PH == 1) {
             if (p < A && active) {
                 fwd_second<A, B>(p, st.y, sm, lane, T);
-                const float2* hs = q.h + by * q.ostride + kx;
                 MVSIM_UNROLL
-                for (int k2 = 0; k2 < B; ++k2) st.y[k2] = cmul(st.y[k2], hs[(p + A * k2) * q.h_estride]);
+                for (int k2 = 0; k2 < B; ++k2) st.y[k2] = cmul(st.y[k2], smh[(p + A * k2) * T + lane]);
             }
         } else if (PH == 2) {
             if (p < A && active) inv_first<A, B>(p, st.y, sm, lane, T, q.tw);
@@ -226,7 +258,7 @@ template <int A_, int B_, int T_> struct ZFused : LineShape<A_, B_> {
             if (p < B && active) {
                 float2 x[A];
                 inv_second<A, B>(p, x, sm, lane, T);
-                float2* dst = q.u + by * q.ostride + kx;
+                float2* dst = q.u + tile * q.u_tstride + outer * q.ostride + lane;
                 MVSIM_UNROLL
                 for (int n1 = 0; n1 < A; ++n1) {
                     const int o = p + n1 * B - q.crop0;
@@ -254,23 +286,18 @@ struct XParams {
     const float2* tw;       // exp(-2 pi i m / N)
     const float2* twist;    // exp(-i pi m / 2N)
     double* partials;       // inverse: per-block sums of the stored voxels (may be null)
-    int X, n_rows, left, zero_ext, crop0;
+    int X, n_rows, left, ext, crop0;
 };
 
 template <int A_, int B_, int R_> struct XFwd : LineShape<A_, B_> {
     using S = LineShape<A_, B_>;
+    static constexpr bool IS_X = true;
     static constexpr int A = A_, B = B_, R = R_;
     static constexpr int THREADS = R * S::P;
     static constexpr int SMEM_BYTES = S::ELEMS * R * (int)sizeof(float2);
     static constexpr int NPH = 2;
     using Params = XParams;
     using State = NoState;
-
-    static MVSIM_HD float fetch(const float* row, int i, int n, int zero_ext)
-    {
-        if (zero_ext) return (unsigned)i < (unsigned)n ? row[i] : 0.f;
-        return row[mirror_single(i, n)];
-    }
 
     template <int PH> static MVSIM_HD void phase(const Params& q, int bx, int, int tid, float2* sm, State&)
     {
@@ -281,14 +308,38 @@ template <int A_, int B_, int R_> struct XFwd : LineShape<A_, B_> {
         if (PH == 0) {
             if (p < B && active) {
                 float2 x[A];
-                const float* src = q.rin + row * q.X;
+                const float* __restrict__ src = q.rin + row * q.X;
+                // indices first (branch free in the common modes), then all loads, then the fold + twist
+                float a[A], b[A];
+                if (q.ext == EXT_MIRROR1) {
+                    int ia[A], ib[A];
+                    MVSIM_UNROLL
+                    for (int n1 = 0; n1 < A; ++n1) {
+                        ia[n1] = mirror_once(p + n1 * B - q.left, q.X);
+                        ib[n1] = mirror_once(p + n1 * B + N - q.left, q.X);
+                    }
+                    MVSIM_UNROLL
+                    for (int n1 = 0; n1 < A; ++n1) { a[n1] = src[ia[n1]]; b[n1] = src[ib[n1]]; }
+                } else if (q.ext == EXT_ZERO) {
+                    MVSIM_UNROLL
+                    for (int n1 = 0; n1 < A; ++n1) {
+                        const int i0 = p + n1 * B - q.left, i1 = i0 + N;
+                        const bool ok0 = (unsigned)i0 < (unsigned)q.X, ok1 = (unsigned)i1 < (unsigned)q.X;
+                        const float v0 = src[ok0 ? i0 : 0], v1 = src[ok1 ? i1 : 0];
+                        a[n1] = ok0 ? v0 : 0.f;
+                        b[n1] = ok1 ? v1 : 0.f;
+                    }
+                } else {
+                    MVSIM_UNROLL
+                    for (int n1 = 0; n1 < A; ++n1) {
+                        a[n1] = src[mirror_single(p + n1 * B - q.left, q.X)];
+                        b[n1] = src[mirror_single(p + n1 * B + N - q.left, q.X)];
+                    }
+                }
                 MVSIM_UNROLL
                 for (int n1 = 0; n1 < A; ++n1) {
-                    const int m = p + n1 * B;
-                    const float a = fetch(src, m - q.left, q.X, q.zero_ext);
-                    const float b = fetch(src, m + N - q.left, q.X, q.zero_ext);
-                    const float2 t = q.twist[m];
-                    x[n1] = make_float2(a * t.x + b * t.y, a * t.y - b * t.x);   // (a - i b) * t
+                    const float2 t = q.twist[p + n1 * B];
+                    x[n1] = make_float2(a[n1] * t.x + b[n1] * t.y, a[n1] * t.y - b[n1] * t.x);   // (a - i b) * t
                 }
                 fwd_first<A, B>(p, x, sm, r * S::ELEMS, 1, q.tw);
             }
@@ -306,6 +357,7 @@ template <int A_, int B_, int R_> struct XFwd : LineShape<A_, B_> {
 
 template <int A_, int B_, int R_> struct XInv : LineShape<A_, B_> {
     using S = LineShape<A_, B_>;
+    static constexpr bool IS_X = true;
     static constexpr int A = A_, B = B_, R = R_;
     static constexpr int THREADS = R * S::P;
     // exchange area + per-thread float partials + 32 double partials

@@ -30,6 +30,7 @@ static constexpr int T = 8;
 template <int A, int B> struct Rows { static constexpr int R = (256 / LineShape<A, B>::P) > 0 ? 256 / LineShape<A, B>::P : 1; };
 
 struct EmuLauncher {
+    int lanes = T;
     int x_blocks(const FftSize& s, int n_rows) const
     {
         const int p = s.a > s.b ? s.a : s.b;
@@ -48,9 +49,10 @@ struct EmuLauncher {
     }
     int launch_strided(bool inverse, const FftSize& s, const StridedParams& q, int n_outer)
     {
-        const int gx = (q.kx_count + T - 1) / T;
+        const int tiles = (q.kx_count + T - 1) / T;
+        const int gx = q.swap_grid ? n_outer : tiles, gy = q.swap_grid ? tiles : n_outer;
         switch (s.n) {
-#define MVSIM_X(n_, a_, b_) case n_: if (inverse) emulate<StridedInv<a_, b_, T>>(q, gx, n_outer); else emulate<StridedFwd<a_, b_, T>>(q, gx, n_outer); return 0;
+#define MVSIM_X(n_, a_, b_) case n_: if (inverse) emulate<StridedInv<a_, b_, T>>(q, gx, gy); else emulate<StridedFwd<a_, b_, T>>(q, gx, gy); return 0;
             MVSIM_FFT_SIZES(MVSIM_X)
 #undef MVSIM_X
         }
@@ -58,9 +60,9 @@ struct EmuLauncher {
     }
     int launch_zfused(const FftSize& s, const ZFusedParams& q, int n_outer)
     {
-        const int gx = (q.kx_count + T - 1) / T;
+        const int tiles = (q.kx_count + T - 1) / T;
         switch (s.n) {
-#define MVSIM_X(n_, a_, b_) case n_: emulate<ZFused<a_, b_, T>>(q, gx, n_outer); return 0;
+#define MVSIM_X(n_, a_, b_) case n_: emulate<ZFused<a_, b_, T>>(q, n_outer, tiles); return 0;
             MVSIM_FFT_SIZES(MVSIM_X)
 #undef MVSIM_X
         }
@@ -85,7 +87,7 @@ extern "C" int emu_convolve(const float* img, const int64_t dims[3], const float
     ConvPlan pl;
     int err = make_conv_plan(dims, kdims, &pl);
     if (err) return err;
-    std::vector<float2> u1(pl.u1_elems()), u2(pl.u2_elems()), h(pl.h_elems()), p1(pl.p1_elems()), p2(pl.p2_elems());
+    std::vector<float2> u1(pl.u1_elems()), u2(pl.u2_elems(T)), h(pl.h_elems(T)), p1(pl.p1_elems()), p2(pl.p2_elems(T));
     std::vector<float2> twx(pl.sx.n), twy(pl.sy.n), twz(pl.sz.n), twist(pl.sx.n);
     fill_twiddles(pl.sx.n, &twx[0].x);
     fill_twiddles(pl.sy.n, &twy[0].x);

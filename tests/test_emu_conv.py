@@ -47,7 +47,8 @@ def _run(emu, vol, psfn):
     ((3, 4, 1), (7, 9, 4)),         # kernel larger than the image: multiple mirror folds, X = 1
     ((1, 1, 1), (3, 3, 3)),
     ((30, 17, 40), (1, 1, 1)),      # identity kernel
-    ((20, 33, 50), (9, 3, 13)),     # partial kx tile, several row blocks
+    ((20, 33, 50), (9, 3, 13)),     # several row blocks
+    ((6, 7, 30), (3, 2, 8)),        # 20 complex columns: partial last kx tile of the tile-major layout
 ])
 def test_emulated_kernels_match_direct_convolution(emu, oracle, shape, kshape):
     rng = np.random.default_rng(11)

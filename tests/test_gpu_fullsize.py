@@ -56,7 +56,8 @@ def test_fullsize_view_slice_selection_and_mean(mv):
     acq = S.simulateView(gt, psf, 75, inc=5, poissonSNR=-1.0, ctx=ctx)
     assert acq.shape == (103, 1024, 1024)
     # adjustImage: mean over the whole convolved volume is 1; every 5th slice is an unbiased sample of it
-    assert acq.min() >= np.float32(0.0001) * 0.999
+    # background: minValue +- float32 FFT round-off (the reference's FFT has the same ~1e-7 * max noise)
+    assert acq.min() >= 1e-4 - 1e-6 * float(acq.max())
     assert 0.8 < float(acq.astype(np.float64).mean()) < 1.25
     noisy = S.simulateView(gt, psf, 75, inc=5, poissonSNR=25.0, rnd=3, ctx=ctx)
     lam = acq.astype(np.float64) * 125.0
