@@ -237,8 +237,22 @@ static int dev_simulate_view(mvsim_ctx* ctx, const mvsim_view_params* p, const f
     DevBuf a(ctx), b(ctx);
     MVSIM_TRY(a.alloc(n * sizeof(float)));
     MVSIM_TRY(b.alloc(n * sizeof(float)));
-    MVSIM_TRY(dev_rotate(ctx, gt, a.f(), p->dims, p->axis, p->degrees));                       // :570
-    MVSIM_TRY(dev_attenuate(ctx, a.f(), b.f(), p->dims, p->delta, p->strict_reference));       // :573
+    {
+        // :570 + :573 in one pass (the rotated volume is not part of this entry point's output)
+        double inv[12];
+        int steps;
+        if (axis_rotation(p->dims, p->axis, p->degrees, nullptr, inv)) return set_error(ctx, MVSIM_EINVAL, "simulate_view: bad axis");
+        MVSIM_TRY(attenuate_steps(ctx, p->dims, p->strict_reference, &steps));
+        int st;
+        {
+            StageTimer t(ctx, MVSIM_T_ROTATE);
+            st = k_rotate_attenuate(ctx, gt, b.f(), p->dims, p->axis, inv, p->delta, steps);
+        }
+        if (st == MVSIM_EUNSUPPORTED) {
+            MVSIM_TRY(dev_rotate(ctx, gt, a.f(), p->dims, p->axis, p->degrees));
+            MVSIM_TRY(dev_attenuate(ctx, a.f(), b.f(), p->dims, p->delta, p->strict_reference));
+        } else if (st != MVSIM_OK) return st;
+    }
     MVSIM_TRY(dev_psf_normalize(ctx, psf, elems(p->kdims)));                                   // :255
     MVSIM_TRY(conv_device(ctx, b.f(), p->dims, psf, p->kdims, a.f(), ctx->d_scalars + 1));     // :580
     {

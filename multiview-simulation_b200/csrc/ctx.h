@@ -65,6 +65,8 @@ int get_tables(mvsim_ctx* ctx, int n, mvsim_tables* t);
 
 // stage kernels (stages.cu); all enqueue on ctx->stream
 int k_rotate(mvsim_ctx* ctx, const float* in, float* out, const int64_t dims[3], int axis, const double inv[12]);
+int k_rotate_attenuate(mvsim_ctx* ctx, const float* in, float* out, const int64_t dims[3], int axis, const double inv[12], double delta,
+                       int steps);      // fused; MVSIM_EUNSUPPORTED when the rotation is not the axis-0 fast path
 int k_attenuate(mvsim_ctx* ctx, const float* in, float* out, const int64_t dims[3], double delta, int steps);
 int k_sum(mvsim_ctx* ctx, const float* in, size_t n, double* d_sum);                 // deterministic double sum
 int k_sum_partials(mvsim_ctx* ctx, const double* partials, size_t n, double* d_sum);

@@ -110,6 +110,159 @@ __global__ void __launch_bounds__(256) rotate_general_kernel(const float* __rest
     out[idx] = acc;
 }
 
+// ---------------------------------------------------------------------------------------------
+// fused rotate (axis 0) + attenuate for the whole-view entry point: the rotated volume never goes to HBM.
+// A tiny pre-pass tabulates, per output row (y,z), the source row pair and the four bilinear weights
+// (exactly the arithmetic of rotate_axis0_kernel); the main kernel marches every (x,z) column from
+// y = Y-1 down, gathers the rotated voxel from the ground truth and applies the recurrence of :343-357.
+// ---------------------------------------------------------------------------------------------
+struct __align__(16) RowTaps { int iy, iz; float w00, w10, w11, w01; int pad0, pad1; };
+
+__global__ void __launch_bounds__(256) rotate_rowtable_kernel(RowTaps* __restrict__ tab, int Y, int Z, Affine a)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)Y * Z) return;
+    const int y = (int)(i % Y), z = (int)(i / Y);
+    const double ly = (double)y, lz = (double)z;
+    const double py = __dadd_rn(__dadd_rn(__dmul_rn(ly, a.m[5]), __dmul_rn(lz, a.m[6])), a.m[7]);
+    const double pz = __dadd_rn(__dadd_rn(__dmul_rn(ly, a.m[9]), __dmul_rn(lz, a.m[10])), a.m[11]);
+    const double fy = floor(py), fz = floor(pz);
+    const double wy = py - fy, wz = pz - fz;
+    const double wyi = 1.0 - wy, wzi = 1.0 - wz;
+    RowTaps t;
+    t.iy = (int)fmax(fmin(fy, 2.0e9), -2.0e9);
+    t.iz = (int)fmax(fmin(fz, 2.0e9), -2.0e9);
+    t.w00 = (float)(wyi * wzi); t.w10 = (float)(wy * wzi); t.w11 = (float)(wy * wz); t.w01 = (float)(wyi * wz);
+    t.pad0 = t.pad1 = 0;
+    tab[i] = t;
+}
+
+template <int VEC> struct VecT;
+template <> struct VecT<1> { using type = float; };
+template <> struct VecT<2> { using type = float2; };
+template <> struct VecT<4> { using type = float4; };
+
+template <int VEC> __device__ __forceinline__ void vload(float (&d)[VEC], const float* p, bool ok)
+{
+    using V = typename VecT<VEC>::type;
+    if (ok) {
+        const V v = __ldg(reinterpret_cast<const V*>(p));
+        const float* f = reinterpret_cast<const float*>(&v);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) d[i] = f[i];
+    } else {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) d[i] = 0.f;
+    }
+}
+
+template <int VEC, int U> __global__ void __launch_bounds__(128) rotate_attenuate_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                                                        const RowTaps* __restrict__ tab, int X, int Y, int Z,
+                                                                                        double delta, int steps)
+{
+    using V = typename VecT<VEC>::type;
+    const int XV = X / VEC;
+    const long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= (long long)XV * Z) return;
+    const int x0 = (int)(col % XV) * VEC, z = (int)(col / XV);
+    const long long sy = X, sz = (long long)X * Y;
+    const RowTaps* trow = tab + (long long)Y * z;
+    float* o = out + x0 + sz * z;
+    double n[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) n[i] = 1.0;
+    int y = Y - 1, s = 0;
+    for (; s + U <= steps; s += U, y -= U) {
+        float t00[U][VEC], t10[U][VEC], t11[U][VEC], t01[U][VEC];
+        RowTaps tp[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) tp[j] = trow[y - j];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const int iy = tp[j].iy, iz = tp[j].iz;
+            const bool y0 = (unsigned)iy < (unsigned)Y, y1 = (unsigned)(iy + 1) < (unsigned)Y;
+            const bool z0 = (unsigned)iz < (unsigned)Z, z1 = (unsigned)(iz + 1) < (unsigned)Z;
+            const float* r = in + x0 + sy * iy + sz * iz;
+            vload<VEC>(t00[j], r, y0 && z0);
+            vload<VEC>(t10[j], r + sy, y1 && z0);
+            vload<VEC>(t11[j], r + sy + sz, y1 && z1);
+            vload<VEC>(t01[j], r + sz, y0 && z1);
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            float res[VEC];
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                const float v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(t00[j][i], tp[j].w00), __fmul_rn(t10[j][i], tp[j].w10)),
+                                                    __fmul_rn(t11[j][i], tp[j].w11)), __fmul_rn(t01[j][i], tp[j].w01));
+                const double dv = (double)v;
+                const double phi = __dmul_rn(__dmul_rn(dv, delta), n[i]);
+                n[i] = fmax(__dsub_rn(n[i], phi), 0.0);
+                res[i] = (float)__dmul_rn(dv, n[i]);
+            }
+            *reinterpret_cast<V*>(o + sy * (y - j)) = *reinterpret_cast<V*>(res);
+        }
+    }
+    for (; s < steps; ++s, --y) {
+        const RowTaps t = trow[y];
+        const bool y0 = (unsigned)t.iy < (unsigned)Y, y1 = (unsigned)(t.iy + 1) < (unsigned)Y;
+        const bool z0 = (unsigned)t.iz < (unsigned)Z, z1 = (unsigned)(t.iz + 1) < (unsigned)Z;
+        const float* r = in + x0 + sy * t.iy + sz * t.iz;
+        float a00[VEC], a10[VEC], a11[VEC], a01[VEC], res[VEC];
+        vload<VEC>(a00, r, y0 && z0);
+        vload<VEC>(a10, r + sy, y1 && z0);
+        vload<VEC>(a11, r + sy + sz, y1 && z1);
+        vload<VEC>(a01, r + sz, y0 && z1);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            const float v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a00[i], t.w00), __fmul_rn(a10[i], t.w10)), __fmul_rn(a11[i], t.w11)),
+                                      __fmul_rn(a01[i], t.w01));
+            const double dv = (double)v;
+            const double phi = __dmul_rn(__dmul_rn(dv, delta), n[i]);
+            n[i] = fmax(__dsub_rn(n[i], phi), 0.0);
+            res[i] = (float)__dmul_rn(dv, n[i]);
+        }
+        *reinterpret_cast<V*>(o + sy * y) = *reinterpret_cast<V*>(res);
+    }
+    float zero[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) zero[i] = 0.f;
+    for (; y >= 0; --y) *reinterpret_cast<V*>(o + sy * y) = *reinterpret_cast<V*>(zero);
+}
+
+// returns MVSIM_EUNSUPPORTED when the fused path does not apply (caller falls back to the two kernels)
+int k_rotate_attenuate(mvsim_ctx* ctx, const float* in, float* out, const int64_t dims[3], int axis, const double inv[12], double delta, int steps)
+{
+    const int X = (int)dims[0], Y = (int)dims[1], Z = (int)dims[2];
+    const bool x_identity = axis == 0 && fabs(inv[0] - 1.0) < 1e-12 && inv[1] == 0.0 && inv[2] == 0.0 && inv[3] == 0.0 &&
+                            inv[4] == 0.0 && inv[8] == 0.0;
+    if (!x_identity) return MVSIM_EUNSUPPORTED;
+    Affine a;
+    for (int i = 0; i < 12; ++i) a.m[i] = inv[i];
+    RowTaps* tab = nullptr;
+    MVSIM_TRY(dev_alloc(ctx, (void**)&tab, sizeof(RowTaps) * (size_t)Y * Z));
+    rotate_rowtable_kernel<<<blocks_for((size_t)Y * Z, 256), 256, 0, ctx->stream>>>(tab, Y, Z, a);
+    ctx->launches++;
+    const bool aligned = (reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) % 16 == 0;
+    // the march along y is sequential per column, so the grid is small (X*Z/VEC threads): pick the widest
+    // vector whose single wave still fits the machine (config 3: 131072 threads x float4, 2 rows in flight)
+    if (X % 4 == 0 && aligned) {
+        const size_t cols = (size_t)(X / 4) * Z;
+        rotate_attenuate_kernel<4, 2><<<blocks_for(cols, 128), 128, 0, ctx->stream>>>(in, out, tab, X, Y, Z, delta, steps);
+    } else if (X % 2 == 0 && aligned) {
+        const size_t cols = (size_t)(X / 2) * Z;
+        rotate_attenuate_kernel<2, 4><<<blocks_for(cols, 128), 128, 0, ctx->stream>>>(in, out, tab, X, Y, Z, delta, steps);
+    } else {
+        const size_t cols = (size_t)X * Z;
+        rotate_attenuate_kernel<1, 4><<<blocks_for(cols, 128), 128, 0, ctx->stream>>>(in, out, tab, X, Y, Z, delta, steps);
+    }
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    dev_free(ctx, tab);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "rotate_attenuate_kernel");
+    return MVSIM_OK;
+}
+
 int k_rotate(mvsim_ctx* ctx, const float* in, float* out, const int64_t dims[3], int axis, const double inv[12])
 {
     Affine a;
@@ -301,17 +454,46 @@ int k_adjust_apply(mvsim_ctx* ctx, float* inout, size_t n, const double* d_corr,
 // slice cz*inc of the input (:206, integer, bit exact).  lambda = v * mul, mul = (SNR/sqrt 5)^2
 // (S/Tools.java:76); the output is the raw count (S/Tools.java:84).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) extract_kernel(const float* __restrict__ in, float* __restrict__ out, long long plane, long long n_out,
-                                                      int inc, const double* __restrict__ d_corr, float min_value, int noise, double mul,
-                                                      PoissonKey key)
+// One thread = four consecutive output voxels (one Philox block pair, float4 traffic when the plane size
+// is a multiple of 4 so that the four voxels are also consecutive in the input).
+template <bool VEC4> __global__ void __launch_bounds__(256) extract_kernel(const float* __restrict__ in, float* __restrict__ out, long long plane,
+                                                                          long long n_out, int inc, const double* __restrict__ d_corr,
+                                                                          float min_value, int noise, double mul, PoissonKey key)
 {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_out) return;
-    const long long cz = i / plane, r = i - cz * plane;
-    float v = __ldg(in + cz * inc * plane + r);
-    if (d_corr) v = adjust_one(v, *d_corr, min_value);
-    if (noise) v = poisson_sample(__dmul_rn((double)v, mul), (uint64_t)i, key);
-    out[i] = v;
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long i0 = 4 * g;
+    if (i0 >= n_out) return;
+    float v[4];
+    if (VEC4) {
+        const long long cz = i0 / plane, r = i0 - cz * plane;
+        const float4 t = __ldg(reinterpret_cast<const float4*>(in + cz * inc * plane + r));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const long long i = i0 + k < n_out ? i0 + k : n_out - 1;
+            const long long cz = i / plane, r = i - cz * plane;
+            v[k] = __ldg(in + cz * inc * plane + r);
+        }
+    }
+    if (d_corr) {
+        const double corr = *d_corr;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = adjust_one(v[k], corr, min_value);
+    }
+    if (noise) {
+        double lam[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) lam[k] = __dmul_rn((double)v[k], mul);
+        poisson_group4(lam, (uint64_t)g, key, v);
+    }
+    if (VEC4) {
+        *reinterpret_cast<float4*>(out + i0) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (i0 + k < n_out) out[i0 + k] = v[k];
+    }
 }
 
 static double snr_to_mul(double snr) { const double q = snr / sqrt(5.0); return pow(q, 2.0); }
@@ -323,21 +505,33 @@ int k_extract(mvsim_ctx* ctx, const float* in, const int64_t dims[3], int inc, c
     const long long nz = (dims[2] - 1) / inc + 1;
     const long long n_out = plane * nz;
     const int noise = snr >= 0.0f ? 1 : 0;
-    extract_kernel<<<blocks_for((size_t)n_out, 256), 256, 0, ctx->stream>>>(in, out, plane, n_out, inc, d_corr, min_value, noise,
-                                                                         snr_to_mul((double)snr), make_poisson_key(seed, stream));
+    const bool vec4 = plane % 4 == 0 && (reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) % 16 == 0;
+    const unsigned blocks = blocks_for((size_t)((n_out + 3) / 4), 256);
+    const double mul = snr_to_mul((double)snr);
+    const PoissonKey key = make_poisson_key(seed, stream);
+    if (vec4) extract_kernel<true><<<blocks, 256, 0, ctx->stream>>>(in, out, plane, n_out, inc, d_corr, min_value, noise, mul, key);
+    else extract_kernel<false><<<blocks, 256, 0, ctx->stream>>>(in, out, plane, n_out, inc, d_corr, min_value, noise, mul, key);
     MVSIM_LAUNCH_CHECK(ctx);
     return MVSIM_OK;
 }
 
 __global__ void __launch_bounds__(256) poisson_kernel(float* __restrict__ a, size_t n, double mul, PoissonKey key)
 {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) a[i] = poisson_sample(__dmul_rn((double)a[i], mul), (uint64_t)i, key);
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (4 * g >= n) return;
+    double lam[4];
+    float v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) lam[k] = 4 * g + k < n ? __dmul_rn((double)a[4 * g + k], mul) : 0.0;
+    poisson_group4(lam, (uint64_t)g, key, v);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (4 * g + k < n) a[4 * g + k] = v[k];
 }
 
 int k_poisson(mvsim_ctx* ctx, float* inout, size_t n, double snr, uint64_t seed, uint64_t stream)
 {
-    poisson_kernel<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(inout, n, snr_to_mul(snr), make_poisson_key(seed, stream));
+    poisson_kernel<<<blocks_for((n + 3) / 4, 256), 256, 0, ctx->stream>>>(inout, n, snr_to_mul(snr), make_poisson_key(seed, stream));
     MVSIM_LAUNCH_CHECK(ctx);
     return MVSIM_OK;
 }
