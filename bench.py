@@ -193,10 +193,7 @@ def run_ours(args, rank, world, local_rank):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the CUDA path is the only implementation (no CPU fallback)")
     torch.cuda.set_device(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    grp = mv.Group("nccl", device=torch.device("cuda", local_rank))     # control plane only: barrier, max, sum
 
     shape, kshape, sigma, degrees, inc, snr = WORKLOADS[args.workload]
     degrees = [d + 7 * rank for d in degrees]          # every rank owns different views
@@ -227,16 +224,10 @@ def run_ours(args, rank, world, local_rank):
 
     def barrier():
         torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
+        grp.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(ms):
-        if dist is None:
-            return ms
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    max_over_ranks = grp.max
 
     # ---- device-resident arm -------------------------------------------------------------------------
     for _ in range(args.warmup):
@@ -256,10 +247,7 @@ def run_ours(args, rank, world, local_rank):
     launches = ctx.kernel_launches - launches0
     stage = ctx.stage_times()
     ctx.profile(False)
-    if dist is not None:
-        t = torch.tensor([launches], dtype=torch.int64, device="cuda")
-        dist.all_reduce(t)
-        launches = int(t.item())
+    launches = grp.sum(launches)
     ms_step = ms_total / args.steps
     value = world * nv * vox_per_view / (ms_step * 1e-3)
 
@@ -287,8 +275,7 @@ def run_ours(args, rank, world, local_rank):
     result_checksum = float(out_pin[0].array[::7, ::31, ::29].astype(np.float64).mean())
 
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
+        grp.close()
         return
 
     # ---- roofline of the dominant kernel ------------------------------------------------------------------
@@ -296,7 +283,8 @@ def run_ours(args, rank, world, local_rank):
     check(lib.mvsim_conv_padded_dims(mv._lib.dims3(shape), mv._lib.dims3(kshape), nfft))
     kxc, ny, nz = nfft[0] // 2, nfft[1], nfft[2]
     z_ms, z_n = stage["fft_zfused"]
-    bytes_zfused = 8 * kxc * ny * (2 * shape[0] + nz)       # pruned: read Z planes, read H (Nz), write Z planes
+    planes_out = oshape[0] + 1 if (inc > 1 and oshape[0] + 1 <= shape[0]) else shape[0]
+    bytes_zfused = 8 * kxc * ny * (shape[0] + nz + planes_out)   # read Z planes, read H (Nz planes), write kept planes + sum plane
     S_model = 8 * (nfft[0] // 2 + 1) * ny * nz
     peak, peak_src = measured_peak_gbs()
     per_launch_ms = z_ms / max(z_n, 1)
@@ -328,8 +316,7 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": launches, "roofline": roofline, "stages": stages_ms, "fft_ms_per_launch": fft_passes,
             "fft_padded_xyz": [int(nfft[0]), int(ny), int(nz)], "cpu_baseline": cpu, "clocks": clk}
     print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.destroy_process_group()
+    grp.close()
 
 
 def main():

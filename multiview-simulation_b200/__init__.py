@@ -7,4 +7,5 @@ from . import tiff                                     # noqa: F401
 from ._lib import LIB_PATH, MvsimError, ViewParams     # noqa: F401
 from .api import (Context, DeviceVolume, JavaRandom, PinnedBuffer, SimulateMultiViewDataset, Tools,   # noqa: F401
                   default_context, make_view_params)
+from .distributed import Group                         # noqa: F401
 from .sharding import views_for_rank                   # noqa: F401

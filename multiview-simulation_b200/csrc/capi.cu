@@ -254,12 +254,18 @@ static int dev_simulate_view(mvsim_ctx* ctx, const mvsim_view_params* p, const f
         } else if (st != MVSIM_OK) return st;
     }
     MVSIM_TRY(dev_psf_normalize(ctx, psf, elems(p->kdims)));                                   // :255
-    MVSIM_TRY(conv_device(ctx, b.f(), p->dims, psf, p->kdims, a.f(), ctx->d_scalars + 1));     // :580
+    int planes = 0;
+    MVSIM_TRY(conv_device(ctx, b.f(), p->dims, psf, p->kdims, a.f(), ctx->d_scalars + 1, p->inc, &planes));   // :580
     {
         StageTimer t(ctx, MVSIM_T_ADJUST);                                                     // :582, applied inside the sampler
         MVSIM_TRY(k_adjust_corr(ctx, ctx->d_scalars + 1, n, p->min_value, p->target_avg, ctx->d_scalars + 2));
     }
     StageTimer t(ctx, MVSIM_T_SAMPLE);                                                         // :585
+    if (planes != p->dims[2]) {
+        // the convolution already delivered the kept slices compacted (plus the sum plane, unused here)
+        const int64_t kept[3] = { p->dims[0], p->dims[1], (p->dims[2] - 1) / p->inc + 1 };
+        return k_extract(ctx, a.f(), kept, 1, ctx->d_scalars + 2, p->min_value, p->snr, p->seed, p->stream, out);
+    }
     return k_extract(ctx, a.f(), p->dims, p->inc, ctx->d_scalars + 2, p->min_value, p->snr, p->seed, p->stream, out);
 }
 

@@ -76,7 +76,7 @@ int strided_lanes()
 }
 
 int conv_device(mvsim_ctx* ctx, const float* img, const int64_t dims[3], const float* psf, const int64_t kdims[3],
-                float* out, double* d_sum)
+                float* out, double* d_sum, int keep_inc, int* out_planes)
 {
     ConvPlan pl;
     const int perr = make_conv_plan(dims, kdims, &pl);
@@ -101,9 +101,11 @@ int conv_device(mvsim_ctx* ctx, const float* img, const int64_t dims[3], const f
     MVSIM_TRY(conv_psf_spectrum(l, pl, ws, psf));
     l.psf_phase = false;
     double* partials = nullptr;
-    const int nblocks = CudaLauncher::x_blocks(pl.sx, pl.dims[1] * pl.dims[2]);
+    const int planes = conv_out_planes(pl, keep_inc);
+    if (out_planes) *out_planes = planes;
+    const int nblocks = CudaLauncher::x_blocks(pl.sx, pl.dims[1] * planes);
     if (d_sum) MVSIM_TRY(buf.get(&partials, (size_t)nblocks));
-    MVSIM_TRY(conv_apply(l, pl, ws, img, out, partials));
+    MVSIM_TRY(conv_apply(l, pl, ws, img, out, partials, keep_inc));
     if (d_sum) {
         StageTimer t(ctx, MVSIM_T_ADJUST);
         MVSIM_TRY(k_sum_partials(ctx, partials, (size_t)nblocks, d_sum));

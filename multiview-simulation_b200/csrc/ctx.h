@@ -78,8 +78,10 @@ int k_extract(mvsim_ctx* ctx, const float* in, const int64_t dims[3], int inc, c
               float snr, uint64_t seed, uint64_t stream, float* out);
 int k_poisson(mvsim_ctx* ctx, float* inout, size_t n, double snr, uint64_t seed, uint64_t stream);
 
-// convolution driver (conv.cu): psf normalised, device pointers; partial sums -> d_sum when non-null
+// convolution driver (conv.cu): psf normalised, device pointers; sum of the output voxels -> d_sum when non-null.
+// keep_inc > 1: out receives *out_planes planes -- the slices z = 0, inc, ... and one plane with the sum of the rest
+// (see conv_out_planes in fft/conv_driver.h); d_sum is still the sum over the whole convolved volume.
 int conv_device(mvsim_ctx* ctx, const float* img, const int64_t dims[3], const float* psf, const int64_t kdims[3],
-                float* out, double* d_sum);
+                float* out, double* d_sum, int keep_inc = 1, int* out_planes = nullptr);
 
 }  // namespace mvsim

@@ -54,9 +54,26 @@ template <class L> int conv_psf_spectrum(L& l, const ConvPlan& pl, const ConvWor
     return l.launch_strided(false, pl.sz, sp, pl.sy.n);
 }
 
-// image -> out, using the spectrum in ws.h.  partials (nullable): one double per x-inverse block.
-template <class L> int conv_apply(L& l, const ConvPlan& pl, const ConvWorkspace& ws, const float* img, float* out, double* partials)
+// Number of z planes conv_apply writes.  keep_inc > 1 (whole-view path, extractSlices keeps every inc-th
+// slice, :206): only the kept slices are carried through the inverse y and x passes, plus ONE plane holding
+// the sum over all dropped slices -- by linearity of the inverse transforms its voxel sum is exactly what
+// adjustImage's mean (S/Tools.java:146) needs from them.  The inverse side shrinks by ~inc.
+inline int conv_out_planes(const ConvPlan& pl, int keep_inc)
 {
+    const int z = pl.dims[2];
+    if (keep_inc <= 1) return z;
+    const int kept = (z - 1) / keep_inc + 1;
+    if (z >= 65536 || keep_inc >= 65536) return z;   // range of the multiply-shift division in the kernel
+    return kept + 1 <= z ? kept + 1 : z;       // no room / nothing to gain: plain path
+}
+
+// image -> out, using the spectrum in ws.h.  partials (nullable): one double per x-inverse block.
+// out has conv_out_planes(pl, keep_inc) planes of Y*X floats.
+template <class L> int conv_apply(L& l, const ConvPlan& pl, const ConvWorkspace& ws, const float* img, float* out, double* partials,
+                                  int keep_inc = 1)
+{
+    const int planes = conv_out_planes(pl, keep_inc);
+    const bool pruned = planes != pl.dims[2];
     const long long kxc = pl.kxc(), T = l.lanes, ny = pl.sy.n;
     XParams xp = {};
     xp.rin = img; xp.cout = ws.u1; xp.tw = ws.tw_x; xp.twist = ws.twist_x;
@@ -78,6 +95,7 @@ template <class L> int conv_apply(L& l, const ConvPlan& pl, const ConvWorkspace&
     zp.u = ws.u2; zp.h = ws.h; zp.tw = ws.tw_z; zp.kx_count = (int)kxc;
     zp.n_src = pl.dims[2]; zp.left = pl.left[2]; zp.crop0 = pl.crop0[2];
     zp.ext = mirror_mode(pl.sz.n, pl.left[2], pl.dims[2]);
+    zp.keep_inc = pruned ? keep_inc : 1; zp.n_keep = planes - 1; zp.keep_magic = div_magic((uint32_t)zp.keep_inc);
     zp.estride = ny * T; zp.ostride = T;
     zp.u_tstride = (long long)pl.dims[2] * ny * T; zp.h_tstride = (long long)pl.sz.n * ny * T;
     err = l.launch_zfused(pl.sz, zp, pl.sy.n);
@@ -89,12 +107,12 @@ template <class L> int conv_apply(L& l, const ConvPlan& pl, const ConvWorkspace&
     ip.in_tstride = (long long)pl.dims[2] * ny * T; ip.in_estride = T; ip.in_ostride = ny * T;
     ip.out_tstride = T; ip.out_estride = kxc; ip.out_ostride = (long long)pl.dims[1] * kxc;
     ip.swap_grid = 0; ip.scale = 1.0f;
-    err = l.launch_strided(true, pl.sy, ip, pl.dims[2]);
+    err = l.launch_strided(true, pl.sy, ip, planes);
     if (err) return err;
 
     XParams ix = {};
     ix.cin = ws.u1; ix.rout = out; ix.tw = ws.tw_x; ix.twist = ws.twist_x; ix.partials = partials;
-    ix.X = pl.dims[0]; ix.n_rows = pl.dims[1] * pl.dims[2]; ix.crop0 = pl.crop0[0];
+    ix.X = pl.dims[0]; ix.n_rows = pl.dims[1] * planes; ix.crop0 = pl.crop0[0];
     return l.launch_x(true, pl.sx, ix);
 }
 

@@ -36,6 +36,17 @@ MVSIM_HD int mirror_single(int i, int n)
     return j >= n ? p - j : j;
 }
 
+MVSIM_HD uint32_t umulhi32(uint32_t a, uint32_t b)
+{
+#ifdef __CUDA_ARCH__
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+#endif
+}
+// floor(n / d) == umulhi32(n, div_magic(d)) for n, d < 2^16
+inline uint32_t div_magic(uint32_t d) { return (uint32_t)((0x100000000ull + d - 1) / d); }
+
 // Extension modes of the line loaders.  EXT_MIRROR1 is the common case (every padded index folds at most
 // once): branch free, so the unrolled loads of a thread are issued back to back.
 enum { EXT_MIRROR1 = 0, EXT_ZERO = 1, EXT_MIRROR_GENERAL = 2 };

@@ -23,6 +23,8 @@ template <class K> __global__ void __launch_bounds__(K::THREADS, min_blocks<K>()
     if constexpr (K::NPH > 1) { __syncthreads(); K::template phase<1>(q, blockIdx.x, blockIdx.y, threadIdx.x, sm, st); }
     if constexpr (K::NPH > 2) { __syncthreads(); K::template phase<2>(q, blockIdx.x, blockIdx.y, threadIdx.x, sm, st); }
     if constexpr (K::NPH > 3) { __syncthreads(); K::template phase<3>(q, blockIdx.x, blockIdx.y, threadIdx.x, sm, st); }
+    if constexpr (K::NPH > 4) { __syncthreads(); K::template phase<4>(q, blockIdx.x, blockIdx.y, threadIdx.x, sm, st); }
+    if constexpr (K::NPH > 5) { __syncthreads(); K::template phase<5>(q, blockIdx.x, blockIdx.y, threadIdx.x, sm, st); }
 }
 
 template <class K> static int launch(const void* params, unsigned gx, unsigned gy, cudaStream_t s)

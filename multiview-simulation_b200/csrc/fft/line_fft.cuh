@@ -204,13 +204,16 @@ struct ZFusedParams {
     const float2* tw;
     int kx_count, n_src, left, crop0;
     int ext;                // EXT_MIRROR1 or EXT_MIRROR_GENERAL
+    unsigned keep_magic;    // div_magic(keep_inc)
+    int keep_inc, n_keep;   // keep_inc > 1: store only z = 0, inc, 2 inc, ... compacted to planes 0..n_keep-1 and the SUM of
+                            // all other cropped z in plane n_keep (enough for extractSlices + the mean of adjustImage)
     long long estride;      // z stride (= Ny*T), same for u and h
     long long ostride;      // ky stride (= T), same for u and h
     long long u_tstride;    // kx-tile stride of u (= Z*Ny*T)
     long long h_tstride;    // kx-tile stride of h (= Nz*Ny*T)
 };
 
-template <int B> struct RegState { float2 y[B]; };
+template <int B> struct RegState { float2 y[B]; float2 acc; };
 
 template <int A_, int B_, int T_> struct ZFused : LineShape<A_, B_> {
     using S = LineShape<A_, B_>;
@@ -218,7 +221,7 @@ template <int A_, int B_, int T_> struct ZFused : LineShape<A_, B_> {
     static constexpr int THREADS = T * S::P;
     // exchange area + the H tile [N][T] (prefetched with cp.async while the forward transform runs)
     static constexpr int SMEM_BYTES = (S::ELEMS + S::N) * T * (int)sizeof(float2);
-    static constexpr int NPH = 4;
+    static constexpr int NPH = 6;
     using Params = ZFusedParams;
     using State = RegState<B>;
 
@@ -254,16 +257,38 @@ template <int A_, int B_, int T_> struct ZFused : LineShape<A_, B_> {
             }
         } else if (PH == 2) {
             if (p < A && active) inv_first<A, B>(p, st.y, sm, lane, T, q.tw);
-        } else {
+        } else if (PH == 3) {
+            st.acc = make_float2(0.f, 0.f);
             if (p < B && active) {
                 float2 x[A];
                 inv_second<A, B>(p, x, sm, lane, T);
                 float2* dst = q.u + tile * q.u_tstride + outer * q.ostride + lane;
-                MVSIM_UNROLL
-                for (int n1 = 0; n1 < A; ++n1) {
-                    const int o = p + n1 * B - q.crop0;
-                    if ((unsigned)o < (unsigned)q.n_src) dst[o * q.estride] = x[n1];
+                if (q.keep_inc > 1) {
+                    MVSIM_UNROLL
+                    for (int n1 = 0; n1 < A; ++n1) {
+                        const int o = p + n1 * B - q.crop0;
+                        if ((unsigned)o < (unsigned)q.n_src) {
+                            const int kz = (int)umulhi32((uint32_t)o, q.keep_magic);
+                            if (kz * q.keep_inc == o) dst[kz * q.estride] = x[n1];
+                            else { st.acc.x += x[n1].x; st.acc.y += x[n1].y; }
+                        }
+                    }
+                } else {
+                    MVSIM_UNROLL
+                    for (int n1 = 0; n1 < A; ++n1) {
+                        const int o = p + n1 * B - q.crop0;
+                        if ((unsigned)o < (unsigned)q.n_src) dst[o * q.estride] = x[n1];
+                    }
                 }
+            }
+        } else if (PH == 4) {
+            // (barrier before: every thread is done reading the exchange area) per-line reduction of the dropped planes
+            if (q.keep_inc > 1 && p < B) sm[p * T + lane] = st.acc;
+        } else {
+            if (q.keep_inc > 1 && p == 0 && active) {
+                float2 s = make_float2(0.f, 0.f);
+                for (int j = 0; j < B; ++j) { s.x += sm[j * T + lane].x; s.y += sm[j * T + lane].y; }
+                q.u[tile * q.u_tstride + outer * q.ostride + lane + q.n_keep * q.estride] = s;
             }
         }
     }

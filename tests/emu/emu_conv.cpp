@@ -23,6 +23,8 @@ template <class K> static void emulate(const typename K::Params& q, int gx, int 
             if (K::NPH > 1) for (int t = 0; t < K::THREADS; ++t) K::template phase<1>(q, bx, by, t, sm.data(), st[t]);
             if (K::NPH > 2) for (int t = 0; t < K::THREADS; ++t) K::template phase<2>(q, bx, by, t, sm.data(), st[t]);
             if (K::NPH > 3) for (int t = 0; t < K::THREADS; ++t) K::template phase<3>(q, bx, by, t, sm.data(), st[t]);
+            if (K::NPH > 4) for (int t = 0; t < K::THREADS; ++t) K::template phase<4>(q, bx, by, t, sm.data(), st[t]);
+            if (K::NPH > 5) for (int t = 0; t < K::THREADS; ++t) K::template phase<5>(q, bx, by, t, sm.data(), st[t]);
         }
 }
 
@@ -81,8 +83,9 @@ extern "C" int emu_plan(const int64_t dims[3], const int64_t kdims[3], int out[9
 }
 
 // psf must already be normalised; sum_out (nullable) receives the sum of the output voxels
+// keep_inc > 1: out receives conv_kept_planes(dims, keep_inc) planes (kept slices, then the sum of the others)
 extern "C" int emu_convolve(const float* img, const int64_t dims[3], const float* psf, const int64_t kdims[3],
-                            float* out, double* sum_out)
+                            float* out, double* sum_out, int keep_inc)
 {
     ConvPlan pl;
     int err = make_conv_plan(dims, kdims, &pl);
@@ -100,8 +103,9 @@ extern "C" int emu_convolve(const float* img, const int64_t dims[3], const float
     EmuLauncher l;
     err = conv_psf_spectrum(l, pl, ws, psf);
     if (err) return err;
-    std::vector<double> partials(l.x_blocks(pl.sx, pl.dims[1] * pl.dims[2]), 0.0);
-    err = conv_apply(l, pl, ws, img, out, partials.data());
+    const int planes = conv_out_planes(pl, keep_inc);
+    std::vector<double> partials(l.x_blocks(pl.sx, pl.dims[1] * planes), 0.0);
+    err = conv_apply(l, pl, ws, img, out, partials.data(), keep_inc);
     if (err) return err;
     if (sum_out) { double s = 0; for (double v : partials) s += v; *sum_out = s; }
     return 0;

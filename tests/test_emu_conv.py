@@ -24,19 +24,19 @@ def emu():
         subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-I", CSRC, SRC, "-o", SO])
     L = C.CDLL(SO)
     i64p, fp = C.POINTER(C.c_int64), C.POINTER(C.c_float)
-    L.emu_convolve.argtypes = [fp, i64p, fp, i64p, fp, C.POINTER(C.c_double)]
+    L.emu_convolve.argtypes = [fp, i64p, fp, i64p, fp, C.POINTER(C.c_double), C.c_int]
     L.emu_plan.argtypes = [i64p, i64p, C.POINTER(C.c_int)]
     return L
 
 
-def _run(emu, vol, psfn):
+def _run(emu, vol, psfn, keep_inc=1, planes=None):
     z, y, x = vol.shape
     kz, ky, kx = psfn.shape
-    out = np.empty_like(vol)
+    out = np.empty_like(vol) if planes is None else np.empty((planes, y, x), dtype=np.float32)
     s = C.c_double(0)
     fp = C.POINTER(C.c_float)
     err = emu.emu_convolve(vol.ctypes.data_as(fp), (C.c_int64 * 3)(x, y, z), psfn.ctypes.data_as(fp),
-                           (C.c_int64 * 3)(kx, ky, kz), out.ctypes.data_as(fp), C.byref(s))
+                           (C.c_int64 * 3)(kx, ky, kz), out.ctypes.data_as(fp), C.byref(s), keep_inc)
     assert err == 0
     return out, s.value
 
@@ -71,3 +71,21 @@ def test_plan_sizes_cover_dim_plus_kdim_minus_one(emu):
         assert 2 * out[0] >= dims[0] + kdims[0] - 1
         assert out[1] >= dims[1] + kdims[1] - 1 and out[2] >= dims[2] + kdims[2] - 1
         assert out[3] * out[4] == out[0] and out[5] * out[6] == out[1] and out[7] * out[8] == out[2]
+
+
+@pytest.mark.parametrize("shape,kshape,inc", [((12, 14, 20), (5, 7, 9), 3), ((9, 10, 11), (4, 6, 8), 5), ((7, 6, 9), (3, 3, 3), 2),
+                                              ((10, 5, 8), (2, 3, 3), 9)])
+def test_kept_slices_and_sum_plane(emu, oracle, shape, kshape, inc):
+    """Whole-view path: only every inc-th slice is carried through the inverse passes, plus one plane with
+    the sum of the dropped slices; the total sum (adjustImage's mean) must not change."""
+    rng = np.random.default_rng(12)
+    vol = rng.random(shape, dtype=np.float32)
+    psf = rng.random(kshape, dtype=np.float32)
+    ref = oracle.convolve(vol, psf, "direct")
+    kept = ref[::inc]
+    nk = kept.shape[0]
+    out, s = _run(emu, vol, psf, keep_inc=inc, planes=nk + 1)
+    assert rel_err(out[:nk], kept) < 5e-6
+    dropped = ref.astype(np.float64).sum(axis=0) - kept.astype(np.float64).sum(axis=0)
+    assert rel_err(out[nk], dropped.astype(np.float32)) < 2e-5
+    assert s == pytest.approx(float(ref.astype(np.float64).sum()), rel=2e-6)
