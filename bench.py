@@ -319,13 +319,63 @@ def run_ours(args, rank, world, local_rank):
     grp.close()
 
 
+def run_slab(args, rank, world, local_rank):
+    """BASELINE config 5 (configs[4]): ONE 2048x2048x1024 volume, PSF 256^3, convolve stage only, z slabs over the
+    N GPUs with two NCCL all-to-all transposes per y block (strong scaling).  Not the default bench line."""
+    import torch
+    import mvsim_b200 as mv
+    from helpers import gaussian_psf
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    grp = mv.Group("nccl", device=dev)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx = mv.Context(local_rank, cuda_stream=stream.cuda_stream)
+    shape, kshape = ((1024, 2048, 2048), (256, 256, 256)) if args.workload == "cfg5" else ((256, 512, 512), (64, 64, 64))
+    sc = mv.SlabConvolution(ctx, shape, kshape, grp.rank, grp.world, grp.dist)
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    img = torch.rand((sc.z_local,) + shape[1:], generator=g, device=dev, dtype=torch.float32)     # generated on device, slab-wise
+    psf = gaussian_psf(kshape, (kshape[0] / 7.3, kshape[1] / 23.0, kshape[2] / 25.0), threshold=1e-3)
+    d_psf = torch.from_numpy(psf).to(dev)
+    d_psf /= d_psf.double().sum().float()
+    out = torch.empty_like(img)
+
+    def barrier():
+        torch.cuda.synchronize()
+        grp.barrier()
+        torch.cuda.synchronize()
+    for _ in range(args.warmup):
+        sc.convolve(img, d_psf, out)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        sc.convolve(img, d_psf, out)
+    e1.record(stream)
+    barrier()
+    ms = grp.max(e0.elapsed_time(e1)) / args.steps
+    chk = float(out[::max(1, sc.z_local // 4), ::97, ::89].double().mean().item())
+    if rank == 0:
+        vox = int(np.prod(shape))
+        print(json.dumps({"metric": "convolved voxels/s (slab-decomposed FFT convolution)", "value": vox / (ms * 1e-3), "unit": "voxels/s",
+                          "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                          "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": "BASELINE config 5 (configs[4])" if args.workload == "cfg5" else args.workload,
+                                     "volume_xyz": list(shape[::-1]), "psf_xyz": list(kshape[::-1]), "fft_padded_xyz": list(sc.nfft),
+                                     "y_blocks": sc.y_blocks, "parallelism": f"z slabs x{world}, NCCL all_to_all_single x{2 * sc.y_blocks}"},
+                          "nvlink_bytes_sent_per_rank_per_step": sc.exchange_bytes_per_rank(), "result_checksum": chk}), flush=True)
+    sc.close()
+    grp.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS) + ["cfg5", "cfg5small"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -339,6 +389,9 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
         raise SystemExit(subprocess.call(cmd))
+    if args.workload.startswith("cfg5"):
+        run_slab(args, rank, world, local_rank)
+        return
     run_ours(args, rank, world, local_rank)
 
 

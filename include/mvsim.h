@@ -143,6 +143,28 @@ int mvsim_dev_extract_slices(mvsim_ctx* ctx, const mvsim_volume* in, int inc, fl
 /* gt: ground truth, psf: raw PSF (normalised in place), out: X*Y*((Z-1)/inc+1) */
 int mvsim_dev_simulate_view(mvsim_ctx* ctx, const mvsim_view_params* p, const mvsim_volume* gt, mvsim_volume* psf, mvsim_volume* out);
 
+/* ---- slab-decomposed convolution of one large volume across ranks (BASELINE config 5) -------
+ * convolve (:253-264) for a volume that is distributed by z slabs over `world` GPUs (one process each).
+ * Rank r holds planes [r*Z/world, (r+1)*Z/world) of the image and of the result; x and y passes are local, the
+ * fused z pass runs on kx tiles after an all-to-all transpose and a second all-to-all brings the slabs back.
+ * The library does the passes; the CALLER runs the two exchanges (NCCL all_to_all_single with equal splits)
+ * on the bound buffers between the calls -- their layout is already the send / receive layout:
+ *     prepare;  for block in 0..y_blocks-1:  forward_y(block); [all_to_all send->recv]; middle_z;
+ *                                            [all_to_all recv->send]; inverse_y(block);   finish
+ * world == 1 skips the exchanges (recv buffer unused).  All pointers are DEVICE pointers; the PSF must already
+ * be normalised (mvsim_dev_psf_normalize).  Needs Z % world == 0 and (kx tile count) % world == 0. */
+typedef struct mvsim_slabconv mvsim_slabconv;
+int mvsim_slabconv_create(mvsim_ctx* ctx, const int64_t dims[3], const int64_t kdims[3], int rank, int world, mvsim_slabconv** plan);
+int mvsim_slabconv_destroy(mvsim_ctx* ctx, mvsim_slabconv* plan);
+/* info = { z_local, z0, y_blocks, exchange buffer size in complex64 elements, nfft_x, nfft_y, nfft_z, tiles_own } */
+int mvsim_slabconv_info(const mvsim_slabconv* plan, int64_t info[8]);
+int mvsim_slabconv_bind(mvsim_slabconv* plan, void* send_buffer, void* recv_buffer);
+int mvsim_slabconv_prepare(mvsim_ctx* ctx, mvsim_slabconv* plan, const float* d_psf, const float* d_img_slab);
+int mvsim_slabconv_forward_y(mvsim_ctx* ctx, mvsim_slabconv* plan, int block);
+int mvsim_slabconv_middle_z(mvsim_ctx* ctx, mvsim_slabconv* plan);
+int mvsim_slabconv_inverse_y(mvsim_ctx* ctx, mvsim_slabconv* plan, int block);
+int mvsim_slabconv_finish(mvsim_ctx* ctx, mvsim_slabconv* plan, float* d_out_slab);
+
 #ifdef __cplusplus
 }
 #endif

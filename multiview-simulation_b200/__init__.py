@@ -9,3 +9,4 @@ from .api import (Context, DeviceVolume, JavaRandom, PinnedBuffer, SimulateMulti
                   default_context, make_view_params)
 from .distributed import Group                         # noqa: F401
 from .sharding import views_for_rank                   # noqa: F401
+from .slab import SlabConvolution                      # noqa: F401

@@ -71,6 +71,15 @@ SYMBOLS = [
     ("mvsim_dev_adjust", C.c_int, [_vp, _vp, C.c_float, C.c_float, _dp]),
     ("mvsim_dev_extract_slices", C.c_int, [_vp, _vp, C.c_int, C.c_float, C.c_uint64, C.c_uint64, _vp]),
     ("mvsim_dev_simulate_view", C.c_int, [_vp, C.POINTER(ViewParams), _vp, _vp, _vp]),
+    ("mvsim_slabconv_create", C.c_int, [_vp, _i64p, _i64p, C.c_int, C.c_int, C.POINTER(_vp)]),
+    ("mvsim_slabconv_destroy", C.c_int, [_vp, _vp]),
+    ("mvsim_slabconv_info", C.c_int, [_vp, _i64p]),
+    ("mvsim_slabconv_bind", C.c_int, [_vp, _vp, _vp]),
+    ("mvsim_slabconv_prepare", C.c_int, [_vp, _vp, _vp, _vp]),
+    ("mvsim_slabconv_forward_y", C.c_int, [_vp, _vp, C.c_int]),
+    ("mvsim_slabconv_middle_z", C.c_int, [_vp, _vp]),
+    ("mvsim_slabconv_inverse_y", C.c_int, [_vp, _vp, C.c_int]),
+    ("mvsim_slabconv_finish", C.c_int, [_vp, _vp, _vp]),
 ]
 
 _lib = None

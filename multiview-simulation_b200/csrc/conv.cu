@@ -32,17 +32,17 @@ struct CudaLauncher {
         StageTimer t(ctx, psf_phase ? MVSIM_T_PSF : (inverse ? MVSIM_T_FFT_XINV : MVSIM_T_FFT_XFWD));
         return finish(fft_launch(inverse ? FFT_XINV : FFT_XFWD, lanes, s.n, &q, (unsigned)x_blocks(s, q.n_rows), 1, ctx->stream), "x pass");
     }
-    int launch_strided(bool inverse, const FftSize& s, const StridedParams& q, int n_outer)
+    int launch_strided(bool inverse, const FftSize& s, const StridedParams& q, int n_tiles, int n_outer)
     {
         StageTimer t(ctx, psf_phase ? MVSIM_T_PSF : (inverse ? MVSIM_T_FFT_YINV : MVSIM_T_FFT_YFWD));
-        const unsigned tiles = (unsigned)((q.kx_count + lanes - 1) / lanes);
+        const unsigned tiles = (unsigned)n_tiles;
         const unsigned gx = q.swap_grid ? (unsigned)n_outer : tiles, gy = q.swap_grid ? tiles : (unsigned)n_outer;
         return finish(fft_launch(inverse ? FFT_SINV : FFT_SFWD, lanes, s.n, &q, gx, gy, ctx->stream), "strided pass");
     }
-    int launch_zfused(const FftSize& s, const ZFusedParams& q, int n_outer)
+    int launch_zfused(const FftSize& s, const ZFusedParams& q, int n_tiles, int n_outer)
     {
         StageTimer t(ctx, MVSIM_T_FFT_ZFUSED);
-        const unsigned tiles = (unsigned)((q.kx_count + lanes - 1) / lanes);
+        const unsigned tiles = (unsigned)n_tiles;
         return finish(fft_launch(FFT_ZFUSED, lanes, s.n, &q, (unsigned)n_outer, tiles, ctx->stream), "fused z pass");
     }
 };
@@ -75,37 +75,49 @@ int strided_lanes()
     return lanes;
 }
 
+static int plan_error(mvsim_ctx* ctx, int perr)
+{
+    if (perr == 1) return set_error(ctx, MVSIM_EINVAL, "convolve: bad dims");
+    return set_error(ctx, MVSIM_EUNSUPPORTED,
+                     "convolve: unsupported size (x: X+KX-1 <= 3200, z: Z+KZ-1 <= 1600, KY <= 1600; slabs need Z and the kx tile count "
+                     "divisible by the number of ranks)");
+}
+
 int conv_device(mvsim_ctx* ctx, const float* img, const int64_t dims[3], const float* psf, const int64_t kdims[3],
                 float* out, double* d_sum, int keep_inc, int* out_planes)
 {
+    const int lanes = strided_lanes();
     ConvPlan pl;
-    const int perr = make_conv_plan(dims, kdims, &pl);
-    if (perr == 1) return set_error(ctx, MVSIM_EINVAL, "convolve: bad dims");
-    if (perr) return set_error(ctx, MVSIM_EUNSUPPORTED, "convolve: dim + kdim - 1 exceeds the largest supported FFT line (1600; x: 3200)");
+    int perr = make_conv_plan(dims, kdims, &pl);
+    if (perr) return plan_error(ctx, perr);
+    SlabGeom g;
+    if ((perr = make_slab_geom(pl, lanes, 0, 1, &g))) return plan_error(ctx, perr);
     mvsim_tables tx, ty, tz;
     MVSIM_TRY(get_tables(ctx, pl.sx.n, &tx));
     MVSIM_TRY(get_tables(ctx, pl.sy.n, &ty));
     MVSIM_TRY(get_tables(ctx, pl.sz.n, &tz));
 
-    const int lanes = strided_lanes();
     Buffers buf(ctx);
     ConvWorkspace ws = {};
-    MVSIM_TRY(buf.get(&ws.u1, (size_t)pl.u1_elems()));
-    MVSIM_TRY(buf.get(&ws.u2, (size_t)pl.u2_elems(lanes)));
-    MVSIM_TRY(buf.get(&ws.h, (size_t)pl.h_elems(lanes)));
+    MVSIM_TRY(buf.get(&ws.u1, (size_t)pl.u1_elems(g.z_local)));
+    ws.u1o = ws.u1;
+    if (pl.y_blocks > 1) MVSIM_TRY(buf.get(&ws.u1o, (size_t)pl.u1_elems(g.z_local)));   // blocks still read halo rows of u1
+    MVSIM_TRY(buf.get(&ws.u2, (size_t)pl.u2_elems(lanes, g.z_local)));
+    ws.ex = ws.u2;
+    MVSIM_TRY(buf.get(&ws.h, (size_t)pl.h_elems(lanes, g.tiles_own)));
     MVSIM_TRY(buf.get(&ws.p1, (size_t)pl.p1_elems()));
-    MVSIM_TRY(buf.get(&ws.p2, (size_t)pl.p2_elems(lanes)));
+    MVSIM_TRY(buf.get(&ws.p2, (size_t)pl.p2_elems(lanes, g.tiles_own)));
     ws.tw_x = tx.tw; ws.twist_x = tx.twist; ws.tw_y = ty.tw; ws.tw_z = tz.tw;
 
     CudaLauncher l = { ctx, true, lanes };
-    MVSIM_TRY(conv_psf_spectrum(l, pl, ws, psf));
+    MVSIM_TRY(conv_psf_spectrum(l, pl, g, ws, psf));
     l.psf_phase = false;
     double* partials = nullptr;
-    const int planes = conv_out_planes(pl, keep_inc);
+    const int planes = conv_out_planes(pl, g, keep_inc);
     if (out_planes) *out_planes = planes;
     const int nblocks = CudaLauncher::x_blocks(pl.sx, pl.dims[1] * planes);
     if (d_sum) MVSIM_TRY(buf.get(&partials, (size_t)nblocks));
-    MVSIM_TRY(conv_apply(l, pl, ws, img, out, partials, keep_inc));
+    MVSIM_TRY(conv_apply(l, pl, g, ws, img, out, partials, keep_inc));
     if (d_sum) {
         StageTimer t(ctx, MVSIM_T_ADJUST);
         MVSIM_TRY(k_sum_partials(ctx, partials, (size_t)nblocks, d_sum));
@@ -114,3 +126,141 @@ int conv_device(mvsim_ctx* ctx, const float* img, const int64_t dims[3], const f
 }
 
 }  // namespace mvsim
+
+// ---- slab-decomposed convolution of the largest single volume (BASELINE config 5) ----------------
+// One plan per rank.  The exchange buffers are owned by the caller (torch tensors in the Python
+// orchestrator, so torch.distributed / NCCL can run the two all-to-all transposes on them).
+struct mvsim_slabconv {
+    mvsim::ConvPlan pl;
+    mvsim::SlabGeom g;
+    int lanes;
+    mvsim::ConvWorkspace ws;
+    void* owned[8];
+    int n_owned;
+    float2 *send, *recv;
+};
+
+using namespace mvsim;
+
+extern "C" {
+
+int mvsim_slabconv_create(mvsim_ctx* ctx, const int64_t dims[3], const int64_t kdims[3], int rank, int world, mvsim_slabconv** out)
+{
+    if (!ctx || !dims || !kdims || !out) return set_error(ctx, MVSIM_EINVAL, "slabconv_create: null argument");
+    *out = nullptr;
+    mvsim_slabconv* p = new mvsim_slabconv();
+    p->lanes = strided_lanes();
+    p->n_owned = 0;
+    p->send = p->recv = nullptr;
+    int perr = make_conv_plan(dims, kdims, &p->pl);
+    if (!perr) perr = make_slab_geom(p->pl, p->lanes, rank, world, &p->g);
+    if (perr) { delete p; return plan_error(ctx, perr); }
+    int st = MVSIM_OK;
+    mvsim_tables tx, ty, tz;
+    auto grab = [&](float2** dst, size_t elems) {
+        if (st != MVSIM_OK) return;
+        void* q = nullptr;
+        cudaError_t e = cudaMalloc(&q, (elems ? elems : 1) * sizeof(float2));
+        if (e != cudaSuccess) { st = cuda_fail(ctx, e, "cudaMalloc(slabconv workspace)"); return; }
+        p->owned[p->n_owned++] = q;
+        *dst = static_cast<float2*>(q);
+    };
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(ctx->device);
+    if ((st = get_tables(ctx, p->pl.sx.n, &tx)) == MVSIM_OK && (st = get_tables(ctx, p->pl.sy.n, &ty)) == MVSIM_OK &&
+        (st = get_tables(ctx, p->pl.sz.n, &tz)) == MVSIM_OK) {
+        p->ws = ConvWorkspace{};
+        grab(&p->ws.u1, (size_t)p->pl.u1_elems(p->g.z_local));
+        p->ws.u1o = p->ws.u1;
+        if (p->pl.y_blocks > 1) grab(&p->ws.u1o, (size_t)p->pl.u1_elems(p->g.z_local));
+        grab(&p->ws.h, (size_t)p->pl.h_elems(p->lanes, p->g.tiles_own));
+        grab(&p->ws.p1, (size_t)p->pl.p1_elems());
+        grab(&p->ws.p2, (size_t)p->pl.p2_elems(p->lanes, p->g.tiles_own));
+        p->ws.tw_x = tx.tw; p->ws.twist_x = tx.twist; p->ws.tw_y = ty.tw; p->ws.tw_z = tz.tw;
+    }
+    if (prev >= 0) cudaSetDevice(prev);
+    if (st != MVSIM_OK) {
+        for (int i = 0; i < p->n_owned; ++i) cudaFree(p->owned[i]);
+        delete p;
+        return st;
+    }
+    *out = p;
+    return MVSIM_OK;
+}
+
+int mvsim_slabconv_destroy(mvsim_ctx* ctx, mvsim_slabconv* p)
+{
+    if (!p) return MVSIM_OK;
+    if (ctx) cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < p->n_owned; ++i) cudaFree(p->owned[i]);
+    delete p;
+    return MVSIM_OK;
+}
+
+int mvsim_slabconv_info(const mvsim_slabconv* p, int64_t info[8])
+{
+    if (!p || !info) return MVSIM_EINVAL;
+    info[0] = p->g.z_local; info[1] = p->g.z0; info[2] = p->pl.y_blocks;
+    info[3] = p->pl.u2_elems(p->lanes, p->g.z_local);         // float2 elements of each exchange buffer
+    info[4] = 2 * p->pl.sx.n; info[5] = p->pl.sy.n; info[6] = p->pl.sz.n;
+    info[7] = p->g.tiles_own;
+    return MVSIM_OK;
+}
+
+int mvsim_slabconv_bind(mvsim_slabconv* p, void* send_buffer, void* recv_buffer)
+{
+    if (!p || !send_buffer || (p->g.world > 1 && !recv_buffer)) return MVSIM_EINVAL;
+    p->send = static_cast<float2*>(send_buffer);
+    p->recv = p->g.world > 1 ? static_cast<float2*>(recv_buffer) : p->send;
+    p->ws.u2 = p->send;
+    p->ws.ex = p->recv;
+    return MVSIM_OK;
+}
+
+#define MVSIM_SLAB_ENTER(ctx, p)                                                                   \
+    if (!(ctx) || !(p)) return mvsim::set_error((ctx), MVSIM_EINVAL, "slabconv: null argument");   \
+    if (!(p)->send) return mvsim::set_error((ctx), MVSIM_EINVAL, "slabconv: bind the exchange buffers first")
+
+int mvsim_slabconv_prepare(mvsim_ctx* ctx, mvsim_slabconv* p, const float* d_psf, const float* d_img_slab)
+{
+    MVSIM_SLAB_ENTER(ctx, p);
+    if (!d_psf || !d_img_slab) return set_error(ctx, MVSIM_EINVAL, "slabconv_prepare: null buffer");
+    CudaLauncher l = { ctx, true, p->lanes };
+    MVSIM_TRY(conv_psf_spectrum(l, p->pl, p->g, p->ws, d_psf));
+    l.psf_phase = false;
+    return conv_forward_x(l, p->pl, p->g, p->ws, d_img_slab);
+}
+
+int mvsim_slabconv_forward_y(mvsim_ctx* ctx, mvsim_slabconv* p, int block)
+{
+    MVSIM_SLAB_ENTER(ctx, p);
+    if (block < 0 || block >= p->pl.y_blocks) return set_error(ctx, MVSIM_EINVAL, "slabconv: bad block");
+    CudaLauncher l = { ctx, false, p->lanes };
+    return conv_forward_y(l, p->pl, p->g, p->ws, block);
+}
+
+int mvsim_slabconv_middle_z(mvsim_ctx* ctx, mvsim_slabconv* p)
+{
+    MVSIM_SLAB_ENTER(ctx, p);
+    CudaLauncher l = { ctx, false, p->lanes };
+    return conv_middle_z(l, p->pl, p->g, p->ws, p->ws.ex, 1);
+}
+
+int mvsim_slabconv_inverse_y(mvsim_ctx* ctx, mvsim_slabconv* p, int block)
+{
+    MVSIM_SLAB_ENTER(ctx, p);
+    if (block < 0 || block >= p->pl.y_blocks) return set_error(ctx, MVSIM_EINVAL, "slabconv: bad block");
+    CudaLauncher l = { ctx, false, p->lanes };
+    return conv_inverse_y(l, p->pl, p->g, p->ws, block, p->g.z_local);
+}
+
+int mvsim_slabconv_finish(mvsim_ctx* ctx, mvsim_slabconv* p, float* d_out_slab)
+{
+    MVSIM_SLAB_ENTER(ctx, p);
+    if (!d_out_slab) return set_error(ctx, MVSIM_EINVAL, "slabconv_finish: null buffer");
+    CudaLauncher l = { ctx, false, p->lanes };
+    return conv_inverse_x(l, p->pl, p->ws, d_out_slab, nullptr, p->g.z_local);
+}
+
+}  // extern "C"

@@ -5,10 +5,16 @@
 // element kdim/2 at the origin, no conjugation, same-size output).  The padded transforms are
 // "pruned": each pass reads only rows that carry data and writes only rows the next pass needs.
 //
-//   PSF:    xfwd(zero ext) -> P1[KZ][KY][KXc] -> y fwd -> P2[KT][KZ][Ny][T] -> z fwd (scaled) -> H[KT][Nz][Ny][T]
-//   image:  xfwd(mirror)   -> U1[Z][Y][KXc]  -> y fwd -> U2[KT][Z][Ny][T]  -> z fwd * H, z inv (in place)
-//           -> y inv -> U1[Z][Y][KXc] -> x inv + crop (+ per-block sums) -> out[Z][Y][X]
-// (KT = kx tiles of T columns; the tile-major layouts keep both strided passes local in memory.)
+//   PSF:    xfwd(zero ext) -> P1[KZ][KY][KXc] -> y fwd -> P2[tiles][KZ][Ny][T] -> z fwd (scaled) -> H[tiles][Nz][Ny][T]
+//   image:  xfwd(mirror)   -> U1[Zl][Y][KXc]
+//           per y block:  y fwd -> U2[KT][Zl][Ny][T]  ==(all-to-all when world > 1)==>  [S][tiles][Zl][Ny][T]
+//                         z fwd * H, z inv (in place)  ==(all-to-all back)==>  U2 -> y inv -> U1'[planes][Y][KXc]
+//           x inv + crop (+ per-block sums) -> out[planes][Y][X]
+// KT = kx tiles of T columns.  On one GPU (world = 1) Zl = Z, tiles = KT, S = 1 and there is no exchange.
+// Slab decomposition (largest single volume): a rank owns Zl = Z/world planes for the x and y passes and
+// KT/world tiles (with all planes) for the z pass; U2 viewed as [world][tiles][Zl][Ny][T] is at once the
+// all-to-all SEND layout (destination major, contiguous equal chunks) and, after the exchange, the
+// segmented layout the fused z pass addresses directly -- pack and unpack are folded into the passes.
 //
 // `L` is the launcher: the CUDA one enqueues kernels on a stream, the emulation one (tests/emu)
 // executes the same phase functions on the CPU.
@@ -19,16 +25,18 @@
 namespace mvsim {
 
 struct ConvWorkspace {
-    float2* u1;     // u1_elems
-    float2* u2;     // u2_elems
-    float2* h;      // h_elems
+    float2* u1;     // u1_elems(z_local): forward x spectra
+    float2* u1o;    // inverse-side rows; may alias u1 when there is a single y block
+    float2* u2;     // u2_elems(T, z_local): y-pass output = exchange send buffer
+    float2* ex;     // exchange receive buffer (== u2 when world == 1)
+    float2* h;      // h_elems(T, tiles_own)
     float2* p1;     // p1_elems
-    float2* p2;     // p2_elems
+    float2* p2;     // p2_elems(T, tiles_own)
     const float2 *tw_x, *tw_y, *tw_z, *twist_x;   // tables for sx.n, sy.n, sz.n
 };
 
-// PSF (already normalised to sum 1) -> scaled spectrum ws.h
-template <class L> int conv_psf_spectrum(L& l, const ConvPlan& pl, const ConvWorkspace& ws, const float* psf)
+// PSF (already normalised to sum 1) -> scaled spectrum ws.h for this rank's tiles
+template <class L> int conv_psf_spectrum(L& l, const ConvPlan& pl, const SlabGeom& g, const ConvWorkspace& ws, const float* psf)
 {
     const long long kxc = pl.kxc(), T = l.lanes, ny = pl.sy.n;
     XParams xp = {};
@@ -37,13 +45,14 @@ template <class L> int conv_psf_spectrum(L& l, const ConvPlan& pl, const ConvWor
     int err = l.launch_x(false, pl.sx, xp);
     if (err) return err;
 
-    StridedParams sp = {};      // y: P1 row-major -> P2 tile-major, outer = kz
+    StridedParams sp = {};      // y: P1 row-major -> P2 tile-major (own tiles), outer = kz
     sp.in = ws.p1; sp.out = ws.p2; sp.tw = ws.tw_y; sp.kx_count = (int)kxc;
     sp.n_src = pl.kdims[1]; sp.left = 0; sp.ext = EXT_ZERO;
     sp.in_tstride = T; sp.in_estride = kxc; sp.in_ostride = (long long)pl.kdims[1] * kxc;
     sp.out_tstride = (long long)pl.kdims[2] * ny * T; sp.out_estride = T; sp.out_ostride = ny * T;
     sp.swap_grid = 0; sp.scale = 1.0f;
-    err = l.launch_strided(false, pl.sy, sp, pl.kdims[2]);
+    sp.tile0 = g.tile0; sp.in_tile_global = 1; sp.out_tile_global = 0;
+    err = l.launch_strided(false, pl.sy, sp, g.tiles_own, pl.kdims[2]);
     if (err) return err;
 
     sp.in = ws.p2; sp.out = ws.h; sp.tw = ws.tw_z;   // z: P2 -> H, both tile-major, outer = ky
@@ -51,69 +60,113 @@ template <class L> int conv_psf_spectrum(L& l, const ConvPlan& pl, const ConvWor
     sp.in_tstride = (long long)pl.kdims[2] * ny * T; sp.in_estride = ny * T; sp.in_ostride = T;
     sp.out_tstride = (long long)pl.sz.n * ny * T; sp.out_estride = ny * T; sp.out_ostride = T;
     sp.swap_grid = 1; sp.scale = (float)pl.scale;
-    return l.launch_strided(false, pl.sz, sp, pl.sy.n);
+    sp.in_tile_global = 0; sp.out_tile_global = 0;
+    return l.launch_strided(false, pl.sz, sp, g.tiles_own, pl.sy.n);
 }
 
-// Number of z planes conv_apply writes.  keep_inc > 1 (whole-view path, extractSlices keeps every inc-th
-// slice, :206): only the kept slices are carried through the inverse y and x passes, plus ONE plane holding
-// the sum over all dropped slices -- by linearity of the inverse transforms its voxel sum is exactly what
-// adjustImage's mean (S/Tools.java:146) needs from them.  The inverse side shrinks by ~inc.
-inline int conv_out_planes(const ConvPlan& pl, int keep_inc)
+// x forward of this rank's planes: img [Zl][Y][X] -> ws.u1
+template <class L> int conv_forward_x(L& l, const ConvPlan& pl, const SlabGeom& g, const ConvWorkspace& ws, const float* img)
+{
+    XParams xp = {};
+    xp.rin = img; xp.cout = ws.u1; xp.tw = ws.tw_x; xp.twist = ws.twist_x;
+    xp.X = pl.dims[0]; xp.n_rows = pl.dims[1] * g.z_local; xp.left = pl.left[0];
+    xp.ext = mirror_mode(2 * pl.sx.n, pl.left[0], pl.dims[0]);
+    return l.launch_x(false, pl.sx, xp);
+}
+
+// y forward of block b: ws.u1 -> ws.u2 [KT][Zl][Ny][T]
+template <class L> int conv_forward_y(L& l, const ConvPlan& pl, const SlabGeom& g, const ConvWorkspace& ws, int b)
+{
+    const long long kxc = pl.kxc(), T = l.lanes, ny = pl.sy.n;
+    StridedParams sp = {};
+    sp.in = ws.u1; sp.out = ws.u2; sp.tw = ws.tw_y; sp.kx_count = (int)kxc;
+    sp.n_src = pl.dims[1];
+    sp.left = pl.left[1] - b * pl.y_block;       // padded index q of block b holds source row q - left[1] + b*y_block
+    // the mirror may be evaluated branch free when every padded index folds at most once
+    {
+        const int lo = -sp.left, hi = pl.sy.n - 1 - sp.left;
+        sp.ext = (pl.dims[1] > 1 && lo >= -(pl.dims[1] - 1) && hi <= 2 * (pl.dims[1] - 1)) ? EXT_MIRROR1 : EXT_MIRROR_GENERAL;
+    }
+    sp.in_tstride = T; sp.in_estride = kxc; sp.in_ostride = (long long)pl.dims[1] * kxc;
+    sp.out_tstride = (long long)g.z_local * ny * T; sp.out_estride = T; sp.out_ostride = ny * T;
+    sp.swap_grid = 0; sp.scale = 1.0f;
+    sp.tile0 = 0; sp.in_tile_global = 1; sp.out_tile_global = 1;
+    return l.launch_strided(false, pl.sy, sp, g.tiles_total, g.z_local);
+}
+
+// Number of z planes the inverse side carries.  keep_inc > 1 (whole-view path on one GPU, extractSlices keeps
+// every inc-th slice, :206): only the kept slices go through the inverse y and x passes, plus ONE plane
+// holding the sum over all dropped slices -- by linearity of the inverse transforms its voxel sum is exactly
+// what adjustImage's mean (S/Tools.java:146) needs from them.  The inverse side shrinks by ~inc.
+inline int conv_out_planes(const ConvPlan& pl, const SlabGeom& g, int keep_inc)
 {
     const int z = pl.dims[2];
+    if (g.world > 1) return g.z_local;
     if (keep_inc <= 1) return z;
     const int kept = (z - 1) / keep_inc + 1;
     if (z >= 65536 || keep_inc >= 65536) return z;   // range of the multiply-shift division in the kernel
     return kept + 1 <= z ? kept + 1 : z;       // no room / nothing to gain: plain path
 }
 
-// image -> out, using the spectrum in ws.h.  partials (nullable): one double per x-inverse block.
-// out has conv_out_planes(pl, keep_inc) planes of Y*X floats.
-template <class L> int conv_apply(L& l, const ConvPlan& pl, const ConvWorkspace& ws, const float* img, float* out, double* partials,
-                                  int keep_inc = 1)
+// fused z pass on this rank's tiles, in place on buf = [S][tiles][Zl][Ny][T]
+template <class L> int conv_middle_z(L& l, const ConvPlan& pl, const SlabGeom& g, const ConvWorkspace& ws, float2* buf, int keep_inc)
 {
-    const int planes = conv_out_planes(pl, keep_inc);
-    const bool pruned = planes != pl.dims[2];
-    const long long kxc = pl.kxc(), T = l.lanes, ny = pl.sy.n;
-    XParams xp = {};
-    xp.rin = img; xp.cout = ws.u1; xp.tw = ws.tw_x; xp.twist = ws.twist_x;
-    xp.X = pl.dims[0]; xp.n_rows = pl.dims[1] * pl.dims[2]; xp.left = pl.left[0];
-    xp.ext = mirror_mode(2 * pl.sx.n, pl.left[0], pl.dims[0]);
-    int err = l.launch_x(false, pl.sx, xp);
-    if (err) return err;
-
-    StridedParams sp = {};      // y forward: U1 row-major -> U2 tile-major, outer = z
-    sp.in = ws.u1; sp.out = ws.u2; sp.tw = ws.tw_y; sp.kx_count = (int)kxc;
-    sp.n_src = pl.dims[1]; sp.left = pl.left[1]; sp.ext = mirror_mode(pl.sy.n, pl.left[1], pl.dims[1]);
-    sp.in_tstride = T; sp.in_estride = kxc; sp.in_ostride = (long long)pl.dims[1] * kxc;
-    sp.out_tstride = (long long)pl.dims[2] * ny * T; sp.out_estride = T; sp.out_ostride = ny * T;
-    sp.swap_grid = 0; sp.scale = 1.0f;
-    err = l.launch_strided(false, pl.sy, sp, pl.dims[2]);
-    if (err) return err;
-
+    const long long T = l.lanes, ny = pl.sy.n;
+    const int planes = conv_out_planes(pl, g, keep_inc);
+    const bool pruned = g.world == 1 && planes != pl.dims[2];
     ZFusedParams zp = {};
-    zp.u = ws.u2; zp.h = ws.h; zp.tw = ws.tw_z; zp.kx_count = (int)kxc;
+    zp.u = buf; zp.h = ws.h; zp.tw = ws.tw_z; zp.kx_count = (int)pl.kxc();
     zp.n_src = pl.dims[2]; zp.left = pl.left[2]; zp.crop0 = pl.crop0[2];
     zp.ext = mirror_mode(pl.sz.n, pl.left[2], pl.dims[2]);
+    zp.tile0 = g.tile0; zp.zg = g.z_local; zp.zg_magic = div_magic((uint32_t)g.z_local);
     zp.keep_inc = pruned ? keep_inc : 1; zp.n_keep = planes - 1; zp.keep_magic = div_magic((uint32_t)zp.keep_inc);
     zp.estride = ny * T; zp.ostride = T;
-    zp.u_tstride = (long long)pl.dims[2] * ny * T; zp.h_tstride = (long long)pl.sz.n * ny * T;
-    err = l.launch_zfused(pl.sz, zp, pl.sy.n);
-    if (err) return err;
+    zp.u_tstride = (long long)g.z_local * ny * T; zp.seg_stride = (long long)g.tiles_own * g.z_local * ny * T;
+    zp.h_tstride = (long long)pl.sz.n * ny * T;
+    if (pl.dims[2] >= 65536) return 5;
+    return l.launch_zfused(pl.sz, zp, g.tiles_own, pl.sy.n);
+}
 
-    StridedParams ip = {};      // y inverse: U2 tile-major -> U1 row-major
-    ip.in = ws.u2; ip.out = ws.u1; ip.tw = ws.tw_y; ip.kx_count = (int)kxc;
-    ip.crop0 = pl.crop0[1]; ip.n_out = pl.dims[1];
-    ip.in_tstride = (long long)pl.dims[2] * ny * T; ip.in_estride = T; ip.in_ostride = ny * T;
+// y inverse of block b: ws.u2 (tile-major [KT][Zl][Ny][T], `planes` of the Zl planes in use) -> rows of ws.u1o
+template <class L> int conv_inverse_y(L& l, const ConvPlan& pl, const SlabGeom& g, const ConvWorkspace& ws, int b, int planes)
+{
+    const long long kxc = pl.kxc(), T = l.lanes, ny = pl.sy.n;
+    const int y0 = b * pl.y_block;
+    StridedParams ip = {};
+    ip.in = ws.u2; ip.out = ws.u1o; ip.tw = ws.tw_y; ip.kx_count = (int)kxc;
+    ip.crop0 = pl.crop0[1];
+    ip.n_out = pl.dims[1] - y0 < pl.y_block ? pl.dims[1] - y0 : pl.y_block;
+    ip.out_offset = y0;
+    ip.in_tstride = (long long)g.z_local * ny * T; ip.in_estride = T; ip.in_ostride = ny * T;
     ip.out_tstride = T; ip.out_estride = kxc; ip.out_ostride = (long long)pl.dims[1] * kxc;
     ip.swap_grid = 0; ip.scale = 1.0f;
-    err = l.launch_strided(true, pl.sy, ip, planes);
-    if (err) return err;
+    ip.tile0 = 0; ip.in_tile_global = 1; ip.out_tile_global = 1;
+    return l.launch_strided(true, pl.sy, ip, g.tiles_total, planes);
+}
 
+// x inverse + crop: ws.u1o -> out [planes][Y][X]; partials (nullable): one double per block
+template <class L> int conv_inverse_x(L& l, const ConvPlan& pl, const ConvWorkspace& ws, float* out, double* partials, int planes)
+{
     XParams ix = {};
-    ix.cin = ws.u1; ix.rout = out; ix.tw = ws.tw_x; ix.twist = ws.twist_x; ix.partials = partials;
+    ix.cin = ws.u1o; ix.rout = out; ix.tw = ws.tw_x; ix.twist = ws.twist_x; ix.partials = partials;
     ix.X = pl.dims[0]; ix.n_rows = pl.dims[1] * planes; ix.crop0 = pl.crop0[0];
     return l.launch_x(true, pl.sx, ix);
+}
+
+// Whole convolution on one GPU (world == 1): image -> out, using the spectrum in ws.h.
+// out has conv_out_planes(pl, g, keep_inc) planes of Y*X floats.
+template <class L> int conv_apply(L& l, const ConvPlan& pl, const SlabGeom& g, const ConvWorkspace& ws, const float* img, float* out,
+                                  double* partials, int keep_inc = 1)
+{
+    const int planes = conv_out_planes(pl, g, keep_inc);
+    int err = conv_forward_x(l, pl, g, ws, img);
+    for (int b = 0; b < pl.y_blocks && !err; ++b) {
+        err = conv_forward_y(l, pl, g, ws, b);
+        if (!err) err = conv_middle_z(l, pl, g, ws, ws.u2, keep_inc);
+        if (!err) err = conv_inverse_y(l, pl, g, ws, b, planes);
+    }
+    if (!err) err = conv_inverse_x(l, pl, ws, out, partials, planes);
+    return err;
 }
 
 }  // namespace mvsim

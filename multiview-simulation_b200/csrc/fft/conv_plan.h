@@ -53,11 +53,21 @@ inline const FftSize* pick_fft_size(int64_t min_n)
     return nullptr;
 }
 
+// How one rank of a slab-decomposed convolution sees the problem (world = 1: the whole problem).
+//   z planes [z0, z0 + z_local) of the image live on this rank for the x and y passes;
+//   kx tiles [tile0, tile0 + tiles_own) with ALL z planes live on it for the z pass.
+struct SlabGeom {
+    int rank, world;
+    int z_local, z0;
+    int tiles_total, tiles_own, tile0;
+};
+
 struct ConvPlan {
-    int dims[3], kdims[3];
-    FftSize sx, sy, sz;     // sx.n = complex length of the folded x rows (padded real length 2*sx.n)
+    int dims[3], kdims[3];  // GLOBAL volume and kernel dims
+    FftSize sx, sy, sz;     // sx.n = complex length of the folded x rows (padded real length 2*sx.n); sy = one y BLOCK
     int left[3];            // padded index p holds source index p - left   (left = kdim - 1 - kdim/2)
     int crop0[3];           // output voxel o lives at padded index o + crop0 (crop0 = kdim - 1)
+    int y_blocks, y_block;  // overlap-save blocks along y: block b produces output rows [b*y_block, min((b+1)*y_block, Y))
     double scale;           // 1 / (sx.n * sy.n * sz.n)
 
     // Workspaces.  U1/P1 are row-major in kx (written by the x pass row by row); U2/P2/H are kx-TILE-major
@@ -66,15 +76,23 @@ struct ConvPlan {
     // keeps the z pass inside a few 2 MB pages and DRAM rows.
     int64_t kxc() const { return sx.n; }
     int64_t ktiles(int t) const { return (sx.n + t - 1) / t; }
-    int64_t u1_elems() const { return (int64_t)dims[2] * dims[1] * sx.n; }               // [Z][Y][KXc]
-    int64_t u2_elems(int t) const { return ktiles(t) * dims[2] * sy.n * t; }             // [KT][Z][Ny][T]
-    int64_t h_elems(int t) const { return ktiles(t) * sz.n * sy.n * t; }                 // [KT][Nz][Ny][T]
-    int64_t p1_elems() const { return (int64_t)kdims[2] * kdims[1] * sx.n; }             // [KZ][KY][KXc]
-    int64_t p2_elems(int t) const { return ktiles(t) * kdims[2] * sy.n * t; }            // [KT][KZ][Ny][T]
+    int64_t u1_elems(int z_local) const { return (int64_t)z_local * dims[1] * sx.n; }               // [Zl][Y][KXc]
+    int64_t u2_elems(int t, int z_local) const { return ktiles(t) * z_local * sy.n * t; }           // [KT][Zl][Ny][T]
+    int64_t h_elems(int t, int tiles_own) const { return (int64_t)tiles_own * sz.n * sy.n * t; }    // [tiles][Nz][Ny][T]
+    int64_t p1_elems() const { return (int64_t)kdims[2] * kdims[1] * sx.n; }                        // [KZ][KY][KXc]
+    int64_t p2_elems(int t, int tiles_own) const { return (int64_t)tiles_own * kdims[2] * sy.n * t; }   // [tiles][KZ][Ny][T]
 };
 
-// 0 ok, 1 invalid dims, 5 unsupported (too large for the size table)
-inline int make_conv_plan(const int64_t dims[3], const int64_t kdims[3], ConvPlan* p)
+inline int max_fft_line()
+{
+    int c;
+    const FftSize* t = fft_size_table(&c);
+    return t[c - 1].n;
+}
+
+// 0 ok, 1 invalid dims, 5 unsupported (too large for the size table).  max_line (tests): cap on the y line length
+// that forces overlap-save blocking at small sizes; 0 = the largest table entry.
+inline int make_conv_plan(const int64_t dims[3], const int64_t kdims[3], ConvPlan* p, int max_line = 0)
 {
     for (int d = 0; d < 3; ++d) {
         if (dims[d] < 1 || kdims[d] < 1 || dims[d] > (1 << 30) || kdims[d] > (1 << 30)) return 1;
@@ -83,12 +101,35 @@ inline int make_conv_plan(const int64_t dims[3], const int64_t kdims[3], ConvPla
         p->left[d] = (int)(kdims[d] - 1 - kdims[d] / 2);
         p->crop0[d] = (int)(kdims[d] - 1);
     }
+    const int cap = max_line > 0 ? max_line : max_fft_line();
+    // y: overlap-save blocks when one padded line would exceed the table.  Every block convolves
+    // y_block + KY - 1 input rows (taken from the mirror-extended volume) into y_block output rows.
+    p->y_blocks = 1;
+    p->y_block = (int)dims[1];
+    if (dims[1] + kdims[1] - 1 > cap) {
+        const int64_t room = cap - (kdims[1] - 1);
+        if (room < 1) return 5;
+        p->y_blocks = (int)((dims[1] + room - 1) / room);
+        p->y_block = (int)((dims[1] + p->y_blocks - 1) / p->y_blocks);
+    }
     const FftSize* sx = pick_fft_size((dims[0] + kdims[0] - 1 + 1) / 2);
-    const FftSize* sy = pick_fft_size(dims[1] + kdims[1] - 1);
+    const FftSize* sy = pick_fft_size(p->y_block + kdims[1] - 1);
     const FftSize* sz = pick_fft_size(dims[2] + kdims[2] - 1);
     if (!sx || !sy || !sz) return 5;
     p->sx = *sx; p->sy = *sy; p->sz = *sz;
     p->scale = 1.0 / ((double)sx->n * (double)sy->n * (double)sz->n);
+    return 0;
+}
+
+// 0 ok, 5 when the decomposition does not divide evenly (slabs of equal size are required)
+inline int make_slab_geom(const ConvPlan& pl, int lanes, int rank, int world, SlabGeom* g)
+{
+    const int kt = (int)pl.ktiles(lanes);
+    if (world < 1 || rank < 0 || rank >= world) return 1;
+    if (pl.dims[2] % world != 0 || kt % world != 0) return 5;
+    g->rank = rank; g->world = world;
+    g->z_local = pl.dims[2] / world; g->z0 = rank * g->z_local;
+    g->tiles_total = kt; g->tiles_own = kt / world; g->tile0 = rank * g->tiles_own;
     return 0;
 }
 

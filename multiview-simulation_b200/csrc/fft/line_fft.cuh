@@ -78,6 +78,7 @@ template <int A, int B> MVSIM_HD void inv_second(int p, float2 (&x)[A], const fl
 template <int A, int B> MVSIM_HD void gather_line(float2 (&x)[A], const float2* __restrict__ src, long long estride, int p, int left,
                                                  int n_src, int ext)
 {
+    // `left` already includes the block offset of overlap-save blocks (padded index q holds source q - left)
     if (ext == EXT_MIRROR1) {
         int idx[A];
         MVSIM_UNROLL
@@ -116,6 +117,9 @@ struct StridedParams {
     long long in_estride, in_ostride, out_estride, out_ostride;   // in float2 units
     long long in_tstride, out_tstride;  // stride between kx tiles: T for row-major [..][KXc], Z*N*T for tile-major [KT][..][..][T]
     int swap_grid;          // 0: blockIdx.x = kx tile, .y = outer; 1: blockIdx.x = outer (neighbouring CTAs share DRAM pages)
+    int tile0;              // global index of this launch's tile 0 (slab decomposition: a rank owns tiles [tile0, tile0 + n))
+    int in_tile_global, out_tile_global;   // 1: that side is indexed by the global tile (row-major U1/P1), 0: by the local tile
+    int out_offset;         // inverse: cropped sample o is stored at line index o + out_offset (overlap-save blocks along y)
     float scale;            // forward: multiplied into the output (folds 1/N and PSF scaling)
 };
 
@@ -134,11 +138,12 @@ template <int A_, int B_, int T_> struct StridedFwd : LineShape<A_, B_> {
     {
         const int lane = tid % T, p = tid / T;
         const int tile = q.swap_grid ? by : bx, outer = q.swap_grid ? bx : by;
-        const bool active = tile * T + lane < q.kx_count;
+        const int tin = q.in_tile_global ? tile + q.tile0 : tile, tout = q.out_tile_global ? tile + q.tile0 : tile;
+        const bool active = (tile + q.tile0) * T + lane < q.kx_count;
         if (PH == 0) {
             if (p < B && active) {
                 float2 x[A];
-                const float2* src = q.in + tile * q.in_tstride + outer * q.in_ostride + lane;
+                const float2* src = q.in + tin * q.in_tstride + outer * q.in_ostride + lane;
                 gather_line<A, B>(x, src, q.in_estride, p, q.left, q.n_src, q.ext);
                 fwd_first<A, B>(p, x, sm, lane, T, q.tw);
             }
@@ -146,7 +151,7 @@ template <int A_, int B_, int T_> struct StridedFwd : LineShape<A_, B_> {
             if (p < A && active) {
                 float2 y[B];
                 fwd_second<A, B>(p, y, sm, lane, T);
-                float2* dst = q.out + tile * q.out_tstride + outer * q.out_ostride + lane;
+                float2* dst = q.out + tout * q.out_tstride + outer * q.out_ostride + lane;
                 MVSIM_UNROLL
                 for (int k2 = 0; k2 < B; ++k2)
                     dst[(p + A * k2) * q.out_estride] = make_float2(y[k2].x * q.scale, y[k2].y * q.scale);
@@ -169,11 +174,12 @@ template <int A_, int B_, int T_> struct StridedInv : LineShape<A_, B_> {
     {
         const int lane = tid % T, p = tid / T;
         const int tile = q.swap_grid ? by : bx, outer = q.swap_grid ? bx : by;
-        const bool active = tile * T + lane < q.kx_count;
+        const int tin = q.in_tile_global ? tile + q.tile0 : tile, tout = q.out_tile_global ? tile + q.tile0 : tile;
+        const bool active = (tile + q.tile0) * T + lane < q.kx_count;
         if (PH == 0) {
             if (p < A && active) {
                 float2 y[B];
-                const float2* src = q.in + tile * q.in_tstride + outer * q.in_ostride + lane;
+                const float2* src = q.in + tin * q.in_tstride + outer * q.in_ostride + lane;
                 MVSIM_UNROLL
                 for (int k2 = 0; k2 < B; ++k2) y[k2] = src[(p + A * k2) * q.in_estride];
                 inv_first<A, B>(p, y, sm, lane, T, q.tw);
@@ -182,11 +188,11 @@ template <int A_, int B_, int T_> struct StridedInv : LineShape<A_, B_> {
             if (p < B && active) {
                 float2 x[A];
                 inv_second<A, B>(p, x, sm, lane, T);
-                float2* dst = q.out + tile * q.out_tstride + outer * q.out_ostride + lane;
+                float2* dst = q.out + tout * q.out_tstride + outer * q.out_ostride + lane;
                 MVSIM_UNROLL
                 for (int n1 = 0; n1 < A; ++n1) {
                     const int o = p + n1 * B - q.crop0;
-                    if ((unsigned)o < (unsigned)q.n_out) dst[o * q.out_estride] = x[n1];
+                    if ((unsigned)o < (unsigned)q.n_out) dst[(o + q.out_offset) * q.out_estride] = x[n1];
                 }
             }
         }
@@ -199,19 +205,32 @@ template <int A_, int B_, int T_> struct StridedInv : LineShape<A_, B_> {
 // In place: a CTA reads its T lines completely before it writes them.
 // ==============================================================================================
 struct ZFusedParams {
-    float2* u;              // tile-major [KT][Z][Ny][T], in place
-    const float2* h;        // tile-major [KT][Nz][Ny][T], already scaled by 1/(N*Ny*Nz)
+    float2* u;              // [S][tiles][zg][Ny][T] in place: S segments of zg planes (S = ranks of a slab-decomposed run: the
+                            // all-to-all receive layout; S = 1, zg = Z on one GPU, i.e. plain tile-major [KT][Z][Ny][T])
+    const float2* h;        // tile-major [tiles][Nz][Ny][T], already scaled by 1/(N*Ny*Nz)
     const float2* tw;
     int kx_count, n_src, left, crop0;
     int ext;                // EXT_MIRROR1 or EXT_MIRROR_GENERAL
+    int tile0;              // global index of local tile 0
+    int zg;                 // planes per segment
+    unsigned zg_magic;      // div_magic(zg)
     unsigned keep_magic;    // div_magic(keep_inc)
-    int keep_inc, n_keep;   // keep_inc > 1: store only z = 0, inc, 2 inc, ... compacted to planes 0..n_keep-1 and the SUM of
-                            // all other cropped z in plane n_keep (enough for extractSlices + the mean of adjustImage)
-    long long estride;      // z stride (= Ny*T), same for u and h
+    int keep_inc, n_keep;   // keep_inc > 1 (single segment only): store only z = 0, inc, 2 inc, ... compacted to planes
+                            // 0..n_keep-1 and the SUM of all other cropped z in plane n_keep (enough for extractSlices + the
+                            // mean of adjustImage)
+    long long estride;      // z stride inside a segment (= Ny*T), also the kz stride of h
     long long ostride;      // ky stride (= T), same for u and h
-    long long u_tstride;    // kx-tile stride of u (= Z*Ny*T)
+    long long u_tstride;    // kx-tile stride of u inside a segment (= zg*Ny*T)
+    long long seg_stride;   // segment stride of u (= tiles*zg*Ny*T)
     long long h_tstride;    // kx-tile stride of h (= Nz*Ny*T)
 };
+
+// offset of global plane z in the segmented layout
+MVSIM_HD long long zfused_plane_offset(const ZFusedParams& q, int z)
+{
+    const int seg = q.zg == 1 ? z : (int)umulhi32((uint32_t)z, q.zg_magic);   // div_magic(1) does not fit 32 bits
+    return seg * q.seg_stride + (z - seg * q.zg) * q.estride;
+}
 
 template <int B> struct RegState { float2 y[B]; float2 acc; };
 
@@ -231,7 +250,7 @@ template <int A_, int B_, int T_> struct ZFused : LineShape<A_, B_> {
         // blockIdx.y = kx tile
         const int lane = tid % T, p = tid / T;
         const int tile = by, outer = bx;
-        const bool active = tile * T + lane < q.kx_count;
+        const bool active = (tile + q.tile0) * T + lane < q.kx_count;
         float2* smh = sm + S::ELEMS * T;
         if (PH == 0) {
             {   // H tile -> shared memory, 16 bytes per copy, rows of T float2
@@ -244,8 +263,17 @@ template <int A_, int B_, int T_> struct ZFused : LineShape<A_, B_> {
             }
             if (p < B && active) {
                 float2 x[A];
-                const float2* src = q.u + tile * q.u_tstride + outer * q.ostride + lane;
-                gather_line<A, B>(x, src, q.estride, p, q.left, q.n_src, q.ext);
+                const float2* __restrict__ src = q.u + tile * q.u_tstride + outer * q.ostride + lane;
+                int idx[A];
+                if (q.ext == EXT_MIRROR1) {
+                    MVSIM_UNROLL
+                    for (int n1 = 0; n1 < A; ++n1) idx[n1] = mirror_once(p + n1 * B - q.left, q.n_src);
+                } else {
+                    MVSIM_UNROLL
+                    for (int n1 = 0; n1 < A; ++n1) idx[n1] = mirror_single(p + n1 * B - q.left, q.n_src);
+                }
+                MVSIM_UNROLL
+                for (int n1 = 0; n1 < A; ++n1) x[n1] = src[zfused_plane_offset(q, idx[n1])];
                 fwd_first<A, B>(p, x, sm, lane, T, q.tw);
             }
             cp_async_wait_all();
@@ -277,7 +305,7 @@ template <int A_, int B_, int T_> struct ZFused : LineShape<A_, B_> {
                     MVSIM_UNROLL
                     for (int n1 = 0; n1 < A; ++n1) {
                         const int o = p + n1 * B - q.crop0;
-                        if ((unsigned)o < (unsigned)q.n_src) dst[o * q.estride] = x[n1];
+                        if ((unsigned)o < (unsigned)q.n_src) dst[zfused_plane_offset(q, o)] = x[n1];
                     }
                 }
             }

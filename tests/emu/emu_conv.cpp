@@ -49,9 +49,8 @@ struct EmuLauncher {
         }
         return 5;
     }
-    int launch_strided(bool inverse, const FftSize& s, const StridedParams& q, int n_outer)
+    int launch_strided(bool inverse, const FftSize& s, const StridedParams& q, int tiles, int n_outer)
     {
-        const int tiles = (q.kx_count + T - 1) / T;
         const int gx = q.swap_grid ? n_outer : tiles, gy = q.swap_grid ? tiles : n_outer;
         switch (s.n) {
 #define MVSIM_X(n_, a_, b_) case n_: if (inverse) emulate<StridedInv<a_, b_, T>>(q, gx, gy); else emulate<StridedFwd<a_, b_, T>>(q, gx, gy); return 0;
@@ -60,9 +59,8 @@ struct EmuLauncher {
         }
         return 5;
     }
-    int launch_zfused(const FftSize& s, const ZFusedParams& q, int n_outer)
+    int launch_zfused(const FftSize& s, const ZFusedParams& q, int tiles, int n_outer)
     {
-        const int tiles = (q.kx_count + T - 1) / T;
         switch (s.n) {
 #define MVSIM_X(n_, a_, b_) case n_: emulate<ZFused<a_, b_, T>>(q, n_outer, tiles); return 0;
             MVSIM_FFT_SIZES(MVSIM_X)
@@ -72,41 +70,89 @@ struct EmuLauncher {
     }
 };
 
-extern "C" int emu_plan(const int64_t dims[3], const int64_t kdims[3], int out[9])
+extern "C" int emu_plan(const int64_t dims[3], const int64_t kdims[3], int out[11], int max_line)
 {
     ConvPlan pl;
-    const int err = make_conv_plan(dims, kdims, &pl);
+    const int err = make_conv_plan(dims, kdims, &pl, max_line);
     if (err) return err;
     out[0] = pl.sx.n; out[1] = pl.sy.n; out[2] = pl.sz.n;
     out[3] = pl.sx.a; out[4] = pl.sx.b; out[5] = pl.sy.a; out[6] = pl.sy.b; out[7] = pl.sz.a; out[8] = pl.sz.b;
+    out[9] = pl.y_blocks; out[10] = pl.y_block;
     return 0;
 }
 
-// psf must already be normalised; sum_out (nullable) receives the sum of the output voxels
-// keep_inc > 1: out receives conv_kept_planes(dims, keep_inc) planes (kept slices, then the sum of the others)
+namespace {
+
+struct RankState {
+    SlabGeom g;
+    std::vector<float2> u1, u1o, u2, ex, h, p1, p2;
+    ConvWorkspace ws;
+};
+
+void poison(std::vector<float2>& v) { for (auto& e : v) { e.x = 3e30f; e.y = -3e30f; } }
+
+}  // namespace
+
+// Emulates `world` ranks of the slab-decomposed convolution in one process (world = 1: the single-GPU path).
+// The all-to-all exchanges are done here on the host with the semantics of all_to_all_single (equal chunks).
+// psf must already be normalised.  keep_inc > 1 (world 1 only): out receives the kept slices then the sum plane.
 extern "C" int emu_convolve(const float* img, const int64_t dims[3], const float* psf, const int64_t kdims[3],
-                            float* out, double* sum_out, int keep_inc)
+                            float* out, double* sum_out, int keep_inc, int world, int max_line)
 {
     ConvPlan pl;
-    int err = make_conv_plan(dims, kdims, &pl);
+    int err = make_conv_plan(dims, kdims, &pl, max_line);
     if (err) return err;
-    std::vector<float2> u1(pl.u1_elems()), u2(pl.u2_elems(T)), h(pl.h_elems(T)), p1(pl.p1_elems()), p2(pl.p2_elems(T));
     std::vector<float2> twx(pl.sx.n), twy(pl.sy.n), twz(pl.sz.n), twist(pl.sx.n);
     fill_twiddles(pl.sx.n, &twx[0].x);
     fill_twiddles(pl.sy.n, &twy[0].x);
     fill_twiddles(pl.sz.n, &twz[0].x);
     fill_twist(pl.sx.n, &twist[0].x);
-    // poison the workspaces: every element that is read must have been written by a pass
-    for (auto* v : { &u1, &u2, &h, &p1, &p2 })
-        for (auto& e : *v) { e.x = 3e30f; e.y = -3e30f; }
-    ConvWorkspace ws = { u1.data(), u2.data(), h.data(), p1.data(), p2.data(), twx.data(), twy.data(), twz.data(), twist.data() };
     EmuLauncher l;
-    err = conv_psf_spectrum(l, pl, ws, psf);
-    if (err) return err;
-    const int planes = conv_out_planes(pl, keep_inc);
-    std::vector<double> partials(l.x_blocks(pl.sx, pl.dims[1] * planes), 0.0);
-    err = conv_apply(l, pl, ws, img, out, partials.data(), keep_inc);
-    if (err) return err;
-    if (sum_out) { double s = 0; for (double v : partials) s += v; *sum_out = s; }
+    std::vector<RankState> rk(world);
+    for (int r = 0; r < world; ++r) {
+        RankState& s = rk[r];
+        err = make_slab_geom(pl, T, r, world, &s.g);
+        if (err) return err;
+        s.u1.resize(pl.u1_elems(s.g.z_local)); s.u1o.resize(pl.y_blocks > 1 ? pl.u1_elems(s.g.z_local) : 0);
+        s.u2.resize(pl.u2_elems(T, s.g.z_local)); s.ex.resize(world > 1 ? s.u2.size() : 0);
+        s.h.resize(pl.h_elems(T, s.g.tiles_own)); s.p1.resize(pl.p1_elems()); s.p2.resize(pl.p2_elems(T, s.g.tiles_own));
+        // poison the workspaces: every element that is read must have been written by a pass
+        for (auto* v : { &s.u1, &s.u1o, &s.u2, &s.ex, &s.h, &s.p1, &s.p2 }) poison(*v);
+        s.ws = ConvWorkspace{ s.u1.data(), pl.y_blocks > 1 ? s.u1o.data() : s.u1.data(), s.u2.data(),
+                              world > 1 ? s.ex.data() : s.u2.data(), s.h.data(), s.p1.data(), s.p2.data(),
+                              twx.data(), twy.data(), twz.data(), twist.data() };
+        err = conv_psf_spectrum(l, pl, s.g, s.ws, psf);
+        if (err) return err;
+        err = conv_forward_x(l, pl, s.g, s.ws, img + (size_t)s.g.z0 * pl.dims[1] * pl.dims[0]);
+        if (err) return err;
+    }
+    const int planes = conv_out_planes(pl, rk[0].g, keep_inc);
+    const size_t chunk = rk[0].u2.size() / world;
+    for (int b = 0; b < pl.y_blocks; ++b) {
+        for (int r = 0; r < world; ++r)
+            if ((err = conv_forward_y(l, pl, rk[r].g, rk[r].ws, b))) return err;
+        if (world > 1)      // all-to-all: chunk d of rank s's send buffer lands in chunk s of rank d's receive buffer
+            for (int s = 0; s < world; ++s)
+                for (int d = 0; d < world; ++d)
+                    std::memcpy(rk[d].ex.data() + s * chunk, rk[s].u2.data() + d * chunk, chunk * sizeof(float2));
+        for (int r = 0; r < world; ++r)
+            if ((err = conv_middle_z(l, pl, rk[r].g, rk[r].ws, rk[r].ws.ex, keep_inc))) return err;
+        if (world > 1) {
+            for (int r = 0; r < world; ++r) poison(rk[r].u2);
+            for (int s = 0; s < world; ++s)
+                for (int d = 0; d < world; ++d)
+                    std::memcpy(rk[d].u2.data() + s * chunk, rk[s].ex.data() + d * chunk, chunk * sizeof(float2));
+        }
+        for (int r = 0; r < world; ++r)
+            if ((err = conv_inverse_y(l, pl, rk[r].g, rk[r].ws, b, planes))) return err;
+    }
+    double total = 0;
+    for (int r = 0; r < world; ++r) {
+        std::vector<double> partials(l.x_blocks(pl.sx, pl.dims[1] * planes), 0.0);
+        float* o = out + (size_t)(world > 1 ? rk[r].g.z0 : 0) * pl.dims[1] * pl.dims[0];
+        if ((err = conv_inverse_x(l, pl, rk[r].ws, o, partials.data(), planes))) return err;
+        for (double v : partials) total += v;
+    }
+    if (sum_out) *sum_out = total;
     return 0;
 }

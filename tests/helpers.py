@@ -11,7 +11,6 @@ def sphere_phantom(shape_zyx, seed=464232194, n_spheres=None):
     big_r = 0.337 * min(shape_zyx)
     c = np.array([(z - 1) / 2.0, (y - 1) / 2.0, (x - 1) / 2.0])
     n = n_spheres or max(8, int(0.002 * z * y * x / 20))
-    zz, yy, xx = np.mgrid[0:z, 0:y, 0:x]
     for _ in range(n):
         while True:
             p = c + rng.uniform(-big_r, big_r, 3)
@@ -19,8 +18,12 @@ def sphere_phantom(shape_zyx, seed=464232194, n_spheres=None):
                 break
         r = rng.integers(1, 6) / 2.0 + 0.5
         v = np.float32(rng.random())
+        lo = np.maximum(np.floor(p - r).astype(int), 0)
+        hi = np.minimum(np.ceil(p + r).astype(int) + 1, shape_zyx)
+        zz, yy, xx = np.mgrid[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]]
         m = (zz - p[0]) ** 2 + (yy - p[1]) ** 2 + (xx - p[2]) ** 2 <= r * r
-        vol[m] = np.maximum(vol[m], v)
+        sub = vol[lo[0]:hi[0], lo[1]:hi[1], lo[2]:hi[2]]
+        sub[m] = np.maximum(sub[m], v)
     return vol
 
 

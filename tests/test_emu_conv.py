@@ -24,19 +24,19 @@ def emu():
         subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-I", CSRC, SRC, "-o", SO])
     L = C.CDLL(SO)
     i64p, fp = C.POINTER(C.c_int64), C.POINTER(C.c_float)
-    L.emu_convolve.argtypes = [fp, i64p, fp, i64p, fp, C.POINTER(C.c_double), C.c_int]
-    L.emu_plan.argtypes = [i64p, i64p, C.POINTER(C.c_int)]
+    L.emu_convolve.argtypes = [fp, i64p, fp, i64p, fp, C.POINTER(C.c_double), C.c_int, C.c_int, C.c_int]
+    L.emu_plan.argtypes = [i64p, i64p, C.POINTER(C.c_int), C.c_int]
     return L
 
 
-def _run(emu, vol, psfn, keep_inc=1, planes=None):
+def _run(emu, vol, psfn, keep_inc=1, planes=None, world=1, max_line=0):
     z, y, x = vol.shape
     kz, ky, kx = psfn.shape
     out = np.empty_like(vol) if planes is None else np.empty((planes, y, x), dtype=np.float32)
     s = C.c_double(0)
     fp = C.POINTER(C.c_float)
     err = emu.emu_convolve(vol.ctypes.data_as(fp), (C.c_int64 * 3)(x, y, z), psfn.ctypes.data_as(fp),
-                           (C.c_int64 * 3)(kx, ky, kz), out.ctypes.data_as(fp), C.byref(s), keep_inc)
+                           (C.c_int64 * 3)(kx, ky, kz), out.ctypes.data_as(fp), C.byref(s), keep_inc, world, max_line)
     assert err == 0
     return out, s.value
 
@@ -61,10 +61,10 @@ def test_emulated_kernels_match_direct_convolution(emu, oracle, shape, kshape):
 
 
 def test_plan_sizes_cover_dim_plus_kdim_minus_one(emu):
-    out = (C.c_int * 9)()
+    out = (C.c_int * 11)()
     for dims, kdims in [((1024, 1024, 512), (128, 128, 128)), ((289, 289, 289), (51, 51, 51)),
                         ((512, 512, 512), (64, 64, 128)), ((1, 1, 1), (1, 1, 1))]:
-        err = emu.emu_plan((C.c_int64 * 3)(*dims), (C.c_int64 * 3)(*kdims), out)
+        err = emu.emu_plan((C.c_int64 * 3)(*dims), (C.c_int64 * 3)(*kdims), out, 0)
         if err == 5:        # emulator is built with the small size table only
             continue
         assert err == 0
@@ -88,4 +88,40 @@ def test_kept_slices_and_sum_plane(emu, oracle, shape, kshape, inc):
     assert rel_err(out[:nk], kept) < 5e-6
     dropped = ref.astype(np.float64).sum(axis=0) - kept.astype(np.float64).sum(axis=0)
     assert rel_err(out[nk], dropped.astype(np.float32)) < 2e-5
+    assert s == pytest.approx(float(ref.astype(np.float64).sum()), rel=2e-6)
+
+
+@pytest.mark.parametrize("shape,kshape,max_line", [((6, 50, 12), (3, 7, 5), 24), ((4, 33, 9), (2, 4, 3), 16), ((5, 70, 8), (3, 9, 3), 32)])
+def test_overlap_save_blocks_along_y(emu, oracle, shape, kshape, max_line):
+    """y lines longer than the size table are convolved in overlap-save blocks (the 2048+255 rows of the
+    largest single volume); max_line forces the same code path at test sizes."""
+    out = (C.c_int * 11)()
+    z, y, x = shape
+    kz, ky, kx = kshape
+    assert emu.emu_plan((C.c_int64 * 3)(x, y, z), (C.c_int64 * 3)(kx, ky, kz), out, max_line) == 0
+    assert out[9] >= 2 and out[1] <= max_line and out[9] * out[10] >= y
+    rng = np.random.default_rng(13)
+    vol = rng.random(shape, dtype=np.float32)
+    psf = rng.random(kshape, dtype=np.float32)
+    ref = oracle.convolve(vol, psf, "direct")
+    got, s = _run(emu, vol, psf, max_line=max_line)
+    assert rel_err(got, ref) < 5e-6
+    assert s == pytest.approx(float(ref.astype(np.float64).sum()), rel=2e-6)
+    kept, _ = _run(emu, vol, psf, keep_inc=2, planes=(z - 1) // 2 + 2, max_line=max_line)
+    assert rel_err(kept[:(z - 1) // 2 + 1], ref[::2]) < 5e-6
+
+
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("shape,kshape,max_line", [((8, 14, 50), (3, 5, 9), 0), ((4, 40, 120), (5, 7, 3), 24)])
+def test_slab_decomposed_convolution_with_host_all_to_all(emu, oracle, world, shape, kshape, max_line):
+    """Largest-single-volume path: z slabs for the x/y passes, kx tiles for the z pass, two
+    all-to-all transposes (done on the host here).  Must equal the undecomposed result."""
+    rng = np.random.default_rng(14)
+    vol = rng.random(shape, dtype=np.float32)
+    psf = rng.random(kshape, dtype=np.float32)
+    ref = oracle.convolve(vol, psf, "direct")
+    got, s = _run(emu, vol, psf, world=world, max_line=max_line)
+    assert rel_err(got, ref) < 5e-6
+    one, _ = _run(emu, vol, psf, world=1, max_line=max_line)
+    assert np.array_equal(got, one)          # the decomposition does not change a single bit
     assert s == pytest.approx(float(ref.astype(np.float64).sum()), rel=2e-6)
