@@ -348,6 +348,7 @@ def run_slab(args, rank, world, local_rank):
     for _ in range(args.warmup):
         sc.convolve(img, d_psf, out)
     barrier()
+    ctx.profile(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
@@ -355,6 +356,7 @@ def run_slab(args, rank, world, local_rank):
     e1.record(stream)
     barrier()
     ms = grp.max(e0.elapsed_time(e1)) / args.steps
+    stage = {k: round(v[0] / args.steps, 3) for k, v in ctx.stage_times().items() if v[1]}
     chk = float(out[::max(1, sc.z_local // 4), ::97, ::89].double().mean().item())
     if rank == 0:
         vox = int(np.prod(shape))
@@ -364,7 +366,8 @@ def run_slab(args, rank, world, local_rank):
                           "config": {"workload": "BASELINE config 5 (configs[4])" if args.workload == "cfg5" else args.workload,
                                      "volume_xyz": list(shape[::-1]), "psf_xyz": list(kshape[::-1]), "fft_padded_xyz": list(sc.nfft),
                                      "y_blocks": sc.y_blocks, "parallelism": f"z slabs x{world}, NCCL all_to_all_single x{2 * sc.y_blocks}"},
-                          "nvlink_bytes_sent_per_rank_per_step": sc.exchange_bytes_per_rank(), "result_checksum": chk}), flush=True)
+                          "nvlink_bytes_sent_per_rank_per_step": sc.exchange_bytes_per_rank(), "rank0_kernel_ms_per_step": stage,
+                          "rank0_kernel_ms_total": round(sum(stage.values()), 3), "result_checksum": chk}), flush=True)
     sc.close()
     grp.close()
 

@@ -23,11 +23,17 @@ class SlabConvolution:
         self.z_local, self.z0, self.y_blocks, self.exchange_elems = int(info[0]), int(info[1]), int(info[2]), int(info[3])
         self.nfft = (int(info[4]), int(info[5]), int(info[6]))
         dev = torch.device("cuda", ctx.device)
-        self.send = torch.empty(self.exchange_elems, dtype=torch.complex64, device=dev)
-        self.recv = torch.empty(self.exchange_elems, dtype=torch.complex64, device=dev) if world > 1 else None
-        check(ctx._lib.mvsim_slabconv_bind(self.h, C.c_void_p(self.send.data_ptr()),
-                                           C.c_void_p(self.recv.data_ptr()) if self.recv is not None else None), ctx.h)
+        # up to three exchange buffer sets: the all-to-all of one y block overlaps the kernels of its neighbours
+        self.nbuf = 1 if world == 1 else min(3, self.y_blocks)
+        self.send = [torch.empty(self.exchange_elems, dtype=torch.complex64, device=dev) for _ in range(self.nbuf)]
+        self.recv = [torch.empty(self.exchange_elems, dtype=torch.complex64, device=dev) if world > 1 else None for _ in range(self.nbuf)]
+        self._bind(0)
         self.shape = tuple(shape_zyx)
+
+    def _bind(self, i):
+        r = self.recv[i]
+        check(self.ctx._lib.mvsim_slabconv_bind(self.h, C.c_void_p(self.send[i].data_ptr()),
+                                                C.c_void_p(r.data_ptr()) if r is not None else None), self.ctx.h)
 
     def exchange_bytes_per_rank(self):
         """bytes this rank sends to OTHER ranks per convolution (two transposes per y block)."""
@@ -40,14 +46,33 @@ class SlabConvolution:
         assert img_slab.is_contiguous() and out_slab.is_contiguous() and psf.is_contiguous()
         assert tuple(img_slab.shape) == (self.z_local,) + self.shape[1:] == tuple(out_slab.shape)
         check(lib.mvsim_slabconv_prepare(ctx.h, self.h, C.c_void_p(psf.data_ptr()), C.c_void_p(img_slab.data_ptr())), ctx.h)
-        for b in range(self.y_blocks):
-            check(lib.mvsim_slabconv_forward_y(ctx.h, self.h, b), ctx.h)
-            if self.world > 1:
-                self.dist.all_to_all_single(self.recv, self.send)
-            check(lib.mvsim_slabconv_middle_z(ctx.h, self.h), ctx.h)
-            if self.world > 1:
-                self.dist.all_to_all_single(self.send, self.recv)
-            check(lib.mvsim_slabconv_inverse_y(ctx.h, self.h, b), ctx.h)
+        nb = self.y_blocks
+        if self.world == 1:
+            for b in range(nb):
+                check(lib.mvsim_slabconv_forward_y(ctx.h, self.h, b), ctx.h)
+                check(lib.mvsim_slabconv_middle_z(ctx.h, self.h), ctx.h)
+                check(lib.mvsim_slabconv_inverse_y(ctx.h, self.h, b), ctx.h)
+        else:
+            # software pipeline over the y blocks: forward(t) | middle(t-1) | inverse(t-2); each exchange is
+            # asynchronous (NCCL's stream) and is waited for only where its data is consumed
+            works = {}
+            for t in range(nb + 2):
+                if t < nb:
+                    i = t % self.nbuf
+                    self._bind(i)
+                    check(lib.mvsim_slabconv_forward_y(ctx.h, self.h, t), ctx.h)
+                    works[t] = self.dist.all_to_all_single(self.recv[i], self.send[i], async_op=True)
+                if 0 <= t - 1 < nb:
+                    b, i = t - 1, (t - 1) % self.nbuf
+                    works.pop(b).wait()
+                    self._bind(i)
+                    check(lib.mvsim_slabconv_middle_z(ctx.h, self.h), ctx.h)
+                    works[b] = self.dist.all_to_all_single(self.send[i], self.recv[i], async_op=True)
+                if 0 <= t - 2 < nb:
+                    b, i = t - 2, (t - 2) % self.nbuf
+                    works.pop(b).wait()
+                    self._bind(i)
+                    check(lib.mvsim_slabconv_inverse_y(ctx.h, self.h, b), ctx.h)
         check(lib.mvsim_slabconv_finish(ctx.h, self.h, C.c_void_p(out_slab.data_ptr())), ctx.h)
         return out_slab
 

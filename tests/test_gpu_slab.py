@@ -78,7 +78,7 @@ def test_two_gpu_nccl_all_to_all_matches_single_gpu(tmp_path):
     world = 4 if n >= 4 else 2
     out = tmp_path / "slab.json"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-           "--master-port", str(29700 + os.getpid() % 200), os.path.join(HERE, "slab_worker.py"), "32x72x120", "9x7x11", str(out)]
+           "--master-port", str(29700 + os.getpid() % 200), os.path.join(HERE, "slab_worker.py"), "32x72x118", "9x7x11", str(out)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-3000:]
     d = json.loads(out.read_text())
