@@ -284,11 +284,20 @@ def run_ours(args, rank, world, local_rank):
     kxc, ny, nz = nfft[0] // 2, nfft[1], nfft[2]
     z_ms, z_n = stage["fft_zfused"]
     planes_out = oshape[0] + 1 if (inc > 1 and oshape[0] + 1 <= shape[0]) else shape[0]
-    bytes_zfused = 8 * kxc * ny * (shape[0] + nz + planes_out)   # read Z planes, read H (Nz planes), write kept planes + sum plane
+    # algorithmic bytes of the fused z pass per launch (= per view): SURVEY section 8(d) counts 3S for it (read S, read the
+    # PSF spectrum S, write S; S = 8 (Nx/2+1) Ny Nz).  The pruned kernel must move less: read Z planes + H (Nz planes) +
+    # write the kept planes and one sum plane; that figure and the ncu DRAM traffic are reported beside it.
     S_model = 8 * (nfft[0] // 2 + 1) * ny * nz
+    bytes_model = 3 * S_model
+    bytes_pruned = 8 * kxc * ny * (shape[0] + nz + planes_out)
     peak, peak_src = measured_peak_gbs()
     per_launch_ms = z_ms / max(z_n, 1)
-    achieved = bytes_zfused / (per_launch_ms * 1e-3) / 1e9
+    achieved = bytes_model / (per_launch_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["fft_zfused"]["bytes"] if args.workload == "cfg3" else None
+    except Exception:
+        pass
     fft_passes = {k: stage[k][0] / max(stage[k][1], 1) for k in ("fft_xfwd", "fft_yfwd", "fft_zfused", "fft_yinv", "fft_xinv")}
     N = vox_per_view
     O = int(np.prod(oshape))
@@ -296,9 +305,11 @@ def run_ours(args, rank, world, local_rank):
     b_stage_model = 32 * N + 11 * S_model + 8 * O
     view_ms = ms_step / nv
     roofline = {"bound": "hbm", "kernel": "fft_zfused (z-forward * PSF spectrum * z-inverse, in place)", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "bytes_per_launch": bytes_zfused, "bytes_per_launch_model_3S": 3 * S_model, "ms_per_launch": per_launch_ms,
-                "launches_timed": z_n,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "bytes_per_launch": bytes_model, "bytes_basis": "SURVEY 8(d): 3S per view for the fused z pass",
+                "bytes_per_launch_pruned": bytes_pruned, "achieved_pruned": bytes_pruned / (per_launch_ms * 1e-3) / 1e9,
+                "frac_pruned": bytes_pruned / (per_launch_ms * 1e-3) / 1e9 / peak,
+                "ms_per_launch": per_launch_ms, "launches_timed": z_n,
                 "whole_view": {"ms": view_ms, "B_fused_model_GB": b_fused_model / 1e9, "B_stage_model_GB": b_stage_model / 1e9,
                                "frac_of_peak_fused_model": b_fused_model / (view_ms * 1e-3) / 1e9 / peak,
                                "frac_of_peak_stage_model": b_stage_model / (view_ms * 1e-3) / 1e9 / peak}}

@@ -22,7 +22,7 @@ FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", CSRC, "-
 
 UNITS = [("stages", "stages.cu", []), ("conv", "conv.cu", []), ("capi", "capi.cu", [])] + \
         [(f"fft_g{g}_t{t}", os.path.join("fft", "fft_group.cu"), [f"-DMVSIM_GROUP={g}", f"-DMVSIM_LANES={t}"])
-         for g in (4, 3, 2, 1, 0) for t in (8, 4)]
+         for g in (4, 3, 2, 1, 0) for t in (8,)]
 
 
 def _nvcc():

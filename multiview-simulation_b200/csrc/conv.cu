@@ -66,14 +66,7 @@ struct Buffers {
 
 }  // namespace
 
-int strided_lanes()
-{
-    static const int lanes = [] {
-        const char* e = getenv("MVSIM_LANES");
-        return (e && atoi(e) == 4) ? 4 : 8;
-    }();
-    return lanes;
-}
+int strided_lanes() { return 8; }
 
 static int plan_error(mvsim_ctx* ctx, int perr)
 {

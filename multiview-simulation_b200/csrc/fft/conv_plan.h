@@ -13,19 +13,24 @@ namespace mvsim {
 
 struct FftSize { int n, a, b; };
 
-// X(n, a, b): supported complex line lengths, ascending, gaps <= 12.5 %.
+// X(n, a, b): supported complex line lengths n = a*b, ascending; a, b are in-register sub-transform sizes
+// (tools/gen_regfft.py).  Balanced splits (a ~ b) keep all threads of a line busy in both halves of the
+// two-level transform, so the planner prefers e.g. 648 = 24*27 over 640 = 20*32 for a 639-point minimum.
 #define MVSIM_FFT_SIZES_SMALL(X) \
-    X(16, 4, 4) X(20, 4, 5) X(24, 4, 6) X(32, 4, 8) X(40, 5, 8) X(48, 6, 8) X(64, 8, 8) X(72, 8, 9) \
-    X(80, 8, 10) X(96, 8, 12)
+    X(16, 4, 4) X(20, 4, 5) X(24, 4, 6) X(30, 5, 6) X(32, 4, 8) X(36, 6, 6) X(40, 5, 8) X(48, 6, 8) X(54, 6, 9) X(64, 8, 8) \
+    X(72, 8, 9) X(80, 8, 10) X(90, 9, 10) X(100, 10, 10) X(108, 9, 12) X(120, 10, 12)
 #define MVSIM_FFT_SIZES_G1(X) \
-    X(108, 9, 12) X(128, 8, 16) X(144, 12, 12) X(160, 10, 16) X(192, 12, 16) X(216, 12, 18) X(240, 15, 16) \
-    X(256, 16, 16) X(288, 16, 18)
+    X(128, 8, 16) X(135, 9, 15) X(144, 12, 12) X(160, 10, 16) X(180, 12, 15) X(192, 12, 16) X(216, 12, 18) X(225, 15, 15) \
+    X(240, 15, 16) X(256, 16, 16) X(288, 16, 18) X(320, 16, 20) X(324, 18, 18) X(360, 18, 20)
 #define MVSIM_FFT_SIZES_G2(X) \
-    X(320, 16, 20) X(360, 18, 20) X(384, 16, 24) X(432, 18, 24) X(480, 20, 24) X(512, 16, 32) X(576, 24, 24)
+    X(384, 16, 24) X(400, 20, 20) X(432, 18, 24) X(480, 20, 24) X(512, 16, 32) X(540, 20, 27) X(576, 24, 24) X(600, 24, 25) \
+    X(625, 25, 25) X(640, 20, 32) X(648, 24, 27)
 #define MVSIM_FFT_SIZES_G3(X) \
-    X(640, 20, 32) X(720, 24, 30) X(768, 24, 32) X(864, 27, 32) X(960, 30, 32) X(1024, 32, 32)
+    X(675, 25, 27) X(720, 24, 30) X(729, 27, 27) X(768, 24, 32) X(810, 27, 30) X(864, 27, 32) X(900, 30, 30) \
+    X(960, 30, 32)
 #define MVSIM_FFT_SIZES_G4(X) \
-    X(1152, 32, 36) X(1280, 32, 40) X(1440, 36, 40) X(1600, 40, 40)
+    X(1024, 32, 32) X(1080, 30, 36) X(1152, 32, 36) X(1200, 30, 40) X(1280, 32, 40) X(1296, 36, 36) X(1440, 36, 40) \
+    X(1600, 40, 40)
 
 #ifdef MVSIM_EMU_SMALL_ONLY
 #define MVSIM_FFT_SIZES(X) MVSIM_FFT_SIZES_SMALL(X)
@@ -43,13 +48,19 @@ inline const FftSize* fft_size_table(int* count)
     return t;
 }
 
-// smallest supported size >= min_n, or nullptr
-inline const FftSize* pick_fft_size(int64_t min_n)
+// Smallest supported size >= min_n (and <= cap when cap > 0), or nullptr.  (A cost model preferring balanced
+// splits, e.g. 648 = 24*27 over 640 = 20*32, was measured on B200 and lost: the radix-3 sub-transforms cost
+// more than the idle threads of the unbalanced power-of-two split.)
+// mult8: x rows want a multiple of 8 complex columns (64-byte aligned row pitch, whole kx tiles).
+inline const FftSize* pick_fft_size(int64_t min_n, bool mult8 = false, int64_t cap = 0)
 {
     int c;
     const FftSize* t = fft_size_table(&c);
-    for (int i = 0; i < c; ++i)
-        if (t[i].n >= min_n) return &t[i];
+    for (int i = 0; i < c; ++i) {
+        if (t[i].n < min_n || (mult8 && t[i].n % 8 != 0)) continue;
+        if (cap > 0 && t[i].n > cap) break;
+        return &t[i];
+    }
     return nullptr;
 }
 
@@ -112,8 +123,8 @@ inline int make_conv_plan(const int64_t dims[3], const int64_t kdims[3], ConvPla
         p->y_blocks = (int)((dims[1] + room - 1) / room);
         p->y_block = (int)((dims[1] + p->y_blocks - 1) / p->y_blocks);
     }
-    const FftSize* sx = pick_fft_size((dims[0] + kdims[0] - 1 + 1) / 2);
-    const FftSize* sy = pick_fft_size(p->y_block + kdims[1] - 1);
+    const FftSize* sx = pick_fft_size((dims[0] + kdims[0] - 1 + 1) / 2, true);
+    const FftSize* sy = pick_fft_size(p->y_block + kdims[1] - 1, false, cap);
     const FftSize* sz = pick_fft_size(dims[2] + kdims[2] - 1);
     if (!sx || !sy || !sz) return 5;
     p->sx = *sx; p->sy = *sy; p->sz = *sz;

@@ -13,30 +13,19 @@ constexpr int kXThreadsTarget = 256; // x passes: rows per CTA = kXThreadsTarget
 
 constexpr int x_rows_per_block(int a, int b) { return (kXThreadsTarget / (a > b ? a : b)) > 0 ? kXThreadsTarget / (a > b ? a : b) : 1; }
 
-// Lanes (T) = neighbouring kx columns a CTA of the strided passes owns: 8 (64-byte segments, 2 CTAs/SM at
-// the large sizes) or 4 (32-byte sectors, 4 CTAs/SM).  Chosen per context (MVSIM_LANES, default 8); the
-// tile-major workspaces are laid out for the chosen T.
+// Lanes (T) = neighbouring kx columns a CTA of the strided passes owns: 8 complex = 64-byte segments.
+// (T = 4 with 4 CTAs/SM was measured on B200 and gave the same throughput; only T = 8 is built.)
 int strided_lanes();
 
-// returns cudaError_t as int, or -1 when `n` is not in this group.  One translation unit per (group, lanes).
+// returns cudaError_t as int, or -1 when `n` is not in this group.  One translation unit per group.
 #define MVSIM_DECL(g, t) int fft_launch_g##g##_t##t(int kind, int n, const void* params, unsigned gx, unsigned gy, cudaStream_t s);
-MVSIM_DECL(0, 4) MVSIM_DECL(1, 4) MVSIM_DECL(2, 4) MVSIM_DECL(3, 4) MVSIM_DECL(4, 4)
 MVSIM_DECL(0, 8) MVSIM_DECL(1, 8) MVSIM_DECL(2, 8) MVSIM_DECL(3, 8) MVSIM_DECL(4, 8)
 #undef MVSIM_DECL
 
-// x passes do not depend on the lane count; they live in the lanes-8 units
 inline int fft_launch(int kind, int lanes, int n, const void* params, unsigned gx, unsigned gy, cudaStream_t s)
 {
-    int r;
-    if (lanes == 4 && kind >= FFT_SFWD) {
-        r = fft_launch_g0_t4(kind, n, params, gx, gy, s);
-        if (r == -1) r = fft_launch_g1_t4(kind, n, params, gx, gy, s);
-        if (r == -1) r = fft_launch_g2_t4(kind, n, params, gx, gy, s);
-        if (r == -1) r = fft_launch_g3_t4(kind, n, params, gx, gy, s);
-        if (r == -1) r = fft_launch_g4_t4(kind, n, params, gx, gy, s);
-        return r;
-    }
-    r = fft_launch_g0_t8(kind, n, params, gx, gy, s);
+    (void)lanes;
+    int r = fft_launch_g0_t8(kind, n, params, gx, gy, s);
     if (r == -1) r = fft_launch_g1_t8(kind, n, params, gx, gy, s);
     if (r == -1) r = fft_launch_g2_t8(kind, n, params, gx, gy, s);
     if (r == -1) r = fft_launch_g3_t8(kind, n, params, gx, gy, s);

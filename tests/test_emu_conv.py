@@ -91,7 +91,7 @@ def test_kept_slices_and_sum_plane(emu, oracle, shape, kshape, inc):
     assert s == pytest.approx(float(ref.astype(np.float64).sum()), rel=2e-6)
 
 
-@pytest.mark.parametrize("shape,kshape,max_line", [((6, 50, 12), (3, 7, 5), 24), ((4, 33, 9), (2, 4, 3), 16), ((5, 70, 8), (3, 9, 3), 32)])
+@pytest.mark.parametrize("shape,kshape,max_line", [((6, 50, 12), (3, 7, 5), 24), ((4, 33, 9), (2, 4, 3), 16), ((5, 70, 8), (3, 9, 3), 30)])
 def test_overlap_save_blocks_along_y(emu, oracle, shape, kshape, max_line):
     """y lines longer than the size table are convolved in overlap-save blocks (the 2048+255 rows of the
     largest single volume); max_line forces the same code path at test sizes."""
@@ -112,7 +112,7 @@ def test_overlap_save_blocks_along_y(emu, oracle, shape, kshape, max_line):
 
 
 @pytest.mark.parametrize("world", [2, 4])
-@pytest.mark.parametrize("shape,kshape,max_line", [((8, 14, 50), (3, 5, 9), 0), ((4, 40, 120), (5, 7, 3), 24)])
+@pytest.mark.parametrize("shape,kshape,max_line", [((8, 14, 110), (3, 5, 9), 0), ((4, 40, 120), (5, 7, 3), 24)])
 def test_slab_decomposed_convolution_with_host_all_to_all(emu, oracle, world, shape, kshape, max_line):
     """Largest-single-volume path: z slabs for the x/y passes, kx tiles for the z pass, two
     all-to-all transposes (done on the host here).  Must equal the undecomposed result."""
