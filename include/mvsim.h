@@ -125,6 +125,16 @@ int mvsim_simulate_view(mvsim_ctx* ctx, const mvsim_view_params* p, const float*
 int mvsim_simulate_views(mvsim_ctx* ctx, int n_views, const mvsim_view_params* params, const float* gt,
                          float* const* psfs, float* const* outs);
 
+/* ---- post-acquisition chain of main() (after the sampler) --------------------------------- */
+#define MVSIM_MAX_WEIGHT_VIEWS 16
+/* makeIsotropic (:144-171): out has X*Y*((Z-1)*inc+1) floats */
+int mvsim_make_isotropic(mvsim_ctx* ctx, const float* in, const int64_t dims[3], int inc, float* out);
+/* computeWeightImage (:280-316): cosine taper over 40 px along y (its `delta` argument is unused in the reference) */
+int mvsim_weight_image(mvsim_ctx* ctx, const int64_t dims[3], float* out);
+/* weight normalisation of main() (:615-661), in place on n_views volumes: w_v = min(1, osem * w_v / sum_v w_v);
+ * sum_out (nullable) receives the sum of the normalised weights (sum_weights.tif, :648-663) */
+int mvsim_normalize_weights(mvsim_ctx* ctx, float* const* weights, int n_views, const int64_t dims[3], float osem, float* sum_out);
+
 /* ---- device-resident volumes (SNR sweeps a la S/SimulateTileStitching.java:131-189) ------- */
 int mvsim_volume_create(mvsim_ctx* ctx, const int64_t dims[3], mvsim_volume** vol);
 int mvsim_volume_free(mvsim_ctx* ctx, mvsim_volume* vol);

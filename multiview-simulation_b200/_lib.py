@@ -58,6 +58,9 @@ SYMBOLS = [
     ("mvsim_poisson", C.c_int, [_vp, _fp, C.c_size_t, C.c_double, C.c_uint64, C.c_uint64]),
     ("mvsim_simulate_view", C.c_int, [_vp, C.POINTER(ViewParams), _fp, _fp, _fp]),
     ("mvsim_simulate_views", C.c_int, [_vp, C.c_int, C.POINTER(ViewParams), _fp, C.POINTER(_fp), C.POINTER(_fp)]),
+    ("mvsim_make_isotropic", C.c_int, [_vp, _fp, _i64p, C.c_int, _fp]),
+    ("mvsim_weight_image", C.c_int, [_vp, _i64p, _fp]),
+    ("mvsim_normalize_weights", C.c_int, [_vp, C.POINTER(_fp), C.c_int, _i64p, C.c_float, _fp]),
     ("mvsim_volume_create", C.c_int, [_vp, _i64p, C.POINTER(_vp)]),
     ("mvsim_volume_free", C.c_int, [_vp, _vp]),
     ("mvsim_volume_dims", C.c_int, [_vp, _i64p]),

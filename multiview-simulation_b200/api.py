@@ -292,6 +292,37 @@ class SimulateMultiViewDataset:
         return out
 
     @staticmethod
+    def makeIsotropic(img, inc, ctx=None):
+        """Linear z up-sampling by `inc` over the mirror-single extension (:144-171)."""
+        ctx = ctx or default_context()
+        img = _vol(img)
+        z, y, x = img.shape
+        out = np.empty(((z - 1) * inc + 1, y, x), dtype=np.float32)
+        check(ctx._lib.mvsim_make_isotropic(ctx.h, fptr(img), dims3(img.shape), inc, fptr(out)), ctx.h)
+        return out
+
+    @staticmethod
+    def computeWeightImage(img_or_shape, delta=None, ctx=None):
+        """Cosine-taper weight image along y with the dims of the argument (:280-316); `delta` is ignored like in the reference."""
+        ctx = ctx or default_context()
+        shape = tuple(img_or_shape.shape) if hasattr(img_or_shape, "shape") else tuple(img_or_shape)
+        out = np.empty(shape, dtype=np.float32)
+        check(ctx._lib.mvsim_weight_image(ctx.h, dims3(shape), fptr(out)), ctx.h)
+        return out
+
+    @staticmethod
+    def normalizeWeights(weights, osem, ctx=None):
+        """The cross-view weight normalisation at the end of main() (:615-661), in place; returns the sum image."""
+        ctx = ctx or default_context()
+        for w in weights:
+            _inplace(w, "weight")
+        fpp = C.POINTER(C.c_float)
+        arr = (fpp * len(weights))(*[fptr(w) for w in weights])
+        s = np.empty_like(weights[0])
+        check(ctx._lib.mvsim_normalize_weights(ctx.h, arr, len(weights), dims3(weights[0].shape), osem, fptr(s)), ctx.h)
+        return s
+
+    @staticmethod
     def simulateViews(gt, psfs, degrees, axis=0, delta=0.01, inc=3, poissonSNR=25.0, rnd=None, ctx=None, outs=None,
                       first_stream=0, strict_reference=True):
         """The view loop of main() (:567-613) for the acquisition stages: one ground truth, one PSF and

@@ -623,6 +623,67 @@ int mvsim_simulate_views(mvsim_ctx* ctx, int n_views, const mvsim_view_params* p
     return st != MVSIM_OK ? st : st2;
 }
 
+// ---- post-acquisition chain ---------------------------------------------------------------------
+int mvsim_make_isotropic(mvsim_ctx* ctx, const float* in, const int64_t dims[3], int inc, float* out)
+{
+    MVSIM_ENTER(ctx);
+    if (!in || !out) return set_error(ctx, MVSIM_EINVAL, "make_isotropic: null buffer");
+    MVSIM_TRY(check_dims(ctx, dims, "make_isotropic"));
+    if (inc < 1) return set_error(ctx, MVSIM_EINVAL, "make_isotropic: inc must be >= 1");
+    const size_t bytes = elems(dims) * sizeof(float);
+    const size_t obytes = (size_t)(dims[0] * dims[1] * ((dims[2] - 1) * inc + 1)) * sizeof(float);
+    DevBuf a(ctx), b(ctx);
+    MVSIM_TRY(a.alloc(bytes));
+    MVSIM_TRY(b.alloc(obytes));
+    MVSIM_TRY(h2d(ctx, a.p, in, bytes));
+    MVSIM_TRY(k_make_isotropic(ctx, a.f(), dims, inc, b.f()));
+    MVSIM_TRY(d2h(ctx, out, b.p, obytes));
+    return sync(ctx);
+}
+
+int mvsim_weight_image(mvsim_ctx* ctx, const int64_t dims[3], float* out)
+{
+    MVSIM_ENTER(ctx);
+    if (!out) return set_error(ctx, MVSIM_EINVAL, "weight_image: null buffer");
+    MVSIM_TRY(check_dims(ctx, dims, "weight_image"));
+    const size_t bytes = elems(dims) * sizeof(float);
+    DevBuf a(ctx);
+    MVSIM_TRY(a.alloc(bytes));
+    MVSIM_TRY(k_weight_image(ctx, dims, a.f()));
+    MVSIM_TRY(d2h(ctx, out, a.p, bytes));
+    return sync(ctx);
+}
+
+int mvsim_normalize_weights(mvsim_ctx* ctx, float* const* weights, int n_views, const int64_t dims[3], float osem, float* sum_out)
+{
+    MVSIM_ENTER(ctx);
+    if (!weights || n_views < 1 || n_views > MVSIM_MAX_WEIGHT_VIEWS) return set_error(ctx, MVSIM_EINVAL, "normalize_weights: 1..%d views", MVSIM_MAX_WEIGHT_VIEWS);
+    MVSIM_TRY(check_dims(ctx, dims, "normalize_weights"));
+    const size_t n = elems(dims), bytes = n * sizeof(float);
+    std::vector<void*> held;
+    float* d[MVSIM_MAX_WEIGHT_VIEWS] = {};
+    int st = MVSIM_OK;
+    for (int v = 0; v < n_views && st == MVSIM_OK; ++v) {
+        if (!weights[v]) { st = set_error(ctx, MVSIM_EINVAL, "normalize_weights: null buffer"); break; }
+        void* q = nullptr;
+        if ((st = dev_alloc(ctx, &q, bytes)) != MVSIM_OK) break;
+        held.push_back(q);
+        d[v] = static_cast<float*>(q);
+        st = h2d(ctx, q, weights[v], bytes);
+    }
+    float* dsum = nullptr;
+    if (st == MVSIM_OK && sum_out) {
+        void* q = nullptr;
+        if ((st = dev_alloc(ctx, &q, bytes)) == MVSIM_OK) { held.push_back(q); dsum = static_cast<float*>(q); }
+    }
+    if (st == MVSIM_OK) st = k_normalize_weights(ctx, d, n_views, n, osem, dsum);
+    for (int v = 0; v < n_views && st == MVSIM_OK; ++v) st = d2h(ctx, weights[v], d[v], bytes);
+    if (st == MVSIM_OK && sum_out) st = d2h(ctx, sum_out, dsum, bytes);
+    const int st2 = sync(ctx);
+    for (void* q : held) dev_free(ctx, q);
+    return st != MVSIM_OK ? st : st2;
+}
+
 // ---- device-resident volumes ------------------------------------------------------------------
 int mvsim_volume_create(mvsim_ctx* ctx, const int64_t dims[3], mvsim_volume** vol)
 {

@@ -76,6 +76,9 @@ int k_adjust_apply(mvsim_ctx* ctx, float* inout, size_t n, const double* d_corr,
 // out[x,y,cz] = f(in[x,y,cz*inc]); d_corr != null fuses adjustImage; snr >= 0 adds Poisson noise
 int k_extract(mvsim_ctx* ctx, const float* in, const int64_t dims[3], int inc, const double* d_corr, float min_value,
               float snr, uint64_t seed, uint64_t stream, float* out);
+int k_make_isotropic(mvsim_ctx* ctx, const float* in, const int64_t dims[3], int inc, float* out);
+int k_weight_image(mvsim_ctx* ctx, const int64_t dims[3], float* out);
+int k_normalize_weights(mvsim_ctx* ctx, float* const* d_weights, int n_views, size_t n, float osem, float* d_sum_out);
 int k_poisson(mvsim_ctx* ctx, float* inout, size_t n, double snr, uint64_t seed, uint64_t stream);
 
 // convolution driver (conv.cu): psf normalised, device pointers; sum of the output voxels -> d_sum when non-null.

@@ -515,6 +515,103 @@ int k_extract(mvsim_ctx* ctx, const float* in, const int64_t dims[3], int inc, c
     return MVSIM_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// post-acquisition chain of main()
+//   makeIsotropic      S/SimulateMultiViewDataset.java:144-171   linear z up-sampling, mirror-single
+//   computeWeightImage S/SimulateMultiViewDataset.java:280-316   cosine taper along y
+//   weight normalisation                                 :615-661 the one cross-view reduction
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int mirror_idx(int i, int n)
+{
+    if ((unsigned)i < (unsigned)n) return i;
+    if (n == 1) return 0;
+    const int p = 2 * (n - 1);
+    int j = i % p;
+    if (j < 0) j += p;
+    return j >= n ? p - j : j;
+}
+
+// x, y are integer positions, so the n-linear interpolation of :150,167 reduces to two taps along z:
+// out = f32(f32(a * (1 - w)) + f32(b * w)), position (float)z / (float)inc widened to double (:165)
+__global__ void __launch_bounds__(256) make_isotropic_kernel(const float* __restrict__ in, float* __restrict__ out, long long plane, int Z,
+                                                             long long n_out, int inc)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_out) return;
+    const int zo = (int)(i / plane);
+    const long long r = i - (long long)zo * plane;
+    const double zf = (double)((float)zo / (float)inc);
+    const double f = floor(zf);
+    const double w = zf - f, wi = 1.0 - w;
+    const int iz = (int)f;
+    const float a = __ldg(in + (long long)mirror_idx(iz, Z) * plane + r);
+    const float b = __ldg(in + (long long)mirror_idx(iz + 1, Z) * plane + r);
+    out[i] = __fadd_rn((float)__dmul_rn((double)a, wi), (float)__dmul_rn((double)b, w));
+}
+
+int k_make_isotropic(mvsim_ctx* ctx, const float* in, const int64_t dims[3], int inc, float* out)
+{
+    const long long plane = (long long)dims[0] * dims[1];
+    const long long n_out = plane * ((dims[2] - 1) * inc + 1);
+    make_isotropic_kernel<<<blocks_for((size_t)n_out, 256), 256, 0, ctx->stream>>>(in, out, plane, (int)dims[2], n_out, inc);
+    MVSIM_LAUNCH_CHECK(ctx);
+    return MVSIM_OK;
+}
+
+__global__ void __launch_bounds__(256) weight_image_kernel(float* __restrict__ out, int X, int Y, long long n)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int y = (int)((i / X) % Y);
+    const int l = Y - y - 1, half = Y / 2, span = 40;       // cosineSpan (:283)
+    float v;
+    if (l < half) v = 1.0f;
+    else if (l > half + span) v = 0.0f;
+    else v = (float)((cos(((double)(l - half) / (double)span) * 3.14159265358979323846) + 1.0) / 2.0);
+    out[i] = v;
+}
+
+int k_weight_image(mvsim_ctx* ctx, const int64_t dims[3], float* out)
+{
+    const size_t n = (size_t)dims[0] * dims[1] * dims[2];
+    weight_image_kernel<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(out, (int)dims[0], (int)dims[1], (long long)n);
+    MVSIM_LAUNCH_CHECK(ctx);
+    return MVSIM_OK;
+}
+
+struct WeightPtrs { float* w[MVSIM_MAX_WEIGHT_VIEWS]; };
+
+// float accumulation in view order like the cursors of :627-639; sum_out = sum of the normalised weights (:648-661)
+__global__ void __launch_bounds__(256) normalize_weights_kernel(WeightPtrs p, int n_views, size_t n, float osem, float* __restrict__ sum_out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float v[MVSIM_MAX_WEIGHT_VIEWS];
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < MVSIM_MAX_WEIGHT_VIEWS; ++k)
+        if (k < n_views) { v[k] = p.w[k][i]; sum = __fadd_rn(sum, v[k]); }
+    float s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < MVSIM_MAX_WEIGHT_VIEWS; ++k)
+        if (k < n_views) {
+            const float o = sum == 0.f ? 0.f : fminf(1.0f, __fmul_rn(osem, __fdiv_rn(v[k], sum)));
+            p.w[k][i] = o;
+            s2 = __fadd_rn(s2, o);
+        }
+    if (sum_out) sum_out[i] = s2;
+}
+
+int k_normalize_weights(mvsim_ctx* ctx, float* const* d_weights, int n_views, size_t n, float osem, float* d_sum_out)
+{
+    if (n_views < 1 || n_views > MVSIM_MAX_WEIGHT_VIEWS) return set_error(ctx, MVSIM_EINVAL, "normalize_weights: 1..%d views", MVSIM_MAX_WEIGHT_VIEWS);
+    WeightPtrs p;
+    for (int k = 0; k < MVSIM_MAX_WEIGHT_VIEWS; ++k) p.w[k] = k < n_views ? d_weights[k] : nullptr;
+    normalize_weights_kernel<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(p, n_views, n, osem, d_sum_out);
+    MVSIM_LAUNCH_CHECK(ctx);
+    return MVSIM_OK;
+}
+
 __global__ void __launch_bounds__(256) poisson_kernel(float* __restrict__ a, size_t n, double mul, PoissonKey key)
 {
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -538,6 +538,66 @@ int orc_extract_slices(const float* in, const int64_t dims[3], int inc, float sn
 }
 
 /* ------------------------------------------------------------------------ */
+/* "next" row f-1: post-acquisition chain of main()                            */
+/* makeIsotropic  S/SimulateMultiViewDataset.java:144-171: linear z up-sampling */
+/* by inc over Views.extendMirrorSingle, position (x, y, (float)z/(float)inc).  */
+/* ------------------------------------------------------------------------ */
+int orc_make_isotropic(const float* in, const int64_t dims[3], int inc, float* out)
+{
+    if (inc < 1) return ORC_EINVAL;
+    const int64_t X = dims[0], Y = dims[1], Z = dims[2];
+    const int64_t ZO = (Z - 1) * inc + 1;
+#pragma omp parallel for collapse(2) schedule(static) num_threads(stage_threads())
+    for (int64_t z = 0; z < ZO; ++z)
+        for (int64_t y = 0; y < Y; ++y)
+            for (int64_t x = 0; x < X; ++x) {
+                double p[3] = { (double)x, (double)y, (double)((float)z / (float)inc) };   /* :163-165 */
+                out[x + X * (y + Y * z)] = nlinear3(in, dims, p, 1);
+            }
+    return ORC_OK;
+}
+
+/* computeWeightImage  S/SimulateMultiViewDataset.java:280-316 (cosine taper over 40 px along y; delta unused) */
+int orc_weight_image(const int64_t dims[3], float* out)
+{
+    const int64_t X = dims[0], Y = dims[1], Z = dims[2];
+    const int cosine_span = 40;
+    const int size_y = (int)Y;
+    for (int64_t z = 0; z < Z; ++z)
+        for (int64_t y = 0; y < Y; ++y) {
+            const int l = size_y - (int)y - 1;
+            float v;
+            if (l < size_y / 2) v = 1.0f;
+            else if (l > size_y / 2 + cosine_span) v = 0.0f;
+            else {
+                const double pos = ((double)(l - size_y / 2) / (double)cosine_span) * 3.14159265358979323846;
+                v = (float)((cos(pos) + 1.0) / 2.0);
+            }
+            for (int64_t x = 0; x < X; ++x) out[x + X * (y + Y * z)] = v;
+        }
+    return ORC_OK;
+}
+
+/* weight normalisation of main()  S/SimulateMultiViewDataset.java:615-661: in place over n_views volumes,
+ * w_v = min(1, osem * (w_v / sum)); sum_out (nullable) = sum of the normalised weights */
+int orc_normalize_weights(float** w, int n_views, size_t n, float osem, float* sum_out)
+{
+    if (n_views < 1) return ORC_EINVAL;
+    for (size_t i = 0; i < n; ++i) {
+        float sum = 0;
+        for (int v = 0; v < n_views; ++v) sum += w[v][i];
+        float s2 = 0;
+        for (int v = 0; v < n_views; ++v) {
+            if (sum == 0) w[v][i] = 0;
+            else w[v][i] = fminf(1.0f, osem * (w[v][i] / (float)sum));
+            s2 += w[v][i];
+        }
+        if (sum_out) sum_out[i] = s2;
+    }
+    return ORC_OK;
+}
+
+/* ------------------------------------------------------------------------ */
 /* The per-view loop body S/SimulateMultiViewDataset.java:570-585, used by     */
 /* smoke() and bench.py's cpu_baseline leg.  times[5] (seconds): rotate,       */
 /* attenuate, convolve, adjust, extract+poisson.                              */

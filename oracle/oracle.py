@@ -59,6 +59,9 @@ def lib():
         L.orc_fft_size.restype = C.c_int64
         L.orc_set_stage_threads.argtypes = [C.c_int]
         L.orc_max_threads.restype = C.c_int
+        L.orc_make_isotropic.argtypes = [fp, i64p, C.c_int, fp]
+        L.orc_weight_image.argtypes = [i64p, fp]
+        L.orc_normalize_weights.argtypes = [C.POINTER(fp), C.c_int, C.c_size_t, C.c_float, fp]
         L.orc_simulate_view.argtypes = [fp, i64p, fp, i64p, C.c_int, C.c_int, C.c_double, C.c_float,
                                         C.c_float, C.c_int, C.c_float, C.c_int64, C.c_int, C.c_int,
                                         fp, fp, dp]
@@ -198,3 +201,27 @@ def simulate_view(gt, psf, axis=0, degrees=15, delta=0.01, min_value=0.0001, tar
         L.orc_set_stage_threads(0)
     _check(err, "simulate_view")
     return out, conv, list(times)
+
+
+def make_isotropic(vol, inc):
+    vol = _vol(vol)
+    z, y, x = vol.shape
+    out = np.empty(((z - 1) * inc + 1, y, x), dtype=np.float32)
+    _check(lib().orc_make_isotropic(_f(vol), _dims(vol), inc, _f(out)), "make_isotropic")
+    return out
+
+
+def weight_image(shape_zyx):
+    out = np.empty(shape_zyx, dtype=np.float32)
+    _check(lib().orc_weight_image(_dims(out), _f(out)), "weight_image")
+    return out
+
+
+def normalize_weights(weights, osem):
+    """In place on a list of equal-shape float32 volumes; returns the sum of the normalised weights."""
+    n = len(weights)
+    fp = C.POINTER(C.c_float)
+    arr = (fp * n)(*[_f(w) for w in weights])
+    s = np.empty_like(weights[0])
+    _check(lib().orc_normalize_weights(arr, n, weights[0].size, osem, _f(s)), "normalize_weights")
+    return s
