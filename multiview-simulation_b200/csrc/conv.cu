@@ -1,6 +1,9 @@
 // CUDA backend of the FFT convolution (host logic in fft/conv_driver.h, kernels in fft/line_fft.cuh).
 // Replaces convolve() S/SimulateMultiViewDataset.java:253-264 (FFTConvolution on an ExecutorService).
+#include <cuda.h>
 #include <stdlib.h>
+
+#include <string.h>
 
 #include "ctx.h"
 #include "fft/conv_driver.h"
@@ -9,6 +12,39 @@
 namespace mvsim {
 
 namespace {
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup (libmvsim.so does not link libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult st;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &st) != cudaSuccess || st != cudaDriverEntryPointSuccess) p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// tensor map over the PSF spectrum h = [tiles][Nz][Ny][T] complex64 seen as float32 [tiles][Nz][Ny][2T]; box = 128 kz rows of one (tile, ky)
+static bool make_h_tensor_map(const ZFusedParams& q, int lanes, int tiles, int nz, int ny, unsigned long long out[16])
+{
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc || getenv("MVSIM_NO_TMA")) return false;
+    static_assert(sizeof(CUtensorMap) == 16 * sizeof(unsigned long long), "CUtensorMap size");
+    CUtensorMap m;
+    const cuuint64_t dims[4] = { (cuuint64_t)(2 * lanes), (cuuint64_t)ny, (cuuint64_t)nz, (cuuint64_t)tiles };
+    const cuuint64_t strides[3] = { (cuuint64_t)lanes * 8, (cuuint64_t)ny * lanes * 8, (cuuint64_t)nz * ny * lanes * 8 };
+    const cuuint32_t box[4] = { (cuuint32_t)(2 * lanes), 1, (cuuint32_t)kTmaBoxRows, 1 };
+    const cuuint32_t estr[4] = { 1, 1, 1, 1 };
+    const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float2*>(q.h), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return false;
+    memcpy(out, &m, sizeof(m));
+    return true;
+}
 
 struct CudaLauncher {
     mvsim_ctx* ctx;
@@ -39,10 +75,12 @@ struct CudaLauncher {
         const unsigned gx = q.swap_grid ? (unsigned)n_outer : tiles, gy = q.swap_grid ? tiles : (unsigned)n_outer;
         return finish(fft_launch(inverse ? FFT_SINV : FFT_SFWD, lanes, s.n, &q, gx, gy, ctx->stream), "strided pass");
     }
-    int launch_zfused(const FftSize& s, const ZFusedParams& q, int n_tiles, int n_outer)
+    int launch_zfused(const FftSize& s, const ZFusedParams& q0, int n_tiles, int n_outer)
     {
         StageTimer t(ctx, MVSIM_T_FFT_ZFUSED);
         const unsigned tiles = (unsigned)n_tiles;
+        ZFusedParams q = q0;
+        q.use_tma = make_h_tensor_map(q, lanes, n_tiles, s.n, n_outer, q.h_tmap) ? 1 : 0;
         return finish(fft_launch(FFT_ZFUSED, lanes, s.n, &q, (unsigned)n_outer, tiles, ctx->stream), "fused z pass");
     }
 };

@@ -14,9 +14,9 @@ template <class K> constexpr int min_blocks()
     return K::IS_X ? (K::THREADS <= 256 ? 3 : 1) : (K::THREADS <= 160 ? 4 : (K::THREADS <= 288 ? 2 : 1));
 }
 
-template <class K> __global__ void __launch_bounds__(K::THREADS, min_blocks<K>()) fft_kernel(const typename K::Params q)
+template <class K> __global__ void __launch_bounds__(K::THREADS, min_blocks<K>()) fft_kernel(const __grid_constant__ typename K::Params q)
 {
-    extern __shared__ __align__(16) unsigned char smraw[];
+    extern __shared__ __align__(128) unsigned char smraw[];
     float2* sm = reinterpret_cast<float2*>(smraw);
     typename K::State st;
     K::template phase<0>(q, blockIdx.x, blockIdx.y, threadIdx.x, sm, st);

@@ -223,7 +223,11 @@ struct ZFusedParams {
     long long u_tstride;    // kx-tile stride of u inside a segment (= zg*Ny*T)
     long long seg_stride;   // segment stride of u (= tiles*zg*Ny*T)
     long long h_tstride;    // kx-tile stride of h (= Nz*Ny*T)
+    int use_tma;            // 1: the H tile is fetched by the TMA unit through h_tmap (device only), 0: cp.async per thread
+    alignas(64) unsigned long long h_tmap[16];   // CUtensorMap over h as float32 [tiles][Nz][Ny][2T], box [1][128][1][2T]
 };
+
+constexpr int kTmaBoxRows = 128;    // kz rows per TMA box
 
 // offset of global plane z in the segmented layout
 MVSIM_HD long long zfused_plane_offset(const ZFusedParams& q, int z)
@@ -238,8 +242,11 @@ template <int A_, int B_, int T_> struct ZFused : LineShape<A_, B_> {
     using S = LineShape<A_, B_>;
     static constexpr int A = A_, B = B_, T = T_;
     static constexpr int THREADS = T * S::P;
-    // exchange area + the H tile [N][T] (prefetched with cp.async while the forward transform runs)
-    static constexpr int SMEM_BYTES = (S::ELEMS + S::N) * T * (int)sizeof(float2);
+    // exchange area (rounded to 128 B) + the H tile [N rounded up to whole TMA boxes][T] (fetched asynchronously -- TMA or
+    // cp.async -- while the forward transform runs) + one mbarrier
+    static constexpr int EXCH_ELEMS = (S::ELEMS * T + 15) / 16 * 16;
+    static constexpr int H_ROWS = (S::N + kTmaBoxRows - 1) / kTmaBoxRows * kTmaBoxRows;
+    static constexpr int SMEM_BYTES = (EXCH_ELEMS + H_ROWS * T) * (int)sizeof(float2) + 16;
     static constexpr int NPH = 6;
     using Params = ZFusedParams;
     using State = RegState<B>;
@@ -251,8 +258,24 @@ template <int A_, int B_, int T_> struct ZFused : LineShape<A_, B_> {
         const int lane = tid % T, p = tid / T;
         const int tile = by, outer = bx;
         const bool active = (tile + q.tile0) * T + lane < q.kx_count;
-        float2* smh = sm + S::ELEMS * T;
+        float2* smh = sm + EXCH_ELEMS;
+#ifdef __CUDA_ARCH__
+        uint64_t* bar = reinterpret_cast<uint64_t*>(smh + H_ROWS * T);
+#endif
         if (PH == 0) {
+#ifdef __CUDA_ARCH__
+            if (q.use_tma) {
+                // one thread programs the TMA unit: ceil(N/128) boxes of 128 kz rows x 64 bytes, completion on the mbarrier
+                if (tid == 0) {
+                    constexpr int NBOX = H_ROWS / kTmaBoxRows;
+                    mbar_init(bar, 1);
+                    mbar_expect_tx(bar, (unsigned)(NBOX * kTmaBoxRows * T * sizeof(float2)));
+                    MVSIM_UNROLL
+                    for (int b = 0; b < NBOX; ++b)
+                        tma_load_4d(smh + b * kTmaBoxRows * T, q.h_tmap, 0, outer, b * kTmaBoxRows, tile, bar);
+                }
+            } else
+#endif
             {   // H tile -> shared memory, 16 bytes per copy, rows of T float2
                 constexpr int CH = T / 2;       // 16-byte chunks per row
                 const float2* hs = q.h + tile * q.h_tstride + outer * q.ostride;
@@ -280,6 +303,9 @@ template <int A_, int B_, int T_> struct ZFused : LineShape<A_, B_> {
         } else if (PH == 1) {
             if (p < A && active) {
                 fwd_second<A, B>(p, st.y, sm, lane, T);
+#ifdef __CUDA_ARCH__
+                if (q.use_tma) mbar_wait(bar, 0);       // the barrier before this phase made the init visible
+#endif
                 MVSIM_UNROLL
                 for (int k2 = 0; k2 < B; ++k2) st.y[k2] = cmul(st.y[k2], smh[(p + A * k2) * T + lane]);
             }
