@@ -62,34 +62,61 @@ MVSIM_HD PoissonKey make_poisson_key(uint64_t seed, uint64_t stream)
 // (0,1) float uniform from 32 random bits (24 significant)
 MVSIM_HD float u01f(uint32_t x) { return ((float)(x >> 8) + 0.5f) * 0x1.0p-24f; }
 
-// One variate from two 32-bit words (ru: inversion uniform / PTRS U, rv: PTRS V).  The arithmetic is
-// float32 on the paths nearly every voxel takes (probabilities accurate to ~1e-7, far below what any
-// finite sample can resolve); only the rare exact acceptance test of PTRS, whose two sides nearly
-// cancel, is evaluated in double.  Rejected PTRS proposals draw fresh words from the voxel's own
-// counter (index, attempt >= 2), so the result depends on (seed, stream, voxel index) only.
-MVSIM_HD float poisson_one(double lam_d, uint32_t ru, uint32_t rv, uint64_t index, PoissonKey key)
+// PTRS hat-function constants for one lambda (float32 everywhere on the fast path)
+struct PtrsParams { float lam, b, a, vr; };
+
+MVSIM_HD PtrsParams ptrs_params(float lam)
 {
-    if (!(lam_d > 0.0)) return 0.f;
-    if (lam_d < 10.0) {
-        // inversion by sequential search: k = min { k : u <= sum_{j<=k} e^-lam lam^j / j! }
-        const float lam = (float)lam_d;
-        const float u = u01f(ru);
-        float p = expf(-lam), s = p;
-        int k = 0;
-        while (u > s && k < 64) { ++k; p *= lam / (float)k; s += p; }
-        return (float)k;
+    PtrsParams q;
+    q.lam = lam;
+    q.b = 0.931f + 2.53f * sqrtf(lam);
+    q.a = -0.059f + 0.02483f * q.b;
+    q.vr = 0.9277f - 3.6224f / (q.b - 2.0f);
+    return q;
+}
+
+// One PTRS proposal from two random words.  Returns 1 = accepted by the squeeze (k valid), 0 = rejected outright,
+// 2 = needs the exact acceptance test (k, us, V valid).
+MVSIM_HD int ptrs_propose(const PtrsParams& q, uint32_t ru, uint32_t rv, float& kf, float& us, float& V)
+{
+    const float U = u01f(ru) - 0.5f;
+    V = u01f(rv);
+    us = 0.5f - fabsf(U);
+    kf = floorf((2.0f * q.a / us + q.b) * U + q.lam + 0.43f);
+    if (us >= 0.07f && V <= q.vr) return 1;
+    if (kf < 0.0f || (us < 0.013f && V > us)) return 0;
+    return 2;
+}
+
+// exact acceptance test  log(V * invalpha / (a/us^2 + b)) <= -lam + k log(lam) - log(k!)
+// with log(k!) by Stirling's series for k >= 10; rewritten around d = k - lam so that the large terms
+// cancel analytically:  rhs = d - k log1p(d/lam) - log(2 pi k)/2 - (1/(12k) - 1/(360k^3) + ...)
+MVSIM_HD bool ptrs_accept(const PtrsParams& q, double lam_d, float kf, float us, float V)
+{
+    const float invalpha = 1.1239f + 1.1328f / (q.b - 3.4f);
+    if (q.lam <= 3.0e4f) {
+        const float lhs = logf(V * invalpha / (q.a / (us * us) + q.b));
+        float rhs;
+        if (kf < 10.0f) {
+            rhs = -q.lam + kf * logf(q.lam) - lgammaf(kf + 1.0f);
+        } else {
+            const float d = kf - q.lam, ik = 1.0f / kf;
+            rhs = d - kf * log1pf(d / q.lam) - 0.5f * logf(6.2831853f * kf) - ik * (0.083333333f - 0.0027777778f * ik * ik);
+        }
+        return lhs <= rhs;
     }
-    if (lam_d > 1.0e7) {
-        // beyond the float32 resolution of the PTRS proposal (and of the float32 output): normal limit
-        const double u1 = ((double)ru + 0.5) * 0x1.0p-32, u2 = ((double)rv + 0.5) * 0x1.0p-32;
-        const double g = sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2);
-        return (float)floor(lam_d + sqrt(lam_d) * g + 0.5);
-    }
-    const float lam = (float)lam_d;
-    const float slam = sqrtf(lam);
-    const float b = 0.931f + 2.53f * slam;
-    const float a = -0.059f + 0.02483f * b;
-    const float vr = 0.9277f - 3.6224f / (b - 2.0f);
+    const double k = (double)kf, usd = (double)us, d = k - lam_d, ik = 1.0 / k;
+    const double lhs = log((double)V * (double)invalpha / ((double)q.a / (usd * usd) + (double)q.b));
+    const double rhs = d - k * log1p(d / lam_d) - 0.5 * log(6.283185307179586 * k) - ik * (1.0 / 12.0 - ik * ik * (1.0 / 360.0 - ik * ik / 1260.0));
+    return lhs <= rhs;
+}
+
+// Finishes a voxel whose first proposal (ru, rv) was not accepted by the squeeze: exact test for it, then fresh
+// proposals from the voxel's own counter (index, attempt >= 2) until one is accepted.
+MVSIM_HD float ptrs_resolve(double lam_d, uint32_t ru, uint32_t rv, uint64_t index, PoissonKey key)
+{
+    const PtrsParams q = ptrs_params((float)lam_d);
+    float kf, us, V;
     for (uint32_t attempt = 0; attempt < 64; ++attempt) {
         if (attempt > 0) {
             Philox4 c;
@@ -97,53 +124,78 @@ MVSIM_HD float poisson_one(double lam_d, uint32_t ru, uint32_t rv, uint64_t inde
             const Philox4 r = philox4x32_10(c, key.k0, key.k1);
             ru = r.x; rv = r.y;
         }
-        const float U = u01f(ru) - 0.5f;
-        const float V = u01f(rv);
-        const float us = 0.5f - fabsf(U);
-        const float kf = floorf((2.0f * a / us + b) * U + lam + 0.43f);
-        if (us >= 0.07f && V <= vr) return kf;
-        if (kf < 0.0f || (us < 0.013f && V > us)) continue;
-        // exact acceptance test  log(V * invalpha / (a/us^2 + b)) <= -lam + k log(lam) - log(k!)
-        // with log(k!) by Stirling's series for k >= 10; rewritten around d = k - lam so that the large terms
-        // cancel analytically:  rhs = d - k log1p(d/lam) - log(2 pi k)/2 - (1/(12k) - 1/(360k^3) + ...)
-        const float invalpha = 1.1239f + 1.1328f / (b - 3.4f);
-        if (lam <= 3.0e4f) {
-            const float lhs = logf(V * invalpha / (a / (us * us) + b));
-            float rhs;
-            if (kf < 10.0f) {
-                rhs = -lam + kf * logf(lam) - lgammaf(kf + 1.0f);
-            } else {
-                const float d = kf - lam, ik = 1.0f / kf;
-                rhs = d - kf * log1pf(d / lam) - 0.5f * logf(6.2831853f * kf) - ik * (0.083333333f - 0.0027777778f * ik * ik);
-            }
-            if (lhs <= rhs) return kf;
-        } else {
-            const double k = (double)kf, usd = (double)us, d = k - lam_d, ik = 1.0 / k;
-            const double lhs = log((double)V * (double)invalpha / ((double)a / (usd * usd) + (double)b));
-            const double rhs = d - k * log1p(d / lam_d) - 0.5 * log(6.283185307179586 * k) -
-                               ik * (1.0 / 12.0 - ik * ik * (1.0 / 360.0 - ik * ik / 1260.0));
-            if (lhs <= rhs) return kf;
-        }
+        const int st = ptrs_propose(q, ru, rv, kf, us, V);
+        if (st == 1 || (st == 2 && ptrs_accept(q, lam_d, kf, us, V))) return kf;
     }
-    return floorf(lam + 0.5f);     // unreachable in practice (acceptance ~ 0.9 per attempt)
+    return floorf((float)lam_d + 0.5f);      // unreachable in practice (acceptance ~ 0.9 per proposal)
 }
 
-// Four consecutive voxels (flat indices 4g .. 4g+3) share two Philox blocks: block (g, 0) supplies the
-// first word of each voxel, block (g, 1) -- generated only if some lambda needs it -- the second.
-MVSIM_HD void poisson_group4(const double (&lam)[4], uint64_t group, PoissonKey key, float (&out)[4])
+// Fast part of one variate.  Returns true when done (out valid); false when the voxel needs ptrs_resolve.
+// The arithmetic is float32 on the paths nearly every voxel takes (probabilities accurate to ~1e-7, far below what
+// any finite sample can resolve).  The result depends on (seed, stream, voxel index) only.
+MVSIM_HD bool poisson_fast(double lam_d, uint32_t ru, uint32_t rv, float& out)
+{
+    out = 0.f;
+    if (!(lam_d > 0.0)) return true;
+    if (lam_d < 10.0) {
+        // inversion by sequential search: k = min { k : u <= sum_{j<=k} e^-lam lam^j / j! }
+        const float lam = (float)lam_d;
+        const float u = u01f(ru);
+        float p = expf(-lam), s = p;
+        int k = 0;
+        while (u > s && k < 64) { ++k; p *= lam / (float)k; s += p; }
+        out = (float)k;
+        return true;
+    }
+    if (lam_d > 1.0e7) {
+        // beyond the float32 resolution of the PTRS proposal (and of the float32 output): normal limit
+        const double u1 = ((double)ru + 0.5) * 0x1.0p-32, u2 = ((double)rv + 0.5) * 0x1.0p-32;
+        const double g = sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2);
+        out = (float)floor(lam_d + sqrt(lam_d) * g + 0.5);
+        return true;
+    }
+    float us, V;
+    return ptrs_propose(ptrs_params((float)lam_d), ru, rv, out, us, V) == 1;
+}
+
+// Four consecutive voxels (flat indices 4g .. 4g+3) share two Philox blocks: block (g, 0) supplies the first word
+// of each voxel, block (g, 1) -- generated only if some lambda needs it -- the second.  Voxels whose first PTRS
+// proposal fails the squeeze are finished afterwards in ONE loop (one copy of the slow code, and lanes of a warp
+// share its iterations), instead of diverging four times.
+// fast part for the four voxels of a group: returns the 4-bit mask of voxels that still need ptrs_resolve and the random
+// words of the group (the first proposal of a pending voxel is re-derived from them)
+MVSIM_HD unsigned poisson_group4_fast(const double (&lam)[4], uint64_t group, PoissonKey key, float (&out)[4], Philox4& r0, Philox4& r1)
 {
     Philox4 c;
     c.x = (uint32_t)group; c.y = (uint32_t)(group >> 32); c.z = key.stream_lo; c.w = 0;
-    const Philox4 r0 = philox4x32_10(c, key.k0, key.k1);
-    Philox4 r1 = { 0u, 0u, 0u, 0u };
+    r0 = philox4x32_10(c, key.k0, key.k1);
+    r1.x = r1.y = r1.z = r1.w = 0u;
     if (lam[0] >= 10.0 || lam[1] >= 10.0 || lam[2] >= 10.0 || lam[3] >= 10.0) {
         c.w = 1;
         r1 = philox4x32_10(c, key.k0, key.k1);
     }
-    out[0] = poisson_one(lam[0], r0.x, r1.x, 4 * group + 0, key);
-    out[1] = poisson_one(lam[1], r0.y, r1.y, 4 * group + 1, key);
-    out[2] = poisson_one(lam[2], r0.z, r1.z, 4 * group + 2, key);
-    out[3] = poisson_one(lam[3], r0.w, r1.w, 4 * group + 3, key);
+    unsigned pending = 0;
+    if (!poisson_fast(lam[0], r0.x, r1.x, out[0])) pending |= 1u;
+    if (!poisson_fast(lam[1], r0.y, r1.y, out[1])) pending |= 2u;
+    if (!poisson_fast(lam[2], r0.z, r1.z, out[2])) pending |= 4u;
+    if (!poisson_fast(lam[3], r0.w, r1.w, out[3])) pending |= 8u;
+    return pending;
+}
+
+MVSIM_HD void poisson_group4(const double (&lam)[4], uint64_t group, PoissonKey key, float (&out)[4])
+{
+    Philox4 r0, r1;
+    unsigned pending = poisson_group4_fast(lam, group, key, out, r0, r1);
+    while (pending) {
+        // lowest pending voxel; selects instead of dynamic indexing keep everything in registers
+        const int i = (pending & 1u) ? 0 : (pending & 2u) ? 1 : (pending & 4u) ? 2 : 3;
+        const double l = i == 0 ? lam[0] : i == 1 ? lam[1] : i == 2 ? lam[2] : lam[3];
+        const uint32_t ru = i == 0 ? r0.x : i == 1 ? r0.y : i == 2 ? r0.z : r0.w;
+        const uint32_t rv = i == 0 ? r1.x : i == 1 ? r1.y : i == 2 ? r1.z : r1.w;
+        const float k = ptrs_resolve(l, ru, rv, 4 * group + (uint64_t)i, key);
+        if (i == 0) out[0] = k; else if (i == 1) out[1] = k; else if (i == 2) out[2] = k; else out[3] = k;
+        pending &= pending - 1;
+    }
 }
 
 }  // namespace mvsim

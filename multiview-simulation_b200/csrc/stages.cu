@@ -454,39 +454,93 @@ int k_adjust_apply(mvsim_ctx* ctx, float* inout, size_t n, const double* d_corr,
 // slice cz*inc of the input (:206, integer, bit exact).  lambda = v * mul, mul = (SNR/sqrt 5)^2
 // (S/Tools.java:76); the output is the raw count (S/Tools.java:84).
 // ---------------------------------------------------------------------------------------------
+// Warp-cooperative finish of the voxels whose first PTRS proposal was not accepted by the squeeze (about 15 % of the
+// voxels with lambda >= 10).  Left to each thread, a warp would run the slow code up to four times with a handful of
+// active lanes; instead the warp compacts its pending voxels into shared memory (exclusive prefix sum of the per-lane
+// counts), all lanes work through the compact list, and the owners read their results back.  The result of a voxel
+// still depends on (seed, stream, voxel index) only.
+struct PendingItem { double lam; unsigned long long index; uint32_t ru, rv; };
+constexpr int kSamplerThreads = 256;
+
+__device__ __forceinline__ void poisson_group4_warp(const double (&lam)[4], uint64_t group, PoissonKey key, float (&out)[4],
+                                                    PendingItem* warp_items, float* warp_results)
+{
+    Philox4 r0, r1;
+    const unsigned pending = poisson_group4_fast(lam, group, key, out, r0, r1);
+    const unsigned lane = threadIdx.x & 31u;
+    const int cnt = __popc(pending);
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, d);
+        if ((int)lane >= d) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) return;                 // warp uniform
+    const int first = incl - cnt;
+    int pos = first;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (pending & (1u << i)) {
+            PendingItem it;
+            it.lam = lam[i];
+            it.index = 4ull * group + (unsigned)i;
+            it.ru = i == 0 ? r0.x : i == 1 ? r0.y : i == 2 ? r0.z : r0.w;
+            it.rv = i == 0 ? r1.x : i == 1 ? r1.y : i == 2 ? r1.z : r1.w;
+            warp_items[pos++] = it;
+        }
+    __syncwarp();
+    for (int j = (int)lane; j < total; j += 32) {
+        const PendingItem it = warp_items[j];
+        warp_results[j] = ptrs_resolve(it.lam, it.ru, it.rv, it.index, key);
+    }
+    __syncwarp();
+    pos = first;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (pending & (1u << i)) out[i] = warp_results[pos++];
+    __syncwarp();                           // the lists are reused by the caller's next group (grid-stride free here, but safe)
+}
+
 // One thread = four consecutive output voxels (one Philox block pair, float4 traffic when the plane size
 // is a multiple of 4 so that the four voxels are also consecutive in the input).
-template <bool VEC4> __global__ void __launch_bounds__(256) extract_kernel(const float* __restrict__ in, float* __restrict__ out, long long plane,
+template <bool VEC4> __global__ void __launch_bounds__(kSamplerThreads) extract_kernel(const float* __restrict__ in, float* __restrict__ out, long long plane,
                                                                           long long n_out, int inc, const double* __restrict__ d_corr,
                                                                           float min_value, int noise, double mul, PoissonKey key)
 {
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long i0 = 4 * g;
-    if (i0 >= n_out) return;
-    float v[4];
-    if (VEC4) {
-        const long long cz = i0 / plane, r = i0 - cz * plane;
-        const float4 t = __ldg(reinterpret_cast<const float4*>(in + cz * inc * plane + r));
-        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-    } else {
+    const bool valid = i0 < n_out;          // no early return: the sampler below is warp cooperative
+    float v[4] = { 0.f, 0.f, 0.f, 0.f };
+    if (valid) {
+        if (VEC4) {
+            const long long cz = i0 / plane, r = i0 - cz * plane;
+            const float4 t = __ldg(reinterpret_cast<const float4*>(in + cz * inc * plane + r));
+            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+        } else {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const long long i = i0 + k < n_out ? i0 + k : n_out - 1;
-            const long long cz = i / plane, r = i - cz * plane;
-            v[k] = __ldg(in + cz * inc * plane + r);
+            for (int k = 0; k < 4; ++k) {
+                const long long i = i0 + k < n_out ? i0 + k : n_out - 1;
+                const long long cz = i / plane, r = i - cz * plane;
+                v[k] = __ldg(in + cz * inc * plane + r);
+            }
+        }
+        if (d_corr) {
+            const double corr = *d_corr;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = adjust_one(v[k], corr, min_value);
         }
     }
-    if (d_corr) {
-        const double corr = *d_corr;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] = adjust_one(v[k], corr, min_value);
-    }
     if (noise) {
+        __shared__ PendingItem items[kSamplerThreads * 4];
+        __shared__ float results[kSamplerThreads * 4];
         double lam[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) lam[k] = __dmul_rn((double)v[k], mul);
-        poisson_group4(lam, (uint64_t)g, key, v);
+        for (int k = 0; k < 4; ++k) lam[k] = valid ? __dmul_rn((double)v[k], mul) : 0.0;
+        const int w = threadIdx.x >> 5;
+        poisson_group4_warp(lam, (uint64_t)g, key, v, items + w * 128, results + w * 128);
     }
+    if (!valid) return;
     if (VEC4) {
         *reinterpret_cast<float4*>(out + i0) = make_float4(v[0], v[1], v[2], v[3]);
     } else {
