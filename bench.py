@@ -343,7 +343,7 @@ def run_slab(args, rank, world, local_rank):
     torch.cuda.set_stream(stream)
     ctx = mv.Context(local_rank, cuda_stream=stream.cuda_stream)
     shape, kshape = ((1024, 2048, 2048), (256, 256, 256)) if args.workload == "cfg5" else ((256, 512, 512), (64, 64, 64))
-    sc = mv.SlabConvolution(ctx, shape, kshape, grp.rank, grp.world, grp.dist)
+    sc = mv.SlabConvolution(ctx, shape, kshape, grp.rank, grp.world, grp.dist, p2p=not os.environ.get("MVSIM_SLAB_NCCL"))
     g = torch.Generator(device=dev)
     g.manual_seed(1234 + rank)
     img = torch.rand((sc.z_local,) + shape[1:], generator=g, device=dev, dtype=torch.float32)     # generated on device, slab-wise
@@ -376,7 +376,8 @@ def run_slab(args, rank, world, local_rank):
                           "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                           "config": {"workload": "BASELINE config 5 (configs[4])" if args.workload == "cfg5" else args.workload,
                                      "volume_xyz": list(shape[::-1]), "psf_xyz": list(kshape[::-1]), "fft_padded_xyz": list(sc.nfft),
-                                     "y_blocks": sc.y_blocks, "parallelism": f"z slabs x{world}, NCCL all_to_all_single x{2 * sc.y_blocks}"},
+                                     "y_blocks": sc.y_blocks, "parallelism": (f"z slabs x{world}, exchanges fused into the y and z kernels as NVLink peer stores" if sc.p2p else
+                                                     f"z slabs x{world}, NCCL all_to_all_single x{2 * sc.y_blocks}")},
                           "nvlink_bytes_sent_per_rank_per_step": sc.exchange_bytes_per_rank(), "rank0_kernel_ms_per_step": stage,
                           "rank0_kernel_ms_total": round(sum(stage.values()), 3), "result_checksum": chk}), flush=True)
     sc.close()

@@ -174,6 +174,15 @@ int mvsim_slabconv_forward_y(mvsim_ctx* ctx, mvsim_slabconv* plan, int block);
 int mvsim_slabconv_middle_z(mvsim_ctx* ctx, mvsim_slabconv* plan);
 int mvsim_slabconv_inverse_y(mvsim_ctx* ctx, mvsim_slabconv* plan, int block);
 int mvsim_slabconv_finish(mvsim_ctx* ctx, mvsim_slabconv* plan, float* d_out_slab);
+/* Peer-to-peer mode (same node, NVLink): instead of bind + two all-to-alls per block, the library allocates nbuf (1 or 2)
+ * buffer sets and exports 2*nbuf CUDA IPC handles of 64 bytes; after the ranks exchanged them (any transport), _p2p_open maps
+ * the peers' buffers.  forward_y then stores each kx tile straight into the z-pass buffer of its owner and middle_z stores each
+ * z slab straight into its owner's inverse-side buffer, so the transfers overlap the transforms tile by tile.  The caller only
+ * places a cross-rank barrier (e.g. a 1-element all-reduce on the same stream) after forward_y and after middle_z:
+ *     prepare;  for block: p2p_select(block % nbuf); forward_y(block); [barrier]; middle_z; [barrier]; inverse_y(block);  finish */
+int mvsim_slabconv_p2p_alloc(mvsim_ctx* ctx, mvsim_slabconv* plan, int nbuf, unsigned char* handles_out /* 2*nbuf*64 bytes */);
+int mvsim_slabconv_p2p_open(mvsim_ctx* ctx, mvsim_slabconv* plan, const unsigned char* all_handles /* world*2*nbuf*64 bytes, rank major */);
+int mvsim_slabconv_p2p_select(mvsim_slabconv* plan, int buffer_set);
 
 #ifdef __cplusplus
 }

@@ -83,6 +83,9 @@ SYMBOLS = [
     ("mvsim_slabconv_middle_z", C.c_int, [_vp, _vp]),
     ("mvsim_slabconv_inverse_y", C.c_int, [_vp, _vp, C.c_int]),
     ("mvsim_slabconv_finish", C.c_int, [_vp, _vp, _vp]),
+    ("mvsim_slabconv_p2p_alloc", C.c_int, [_vp, _vp, C.c_int, _vp]),
+    ("mvsim_slabconv_p2p_open", C.c_int, [_vp, _vp, _vp]),
+    ("mvsim_slabconv_p2p_select", C.c_int, [_vp, C.c_int]),
 ]
 
 _lib = None

@@ -161,14 +161,28 @@ int conv_device(mvsim_ctx* ctx, const float* img, const int64_t dims[3], const f
 // ---- slab-decomposed convolution of the largest single volume (BASELINE config 5) ----------------
 // One plan per rank.  The exchange buffers are owned by the caller (torch tensors in the Python
 // orchestrator, so torch.distributed / NCCL can run the two all-to-all transposes on them).
+namespace {
+struct DeviceGuard {
+    int prev;
+    explicit DeviceGuard(int dev) : prev(-1) { cudaGetDevice(&prev); cudaSetDevice(dev); }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+}  // namespace
+
 struct mvsim_slabconv {
     mvsim::ConvPlan pl;
     mvsim::SlabGeom g;
     int lanes;
     mvsim::ConvWorkspace ws;
-    void* owned[8];
+    void* owned[16];
     int n_owned;
     float2 *send, *recv;
+    // peer-to-peer mode: per buffer set the z-pass buffer X and the inverse-side buffer Y of every rank
+    int p2p_sets;
+    float2* px[2][mvsim::kMaxRanks];
+    float2* py[2][mvsim::kMaxRanks];
+    void* opened[4 * mvsim::kMaxRanks];
+    int n_opened;
 };
 
 using namespace mvsim;
@@ -183,6 +197,8 @@ int mvsim_slabconv_create(mvsim_ctx* ctx, const int64_t dims[3], const int64_t k
     p->lanes = strided_lanes();
     p->n_owned = 0;
     p->send = p->recv = nullptr;
+    p->p2p_sets = 0;
+    p->n_opened = 0;
     int perr = make_conv_plan(dims, kdims, &p->pl);
     if (!perr) perr = make_slab_geom(p->pl, p->lanes, rank, world, &p->g);
     if (perr) { delete p; return plan_error(ctx, perr); }
@@ -224,8 +240,64 @@ int mvsim_slabconv_destroy(mvsim_ctx* ctx, mvsim_slabconv* p)
 {
     if (!p) return MVSIM_OK;
     if (ctx) cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < p->n_opened; ++i) cudaIpcCloseMemHandle(p->opened[i]);
     for (int i = 0; i < p->n_owned; ++i) cudaFree(p->owned[i]);
     delete p;
+    return MVSIM_OK;
+}
+
+// ---- peer-to-peer mode: the exchanges are fused into the y forward pass and the fused z pass (NVLink stores) ----------
+int mvsim_slabconv_p2p_alloc(mvsim_ctx* ctx, mvsim_slabconv* p, int nbuf, unsigned char* handles_out)
+{
+    if (!ctx || !p || !handles_out || nbuf < 1 || nbuf > 2) return set_error(ctx, MVSIM_EINVAL, "slabconv_p2p_alloc: bad argument");
+    if (p->g.world > kMaxRanks) return set_error(ctx, MVSIM_EUNSUPPORTED, "slabconv_p2p: at most %d ranks", kMaxRanks);
+    if (p->p2p_sets) return set_error(ctx, MVSIM_EINVAL, "slabconv_p2p_alloc: already allocated");
+    DeviceGuard guard(ctx->device);
+    const size_t bytes = (size_t)p->pl.u2_elems(p->lanes, p->g.z_local) * sizeof(float2);
+    for (int i = 0; i < nbuf; ++i)
+        for (int k = 0; k < 2; ++k) {
+            void* q = nullptr;
+            MVSIM_CUDA(ctx, cudaMalloc(&q, bytes));
+            p->owned[p->n_owned++] = q;
+            (k == 0 ? p->px : p->py)[i][p->g.rank] = static_cast<float2*>(q);
+            cudaIpcMemHandle_t h;
+            MVSIM_CUDA(ctx, cudaIpcGetMemHandle(&h, q));
+            static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t size");
+            memcpy(handles_out + (size_t)(i * 2 + k) * 64, &h, 64);
+        }
+    p->p2p_sets = nbuf;
+    return MVSIM_OK;
+}
+
+int mvsim_slabconv_p2p_open(mvsim_ctx* ctx, mvsim_slabconv* p, const unsigned char* all_handles)
+{
+    if (!ctx || !p || !all_handles || !p->p2p_sets) return set_error(ctx, MVSIM_EINVAL, "slabconv_p2p_open: allocate first");
+    DeviceGuard guard(ctx->device);
+    const int per_rank = p->p2p_sets * 2;
+    for (int r = 0; r < p->g.world; ++r) {
+        if (r == p->g.rank) continue;
+        for (int i = 0; i < p->p2p_sets; ++i)
+            for (int k = 0; k < 2; ++k) {
+                cudaIpcMemHandle_t h;
+                memcpy(&h, all_handles + ((size_t)r * per_rank + i * 2 + k) * 64, 64);
+                void* q = nullptr;
+                MVSIM_CUDA(ctx, cudaIpcOpenMemHandle(&q, h, cudaIpcMemLazyEnablePeerAccess));
+                p->opened[p->n_opened++] = q;
+                (k == 0 ? p->px : p->py)[i][r] = static_cast<float2*>(q);
+            }
+    }
+    return MVSIM_OK;
+}
+
+int mvsim_slabconv_p2p_select(mvsim_slabconv* p, int set)
+{
+    if (!p || set < 0 || set >= p->p2p_sets) return MVSIM_EINVAL;
+    p->ws.n_peers = p->g.world;
+    for (int r = 0; r < p->g.world; ++r) { p->ws.peers_x[r] = p->px[set][r]; p->ws.peers_y[r] = p->py[set][r]; }
+    p->send = p->py[set][p->g.rank];
+    p->recv = p->px[set][p->g.rank];
+    p->ws.u2 = p->send;         // the inverse y pass reads what the peers' z passes delivered
+    p->ws.ex = p->recv;         // the fused z pass reads what the peers' y passes delivered
     return MVSIM_OK;
 }
 

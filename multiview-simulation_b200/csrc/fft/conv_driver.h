@@ -33,6 +33,12 @@ struct ConvWorkspace {
     float2* p1;     // p1_elems
     float2* p2;     // p2_elems(T, tiles_own)
     const float2 *tw_x, *tw_y, *tw_z, *twist_x;   // tables for sx.n, sy.n, sz.n
+    // peer-to-peer slab mode (n_peers = world > 1): z-pass input buffers [S][tiles][Zl][Ny][T] and inverse-side buffers
+    // [KT][Zl][Ny][T] of EVERY rank (own entries are local pointers); the y forward pass and the fused z pass store
+    // straight into the owners' buffers, so ex == peers_x[rank] and u2 == peers_y[rank]
+    int n_peers;
+    float2* peers_x[kMaxRanks];
+    float2* peers_y[kMaxRanks];
 };
 
 // PSF (already normalised to sum 1) -> scaled spectrum ws.h for this rank's tiles
@@ -91,6 +97,10 @@ template <class L> int conv_forward_y(L& l, const ConvPlan& pl, const SlabGeom& 
     sp.out_tstride = (long long)g.z_local * ny * T; sp.out_estride = T; sp.out_ostride = ny * T;
     sp.swap_grid = 0; sp.scale = 1.0f;
     sp.tile0 = 0; sp.in_tile_global = 1; sp.out_tile_global = 1;
+    if (ws.n_peers > 1) {
+        sp.n_peers = ws.n_peers; sp.my_rank = g.rank; sp.peer_tiles = g.tiles_own; sp.peer_tiles_magic = div_magic((uint32_t)g.tiles_own);
+        for (int r = 0; r < ws.n_peers; ++r) sp.out_peers[r] = ws.peers_x[r];
+    }
     return l.launch_strided(false, pl.sy, sp, g.tiles_total, g.z_local);
 }
 
@@ -124,6 +134,10 @@ template <class L> int conv_middle_z(L& l, const ConvPlan& pl, const SlabGeom& g
     zp.u_tstride = (long long)g.z_local * ny * T; zp.seg_stride = (long long)g.tiles_own * g.z_local * ny * T;
     zp.h_tstride = (long long)pl.sz.n * ny * T;
     if (pl.dims[2] >= 65536) return 5;
+    if (ws.n_peers > 1) {
+        zp.n_peers = ws.n_peers;
+        for (int r = 0; r < ws.n_peers; ++r) zp.out_peers[r] = ws.peers_y[r];
+    }
     return l.launch_zfused(pl.sz, zp, g.tiles_own, pl.sy.n);
 }
 

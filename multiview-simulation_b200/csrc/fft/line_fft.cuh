@@ -105,6 +105,8 @@ template <int A, int B> MVSIM_HD void gather_line(float2 (&x)[A], const float2* 
 // The source line (length n_src) is extended on the fly: mirror-single (image; imglib2
 // Views.extendMirrorSingle) or zero (kernel; Views.extendValue(kernel, 0)); `left` = kdim-1-kdim/2.
 // ==============================================================================================
+constexpr int kMaxRanks = 16;
+
 struct StridedParams {
     const float2* in;
     float2* out;
@@ -121,6 +123,13 @@ struct StridedParams {
     int in_tile_global, out_tile_global;   // 1: that side is indexed by the global tile (row-major U1/P1), 0: by the local tile
     int out_offset;         // inverse: cropped sample o is stored at line index o + out_offset (overlap-save blocks along y)
     float scale;            // forward: multiplied into the output (folds 1/N and PSF scaling)
+    // Slab decomposition with peer-to-peer stores (forward y pass only, n_peers > 1): the kx tile `t` of this rank's planes
+    // goes straight into the z-pass buffer of its owner d = t / peer_tiles, segment my_rank:
+    //   out_peers[d] + ((my_rank * peer_tiles + t - d * peer_tiles) * out_tstride) + outer * out_ostride + k * out_estride
+    // (out_tstride = Zl*Ny*T).  The transfer over NVLink overlaps the transform tile by tile; no all-to-all pass exists.
+    int n_peers, my_rank, peer_tiles;
+    unsigned peer_tiles_magic;
+    float2* out_peers[kMaxRanks];
 };
 
 struct NoState {};
@@ -151,7 +160,13 @@ template <int A_, int B_, int T_> struct StridedFwd : LineShape<A_, B_> {
             if (p < A && active) {
                 float2 y[B];
                 fwd_second<A, B>(p, y, sm, lane, T);
-                float2* dst = q.out + tout * q.out_tstride + outer * q.out_ostride + lane;
+                float2* dst;
+                if (q.n_peers > 1) {
+                    const int d = q.peer_tiles == 1 ? tout : (int)umulhi32((uint32_t)tout, q.peer_tiles_magic);
+                    dst = q.out_peers[d] + (long long)(q.my_rank * q.peer_tiles + tout - d * q.peer_tiles) * q.out_tstride + outer * q.out_ostride + lane;
+                } else {
+                    dst = q.out + tout * q.out_tstride + outer * q.out_ostride + lane;
+                }
                 MVSIM_UNROLL
                 for (int k2 = 0; k2 < B; ++k2)
                     dst[(p + A * k2) * q.out_estride] = make_float2(y[k2].x * q.scale, y[k2].y * q.scale);
@@ -223,6 +238,11 @@ struct ZFusedParams {
     long long u_tstride;    // kx-tile stride of u inside a segment (= zg*Ny*T)
     long long seg_stride;   // segment stride of u (= tiles*zg*Ny*T)
     long long h_tstride;    // kx-tile stride of h (= Nz*Ny*T)
+    // Slab decomposition with peer-to-peer stores (n_peers > 1): plane o of tile `tile` goes to its owner seg = o / zg:
+    //   out_peers[seg] + ((tile0 + tile) * u_tstride) + (o - seg*zg) * estride + ky * ostride   (tile-major [KT][zg][Ny][T])
+    // instead of being written back in place; the all-to-all back is fused into the store.
+    int n_peers;
+    float2* out_peers[kMaxRanks];
     int use_tma;            // 1: the H tile is fetched by the TMA unit through h_tmap (device only), 0: cp.async per thread
     alignas(64) unsigned long long h_tmap[16];   // CUtensorMap over h as float32 [tiles][Nz][Ny][2T], box [1][128][1][2T]
 };
@@ -325,6 +345,16 @@ template <int A_, int B_, int T_> struct ZFused : LineShape<A_, B_> {
                             const int kz = (int)umulhi32((uint32_t)o, q.keep_magic);
                             if (kz * q.keep_inc == o) dst[kz * q.estride] = x[n1];
                             else { st.acc.x += x[n1].x; st.acc.y += x[n1].y; }
+                        }
+                    }
+                } else if (q.n_peers > 1) {
+                    const long long tile_off = (long long)(q.tile0 + tile) * q.u_tstride + outer * q.ostride + lane;
+                    MVSIM_UNROLL
+                    for (int n1 = 0; n1 < A; ++n1) {
+                        const int o = p + n1 * B - q.crop0;
+                        if ((unsigned)o < (unsigned)q.n_src) {
+                            const int seg = q.zg == 1 ? o : (int)umulhi32((uint32_t)o, q.zg_magic);
+                            q.out_peers[seg][tile_off + (o - seg * q.zg) * q.estride] = x[n1];
                         }
                     }
                 } else {

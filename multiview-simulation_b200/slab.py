@@ -13,7 +13,9 @@ from ._lib import check, dims3
 class SlabConvolution:
     """One rank's share of `convolve` for a global (Z, Y, X) volume.  Buffers are torch CUDA tensors."""
 
-    def __init__(self, ctx, shape_zyx, kshape_zyx, rank=0, world=1, dist=None):
+    def __init__(self, ctx, shape_zyx, kshape_zyx, rank=0, world=1, dist=None, p2p=True):
+        """p2p (world > 1): exchanges fused into the kernels as NVLink peer stores (CUDA IPC buffers, one stream-ordered
+        barrier after the y pass and after the z pass); p2p=False: two NCCL all_to_all_single per y block."""
         import torch
         self.ctx, self.rank, self.world, self.dist = ctx, rank, world, dist
         self.h = C.c_void_p()
@@ -23,6 +25,22 @@ class SlabConvolution:
         self.z_local, self.z0, self.y_blocks, self.exchange_elems = int(info[0]), int(info[1]), int(info[2]), int(info[3])
         self.nfft = (int(info[4]), int(info[5]), int(info[6]))
         dev = torch.device("cuda", ctx.device)
+        self.shape = tuple(shape_zyx)
+        self.p2p = bool(p2p) and world > 1
+        if self.p2p:
+            import numpy as np
+            self.nbuf = min(2, self.y_blocks)
+            mine = np.zeros(self.nbuf * 2 * 64, dtype=np.uint8)
+            check(ctx._lib.mvsim_slabconv_p2p_alloc(ctx.h, self.h, self.nbuf, C.c_void_p(mine.ctypes.data)), ctx.h)
+            t = torch.from_numpy(mine).to(dev)
+            parts = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(parts, t)
+            allh = torch.cat(parts).cpu().numpy()
+            check(ctx._lib.mvsim_slabconv_p2p_open(ctx.h, self.h, C.c_void_p(allh.ctypes.data)), ctx.h)
+            check(ctx._lib.mvsim_slabconv_p2p_select(self.h, 0), ctx.h)
+            self._flag = torch.zeros(1, dtype=torch.float32, device=dev)
+            dist.barrier()
+            return
         # up to three exchange buffer sets: the all-to-all of one y block overlaps the kernels of its neighbours
         self.nbuf = 1 if world == 1 else min(3, self.y_blocks)
         self.send = [torch.empty(self.exchange_elems, dtype=torch.complex64, device=dev) for _ in range(self.nbuf)]
@@ -36,7 +54,8 @@ class SlabConvolution:
                                                 C.c_void_p(r.data_ptr()) if r is not None else None), self.ctx.h)
 
     def exchange_bytes_per_rank(self):
-        """bytes this rank sends to OTHER ranks per convolution (two transposes per y block)."""
+        """bytes this rank sends to OTHER ranks per convolution (two transposes per y block; in p2p mode the same bytes
+        leave as peer stores of the y and z kernels)."""
         return 2 * self.y_blocks * self.exchange_elems * 8 * (self.world - 1) // self.world
 
     def convolve(self, img_slab, psf, out_slab):
@@ -47,7 +66,15 @@ class SlabConvolution:
         assert tuple(img_slab.shape) == (self.z_local,) + self.shape[1:] == tuple(out_slab.shape)
         check(lib.mvsim_slabconv_prepare(ctx.h, self.h, C.c_void_p(psf.data_ptr()), C.c_void_p(img_slab.data_ptr())), ctx.h)
         nb = self.y_blocks
-        if self.world == 1:
+        if self.p2p:
+            for b in range(nb):
+                check(lib.mvsim_slabconv_p2p_select(self.h, b % self.nbuf), ctx.h)
+                check(lib.mvsim_slabconv_forward_y(ctx.h, self.h, b), ctx.h)       # stores into the owners' z-pass buffers
+                self.dist.all_reduce(self._flag)                                    # stream-ordered cross-rank barrier
+                check(lib.mvsim_slabconv_middle_z(ctx.h, self.h), ctx.h)            # stores into the owners' inverse buffers
+                self.dist.all_reduce(self._flag)
+                check(lib.mvsim_slabconv_inverse_y(ctx.h, self.h, b), ctx.h)
+        elif self.world == 1:
             for b in range(nb):
                 check(lib.mvsim_slabconv_forward_y(ctx.h, self.h, b), ctx.h)
                 check(lib.mvsim_slabconv_middle_z(ctx.h, self.h), ctx.h)

@@ -96,8 +96,10 @@ void poison(std::vector<float2>& v) { for (auto& e : v) { e.x = 3e30f; e.y = -3e
 // Emulates `world` ranks of the slab-decomposed convolution in one process (world = 1: the single-GPU path).
 // The all-to-all exchanges are done here on the host with the semantics of all_to_all_single (equal chunks).
 // psf must already be normalised.  keep_inc > 1 (world 1 only): out receives the kept slices then the sum plane.
+// p2p != 0 (world > 1): no exchange pass at all -- the y forward pass and the fused z pass store straight into the
+// owners' buffers through pointer tables (on the GPU: peer memory over NVLink)
 extern "C" int emu_convolve(const float* img, const int64_t dims[3], const float* psf, const int64_t kdims[3],
-                            float* out, double* sum_out, int keep_inc, int world, int max_line)
+                            float* out, double* sum_out, int keep_inc, int world, int max_line, int p2p)
 {
     ConvPlan pl;
     int err = make_conv_plan(dims, kdims, &pl, max_line);
@@ -118,31 +120,39 @@ extern "C" int emu_convolve(const float* img, const int64_t dims[3], const float
         s.h.resize(pl.h_elems(T, s.g.tiles_own)); s.p1.resize(pl.p1_elems()); s.p2.resize(pl.p2_elems(T, s.g.tiles_own));
         // poison the workspaces: every element that is read must have been written by a pass
         for (auto* v : { &s.u1, &s.u1o, &s.u2, &s.ex, &s.h, &s.p1, &s.p2 }) poison(*v);
-        s.ws = ConvWorkspace{ s.u1.data(), pl.y_blocks > 1 ? s.u1o.data() : s.u1.data(), s.u2.data(),
-                              world > 1 ? s.ex.data() : s.u2.data(), s.h.data(), s.p1.data(), s.p2.data(),
-                              twx.data(), twy.data(), twz.data(), twist.data() };
+        s.ws = ConvWorkspace{};
+        s.ws.u1 = s.u1.data(); s.ws.u1o = pl.y_blocks > 1 ? s.u1o.data() : s.u1.data(); s.ws.u2 = s.u2.data();
+        s.ws.ex = world > 1 ? s.ex.data() : s.u2.data(); s.ws.h = s.h.data(); s.ws.p1 = s.p1.data(); s.ws.p2 = s.p2.data();
+        s.ws.tw_x = twx.data(); s.ws.tw_y = twy.data(); s.ws.tw_z = twz.data(); s.ws.twist_x = twist.data();
         err = conv_psf_spectrum(l, pl, s.g, s.ws, psf);
         if (err) return err;
         err = conv_forward_x(l, pl, s.g, s.ws, img + (size_t)s.g.z0 * pl.dims[1] * pl.dims[0]);
         if (err) return err;
     }
+    if (p2p && world > 1)
+        for (int r = 0; r < world; ++r) {
+            rk[r].ws.n_peers = world;
+            for (int q = 0; q < world; ++q) { rk[r].ws.peers_x[q] = rk[q].ex.data(); rk[r].ws.peers_y[q] = rk[q].u2.data(); }
+        }
     const int planes = conv_out_planes(pl, rk[0].g, keep_inc);
     const size_t chunk = rk[0].u2.size() / world;
     for (int b = 0; b < pl.y_blocks; ++b) {
+        if (world > 1 && p2p)
+            for (int r = 0; r < world; ++r) poison(rk[r].ex);     // the y passes of ALL ranks must fill every z-pass buffer
         for (int r = 0; r < world; ++r)
             if ((err = conv_forward_y(l, pl, rk[r].g, rk[r].ws, b))) return err;
-        if (world > 1)      // all-to-all: chunk d of rank s's send buffer lands in chunk s of rank d's receive buffer
+        if (world > 1 && !p2p)      // all-to-all: chunk d of rank s's send buffer lands in chunk s of rank d's receive buffer
             for (int s = 0; s < world; ++s)
                 for (int d = 0; d < world; ++d)
                     std::memcpy(rk[d].ex.data() + s * chunk, rk[s].u2.data() + d * chunk, chunk * sizeof(float2));
+        if (world > 1)
+            for (int r = 0; r < world; ++r) poison(rk[r].u2);     // everything the inverse reads must arrive again
         for (int r = 0; r < world; ++r)
             if ((err = conv_middle_z(l, pl, rk[r].g, rk[r].ws, rk[r].ws.ex, keep_inc))) return err;
-        if (world > 1) {
-            for (int r = 0; r < world; ++r) poison(rk[r].u2);
+        if (world > 1 && !p2p)
             for (int s = 0; s < world; ++s)
                 for (int d = 0; d < world; ++d)
                     std::memcpy(rk[d].u2.data() + s * chunk, rk[s].ex.data() + d * chunk, chunk * sizeof(float2));
-        }
         for (int r = 0; r < world; ++r)
             if ((err = conv_inverse_y(l, pl, rk[r].g, rk[r].ws, b, planes))) return err;
     }

@@ -20,6 +20,7 @@ def main():
     shape = tuple(int(v) for v in sys.argv[1].split("x"))       # Z x Y x X
     kshape = tuple(int(v) for v in sys.argv[2].split("x"))
     out_path = sys.argv[3]
+    p2p = len(sys.argv) < 5 or sys.argv[4] != "nccl"
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -31,7 +32,7 @@ def main():
     vol = rng.random(shape, dtype=np.float32)
     psf = gaussian_psf(kshape, (kshape[0] / 7.0, kshape[1] / 6.0, kshape[2] / 5.0))
     mv.Tools.normImage(psf, ctx=ctx)
-    sc = mv.SlabConvolution(ctx, shape, kshape, grp.rank, grp.world, grp.dist)
+    sc = mv.SlabConvolution(ctx, shape, kshape, grp.rank, grp.world, grp.dist, p2p=p2p)
     z0, zl = sc.z0, sc.z_local
     img = torch.from_numpy(vol[z0:z0 + zl]).to(dev)
     d_psf = torch.from_numpy(psf).to(dev)
@@ -48,7 +49,7 @@ def main():
         ref = mv.SimulateMultiViewDataset.convolve(vol, psf.copy(), ctx=ctx)      # undecomposed, same GPU kernels
         err = float(np.abs(got.astype(np.float64) - ref).max() / np.abs(ref).max())
         with open(out_path, "w") as f:
-            json.dump({"world": grp.world, "y_blocks": sc.y_blocks, "nfft": sc.nfft, "max_rel_err": err,
+            json.dump({"world": grp.world, "p2p": sc.p2p, "y_blocks": sc.y_blocks, "nfft": sc.nfft, "max_rel_err": err,
                        "identical": bool(np.array_equal(got, ref))}, f)
     sc.close()
     grp.close()

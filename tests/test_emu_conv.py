@@ -24,19 +24,19 @@ def emu():
         subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-I", CSRC, SRC, "-o", SO])
     L = C.CDLL(SO)
     i64p, fp = C.POINTER(C.c_int64), C.POINTER(C.c_float)
-    L.emu_convolve.argtypes = [fp, i64p, fp, i64p, fp, C.POINTER(C.c_double), C.c_int, C.c_int, C.c_int]
+    L.emu_convolve.argtypes = [fp, i64p, fp, i64p, fp, C.POINTER(C.c_double), C.c_int, C.c_int, C.c_int, C.c_int]
     L.emu_plan.argtypes = [i64p, i64p, C.POINTER(C.c_int), C.c_int]
     return L
 
 
-def _run(emu, vol, psfn, keep_inc=1, planes=None, world=1, max_line=0):
+def _run(emu, vol, psfn, keep_inc=1, planes=None, world=1, max_line=0, p2p=0):
     z, y, x = vol.shape
     kz, ky, kx = psfn.shape
     out = np.empty_like(vol) if planes is None else np.empty((planes, y, x), dtype=np.float32)
     s = C.c_double(0)
     fp = C.POINTER(C.c_float)
     err = emu.emu_convolve(vol.ctypes.data_as(fp), (C.c_int64 * 3)(x, y, z), psfn.ctypes.data_as(fp),
-                           (C.c_int64 * 3)(kx, ky, kz), out.ctypes.data_as(fp), C.byref(s), keep_inc, world, max_line)
+                           (C.c_int64 * 3)(kx, ky, kz), out.ctypes.data_as(fp), C.byref(s), keep_inc, world, max_line, p2p)
     assert err == 0
     return out, s.value
 
@@ -125,3 +125,6 @@ def test_slab_decomposed_convolution_with_host_all_to_all(emu, oracle, world, sh
     one, _ = _run(emu, vol, psf, world=1, max_line=max_line)
     assert np.array_equal(got, one)          # the decomposition does not change a single bit
     assert s == pytest.approx(float(ref.astype(np.float64).sum()), rel=2e-6)
+    # peer-to-peer variant: no exchange pass, the y and z passes store into the owners' buffers
+    p2p, _ = _run(emu, vol, psf, world=world, max_line=max_line, p2p=1)
+    assert np.array_equal(p2p, one)

@@ -70,7 +70,9 @@ def test_y_lines_beyond_the_size_table_use_overlap_save_blocks(mv):
         assert got[z, y, x] == pytest.approx(exp, rel=2e-5)
 
 
-def test_two_gpu_nccl_all_to_all_matches_single_gpu(tmp_path):
+@pytest.mark.parametrize("mode", ["p2p", "nccl"])
+def test_multi_gpu_slab_convolution_matches_single_gpu(tmp_path, mode):
+    """p2p: exchanges fused into the kernels as NVLink peer stores; nccl: two all_to_all_single per y block."""
     import torch
     n = torch.cuda.device_count()
     if n < 2:
@@ -78,8 +80,8 @@ def test_two_gpu_nccl_all_to_all_matches_single_gpu(tmp_path):
     world = 4 if n >= 4 else 2
     out = tmp_path / "slab.json"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-           "--master-port", str(29700 + os.getpid() % 200), os.path.join(HERE, "slab_worker.py"), "32x72x118", "9x7x11", str(out)]
+           "--master-port", str(29700 + os.getpid() % 200), os.path.join(HERE, "slab_worker.py"), "32x72x118", "9x7x11", str(out), mode]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-3000:]
     d = json.loads(out.read_text())
-    assert d["world"] == world and d["identical"], d
+    assert d["world"] == world and d["p2p"] == (mode == "p2p") and d["identical"], d
