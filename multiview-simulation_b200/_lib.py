@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libmvsim.so")
+LIB_PATH = os.environ.get("MVSIM_LIB") or os.path.join(_PKG, "libmvsim.so")
 
 MVSIM_OK, MVSIM_EINVAL, MVSIM_ENOMEM, MVSIM_ECUDA, MVSIM_ENCCL, MVSIM_EUNSUPPORTED = range(6)
 STAGE_NAMES = ["h2d", "rotate", "attenuate", "psf", "fft_xfwd", "fft_yfwd", "fft_zfused", "fft_yinv", "fft_xinv",

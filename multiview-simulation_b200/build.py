@@ -14,11 +14,14 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
-OBJ = os.path.join(ROOT, "build")
-LIB = os.path.join(PKG, "libmvsim.so")
+# MVSIM_PACKED_FFT=0 builds the butterflies on scalar FADD/FFMA instead of Blackwell's packed FP32x2 pipe (A/B measurements)
+PACKED = os.environ.get("MVSIM_PACKED_FFT", "1") != "0"
+OBJ = os.path.join(ROOT, "build" if PACKED else "build_scalar")
+LIB = os.path.join(PKG, "libmvsim.so" if PACKED else "libmvsim_scalar.so")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", CSRC, "-I", os.path.join(ROOT, "include")]
+FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", CSRC, "-I", os.path.join(ROOT, "include"),
+         f"-DMVSIM_PACKED_FFT={1 if PACKED else 0}"]
 
 UNITS = [("stages", "stages.cu", []), ("conv", "conv.cu", []), ("capi", "capi.cu", [])] + \
         [(f"fft_g{g}_t{t}", os.path.join("fft", "fft_group.cu"), [f"-DMVSIM_GROUP={g}", f"-DMVSIM_LANES={t}"])

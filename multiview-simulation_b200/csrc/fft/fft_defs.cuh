@@ -21,6 +21,32 @@ static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y;
 
 namespace mvsim {
 
+// Blackwell's packed FP32x2 arithmetic (crt/sm_100_rt.h: FADD2 / FMUL2 / FFMA2 in SASS); plain float pairs in the CPU emulation
+MVSIM_HD float2 add2(float2 a, float2 b)
+{
+#ifdef __CUDA_ARCH__
+    return __fadd2_rn(a, b);
+#else
+    return make_float2(a.x + b.x, a.y + b.y);
+#endif
+}
+MVSIM_HD float2 mul2(float2 a, float2 b)
+{
+#ifdef __CUDA_ARCH__
+    return __fmul2_rn(a, b);
+#else
+    return make_float2(a.x * b.x, a.y * b.y);
+#endif
+}
+MVSIM_HD float2 fma2(float2 a, float2 b, float2 c)
+{
+#ifdef __CUDA_ARCH__
+    return __ffma2_rn(a, b, c);
+#else
+    return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#endif
+}
+
 MVSIM_HD float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 // a * conj(b)
 MVSIM_HD float2 cmulc(float2 a, float2 b) { return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }

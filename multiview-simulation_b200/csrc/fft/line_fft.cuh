@@ -18,9 +18,21 @@
 // phases are __host__ __device__: tests/emu runs the very same code on the CPU, thread by thread.
 #pragma once
 #include "fft_defs.cuh"
-#include "regfft_gen.cuh"
+#include "regfft_gen.cuh"              // RegFFT : scalar FADD / FFMA butterflies
+#include "regfft_gen_packed.cuh"       // RegFFTP: the same dataflow on Blackwell's packed FP32x2 pipe (FADD2 / FFMA2)
+
+#ifndef MVSIM_PACKED_FFT
+#define MVSIM_PACKED_FFT 1
+#endif
 
 namespace mvsim {
+
+// Measured on B200 (config 3): the packed butterflies cut the strided passes by 11-12 % (fewer issue slots, shorter
+// dependent chains) but slow the x passes by 15 % (80-register cap at 3 CTAs/SM, aligned register pairs), so the x passes
+// stay scalar.  MVSIM_PACKED_FFT=0 builds everything scalar (A/B measurements).
+template <int N, int DIR, bool PK> struct RegSel { static MVSIM_HD void run(float2 (&x)[N]) { RegFFT<N, DIR>::run(x); } };
+template <int N, int DIR> struct RegSel<N, DIR, true> { static MVSIM_HD void run(float2 (&x)[N]) { RegFFTP<N, DIR>::run(x); } };
+constexpr bool kPackedStrided = MVSIM_PACKED_FFT != 0;
 
 template <int A_, int B_> struct LineShape {
     static constexpr int A = A_, B = B_;
@@ -33,10 +45,10 @@ template <int A_, int B_> struct LineShape {
 
 // ---- forward halves ---------------------------------------------------------------------------
 // thread p < B.  x[n1] = line[p + n1*B] on entry.
-template <int A, int B> MVSIM_HD void fwd_first(int p, float2 (&x)[A], float2* sm, int base, int ls, const float2* __restrict__ tw)
+template <int A, int B, bool PK = false> MVSIM_HD void fwd_first(int p, float2 (&x)[A], float2* sm, int base, int ls, const float2* __restrict__ tw)
 {
     constexpr int BP = B | 1;
-    RegFFT<A, -1>::run(x);
+    RegSel<A, -1, PK>::run(x);
     MVSIM_UNROLL
     for (int k1 = 0; k1 < A; ++k1) {
         const float2 v = k1 == 0 ? x[0] : cmul(x[k1], tw[k1 * p]);
@@ -44,20 +56,20 @@ template <int A, int B> MVSIM_HD void fwd_first(int p, float2 (&x)[A], float2* s
     }
 }
 // thread p < A.  On exit y[k2] = X[p + A*k2].
-template <int A, int B> MVSIM_HD void fwd_second(int p, float2 (&y)[B], const float2* sm, int base, int ls)
+template <int A, int B, bool PK = false> MVSIM_HD void fwd_second(int p, float2 (&y)[B], const float2* sm, int base, int ls)
 {
     constexpr int BP = B | 1;
     MVSIM_UNROLL
     for (int n2 = 0; n2 < B; ++n2) y[n2] = sm[base + (p * BP + n2) * ls];
-    RegFFT<B, -1>::run(y);
+    RegSel<B, -1, PK>::run(y);
 }
 
 // ---- inverse halves (unscaled) ----------------------------------------------------------------
 // thread p < A.  y[k2] = X[p + A*k2] on entry.
-template <int A, int B> MVSIM_HD void inv_first(int p, float2 (&y)[B], float2* sm, int base, int ls, const float2* __restrict__ tw)
+template <int A, int B, bool PK = false> MVSIM_HD void inv_first(int p, float2 (&y)[B], float2* sm, int base, int ls, const float2* __restrict__ tw)
 {
     constexpr int BP = B | 1;
-    RegFFT<B, 1>::run(y);
+    RegSel<B, 1, PK>::run(y);
     MVSIM_UNROLL
     for (int n2 = 0; n2 < B; ++n2) {
         const float2 v = n2 == 0 ? y[0] : cmulc(y[n2], tw[n2 * p]);
@@ -65,12 +77,12 @@ template <int A, int B> MVSIM_HD void inv_first(int p, float2 (&y)[B], float2* s
     }
 }
 // thread p < B.  On exit x[n1] = line[p + n1*B].
-template <int A, int B> MVSIM_HD void inv_second(int p, float2 (&x)[A], const float2* sm, int base, int ls)
+template <int A, int B, bool PK = false> MVSIM_HD void inv_second(int p, float2 (&x)[A], const float2* sm, int base, int ls)
 {
     constexpr int BP = B | 1;
     MVSIM_UNROLL
     for (int k1 = 0; k1 < A; ++k1) x[k1] = sm[base + (k1 * BP + p) * ls];
-    RegFFT<A, 1>::run(x);
+    RegSel<A, 1, PK>::run(x);
 }
 
 // Gathers x[n1] = ext(line)[p + n1*B - left], n1 < A, from a strided line.  All index arithmetic is done
@@ -154,12 +166,12 @@ template <int A_, int B_, int T_> struct StridedFwd : LineShape<A_, B_> {
                 float2 x[A];
                 const float2* src = q.in + tin * q.in_tstride + outer * q.in_ostride + lane;
                 gather_line<A, B>(x, src, q.in_estride, p, q.left, q.n_src, q.ext);
-                fwd_first<A, B>(p, x, sm, lane, T, q.tw);
+                fwd_first<A, B, kPackedStrided>(p, x, sm, lane, T, q.tw);
             }
         } else {
             if (p < A && active) {
                 float2 y[B];
-                fwd_second<A, B>(p, y, sm, lane, T);
+                fwd_second<A, B, kPackedStrided>(p, y, sm, lane, T);
                 float2* dst;
                 if (q.n_peers > 1) {
                     const int d = q.peer_tiles == 1 ? tout : (int)umulhi32((uint32_t)tout, q.peer_tiles_magic);
@@ -197,12 +209,12 @@ template <int A_, int B_, int T_> struct StridedInv : LineShape<A_, B_> {
                 const float2* src = q.in + tin * q.in_tstride + outer * q.in_ostride + lane;
                 MVSIM_UNROLL
                 for (int k2 = 0; k2 < B; ++k2) y[k2] = src[(p + A * k2) * q.in_estride];
-                inv_first<A, B>(p, y, sm, lane, T, q.tw);
+                inv_first<A, B, kPackedStrided>(p, y, sm, lane, T, q.tw);
             }
         } else {
             if (p < B && active) {
                 float2 x[A];
-                inv_second<A, B>(p, x, sm, lane, T);
+                inv_second<A, B, kPackedStrided>(p, x, sm, lane, T);
                 float2* dst = q.out + tout * q.out_tstride + outer * q.out_ostride + lane;
                 MVSIM_UNROLL
                 for (int n1 = 0; n1 < A; ++n1) {
@@ -317,12 +329,12 @@ template <int A_, int B_, int T_> struct ZFused : LineShape<A_, B_> {
                 }
                 MVSIM_UNROLL
                 for (int n1 = 0; n1 < A; ++n1) x[n1] = src[zfused_plane_offset(q, idx[n1])];
-                fwd_first<A, B>(p, x, sm, lane, T, q.tw);
+                fwd_first<A, B, kPackedStrided>(p, x, sm, lane, T, q.tw);
             }
             cp_async_wait_all();
         } else if (PH == 1) {
             if (p < A && active) {
-                fwd_second<A, B>(p, st.y, sm, lane, T);
+                fwd_second<A, B, kPackedStrided>(p, st.y, sm, lane, T);
 #ifdef __CUDA_ARCH__
                 if (q.use_tma) mbar_wait(bar, 0);       // the barrier before this phase made the init visible
 #endif
@@ -330,12 +342,12 @@ template <int A_, int B_, int T_> struct ZFused : LineShape<A_, B_> {
                 for (int k2 = 0; k2 < B; ++k2) st.y[k2] = cmul(st.y[k2], smh[(p + A * k2) * T + lane]);
             }
         } else if (PH == 2) {
-            if (p < A && active) inv_first<A, B>(p, st.y, sm, lane, T, q.tw);
+            if (p < A && active) inv_first<A, B, kPackedStrided>(p, st.y, sm, lane, T, q.tw);
         } else if (PH == 3) {
             st.acc = make_float2(0.f, 0.f);
             if (p < B && active) {
                 float2 x[A];
-                inv_second<A, B>(p, x, sm, lane, T);
+                inv_second<A, B, kPackedStrided>(p, x, sm, lane, T);
                 float2* dst = q.u + tile * q.u_tstride + outer * q.ostride + lane;
                 if (q.keep_inc > 1) {
                     MVSIM_UNROLL

@@ -3,6 +3,7 @@
 // with a barrier between phases, driven by the same host logic (conv_driver.h).  Built with g++
 // by tests/test_emu_conv.py; this is a test of the index arithmetic, not a product path.
 #define MVSIM_EMU_SMALL_ONLY 1
+#define MVSIM_PACKED_FFT 1
 #include "fft/conv_driver.h"
 
 #include <cstdlib>

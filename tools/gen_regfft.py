@@ -141,6 +141,72 @@ class Gen:
         return out
 
 
+class GenPacked(Gen):
+    """Same dataflow, but every complex value is one float2 and the arithmetic uses Blackwell's packed FP32x2
+    instructions (add2 / mul2 / fma2 = __fadd2_rn / __fmul2_rn / __ffma2_rn -> FADD2 / FMUL2 / FFMA2): one instruction per complex add."""
+
+    def emit(self, expr):
+        v = self.tmp()
+        self.lines.append(f"const float2 {v} = {expr};")
+        return v
+
+    def pair(self, a, b):
+        return f"make_float2({self.lit(a)}, {self.lit(b)})"
+
+    def swap(self, a):
+        return f"make_float2({a}.y, {a}.x)"
+
+    def add(self, a, b):
+        return self.emit(f"add2({a}, {b})")
+
+    def sub(self, a, b):
+        return self.emit(f"fma2({b}, {self.pair(-1.0, -1.0)}, {a})")
+
+    def scale(self, a, c):
+        return self.emit(f"mul2({a}, {self.pair(c, c)})")
+
+    def add_i(self, a, b, s):
+        # a + s*i*b = (a.x - s b.y, a.y + s b.x)
+        return self.emit(f"fma2({self.swap(b)}, {self.pair(-s, s)}, {a})")
+
+    def fma2(self, a, b, cb, c=None, cc=None):
+        first = f"fma2({b}, {self.pair(cb, cb)}, {a})"
+        if c is None:
+            return self.emit(first)
+        return self.emit(f"fma2({c}, {self.pair(cc, cc)}, {first})")
+
+    def lin2(self, b, cb, c, cc):
+        return self.emit(f"fma2({c}, {self.pair(cc, cc)}, mul2({b}, {self.pair(cb, cb)}))")
+
+    def twiddle(self, a, num, den):
+        num %= den
+        if num == 0:
+            return a
+        g = math.gcd(num, den)
+        num //= g
+        den //= g
+        if den == 2:
+            return self.emit(f"mul2({a}, {self.pair(-1.0, -1.0)})")
+        if den == 4:
+            s = self.sign if num == 1 else -self.sign
+            return self.emit(f"mul2({self.swap(a)}, {self.pair(-s, s)})")
+        ang = self.sign * 2.0 * math.pi * num / den
+        c, sn = math.cos(ang), math.sin(ang)
+        return self.emit(f"fma2({self.swap(a)}, {self.pair(-sn, sn)}, mul2({a}, {self.pair(c, c)}))")
+
+
+def gen_size_packed(n, sign):
+    g = GenPacked(sign)
+    x = [f"x[{i}]" for i in range(n)]
+    out = g.fft(n, x)
+    body = ["    " + l for l in g.lines]
+    for i, v in enumerate(out):
+        body.append(f"    x[{i}] = {v};")
+    name = "-1" if sign < 0 else "1"
+    return (f"template <> struct RegFFTP<{n}, {name}> {{\n"
+            f"  static MVSIM_HD void run(float2 (&x)[{n}]) {{\n" + "\n".join(body) + "\n  }\n};\n")
+
+
 def gen_size(n, sign):
     g = Gen(sign)
     x = [(f"x[{i}].x", f"x[{i}].y") for i in range(n)]
@@ -151,6 +217,21 @@ def gen_size(n, sign):
     name = "-1" if sign < 0 else "1"
     return (f"template <> struct RegFFT<{n}, {name}> {{\n"
             f"  static MVSIM_HD void run(float2 (&x)[{n}]) {{\n" + "\n".join(body) + "\n  }\n};\n")
+
+
+def main_packed(path):
+    parts = ["// GENERATED by tools/gen_regfft.py -- do not edit.\n"
+             "// Packed variant: complex values are float2, arithmetic is Blackwell FP32x2 (FADD2 / FMUL2 / FFMA2).\n"
+             "#pragma once\n#include \"fft_defs.cuh\"\n\nnamespace mvsim {\n\n"
+             "template <int N, int DIR> struct RegFFTP;\n\n"
+             "template <int DIR> struct RegFFTP<1, DIR> { static MVSIM_HD void run(float2 (&)[1]) {} };\n\n"]
+    for n in SIZES:
+        for sign in (-1, 1):
+            parts.append(gen_size_packed(n, sign))
+            parts.append("\n")
+    parts.append("}  // namespace mvsim\n")
+    with open(path, "w") as f:
+        f.write("".join(parts))
 
 
 def main(path):
@@ -170,3 +251,4 @@ def main(path):
 
 if __name__ == "__main__":
     main(sys.argv[1] if len(sys.argv) > 1 else "multiview-simulation_b200/csrc/fft/regfft_gen.cuh")
+    main_packed(sys.argv[2] if len(sys.argv) > 2 else "multiview-simulation_b200/csrc/fft/regfft_gen_packed.cuh")
