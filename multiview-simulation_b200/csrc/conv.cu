@@ -46,10 +46,17 @@ static bool make_h_tensor_map(const ZFusedParams& q, int lanes, int tiles, int n
     return true;
 }
 
+static bool otf_default()
+{
+    static const bool on = getenv("MVSIM_H_MATERIALIZE") == nullptr;   // default: PSF spectrum computed inside the fused z pass
+    return on;
+}
+
 struct CudaLauncher {
     mvsim_ctx* ctx;
     bool psf_phase;
     int lanes;
+    bool h_on_the_fly = otf_default();
 
     static int x_blocks(const FftSize& s, int n_rows)
     {
@@ -80,6 +87,10 @@ struct CudaLauncher {
         StageTimer t(ctx, MVSIM_T_FFT_ZFUSED);
         const unsigned tiles = (unsigned)n_tiles;
         ZFusedParams q = q0;
+        if (q.h_mode) {
+            q.use_tma = 0;
+            return finish(fft_launch(FFT_ZFUSED_OTF, lanes, s.n, &q, (unsigned)n_outer, tiles, ctx->stream), "fused z pass (PSF spectrum on the fly)");
+        }
         q.use_tma = make_h_tensor_map(q, lanes, n_tiles, s.n, n_outer, q.h_tmap) ? 1 : 0;
         return finish(fft_launch(FFT_ZFUSED, lanes, s.n, &q, (unsigned)n_outer, tiles, ctx->stream), "fused z pass");
     }
@@ -135,7 +146,7 @@ int conv_device(mvsim_ctx* ctx, const float* img, const int64_t dims[3], const f
     if (pl.y_blocks > 1) MVSIM_TRY(buf.get(&ws.u1o, (size_t)pl.u1_elems(g.z_local)));   // blocks still read halo rows of u1
     MVSIM_TRY(buf.get(&ws.u2, (size_t)pl.u2_elems(lanes, g.z_local)));
     ws.ex = ws.u2;
-    MVSIM_TRY(buf.get(&ws.h, (size_t)pl.h_elems(lanes, g.tiles_own)));
+    if (!otf_default()) MVSIM_TRY(buf.get(&ws.h, (size_t)pl.h_elems(lanes, g.tiles_own)));
     MVSIM_TRY(buf.get(&ws.p1, (size_t)pl.p1_elems()));
     MVSIM_TRY(buf.get(&ws.p2, (size_t)pl.p2_elems(lanes, g.tiles_own)));
     ws.tw_x = tx.tw; ws.twist_x = tx.twist; ws.tw_y = ty.tw; ws.tw_z = tz.tw;
@@ -221,7 +232,7 @@ int mvsim_slabconv_create(mvsim_ctx* ctx, const int64_t dims[3], const int64_t k
         grab(&p->ws.u1, (size_t)p->pl.u1_elems(p->g.z_local));
         p->ws.u1o = p->ws.u1;
         if (p->pl.y_blocks > 1) grab(&p->ws.u1o, (size_t)p->pl.u1_elems(p->g.z_local));
-        grab(&p->ws.h, (size_t)p->pl.h_elems(p->lanes, p->g.tiles_own));
+        if (!otf_default()) grab(&p->ws.h, (size_t)p->pl.h_elems(p->lanes, p->g.tiles_own));
         grab(&p->ws.p1, (size_t)p->pl.p1_elems());
         grab(&p->ws.p2, (size_t)p->pl.p2_elems(p->lanes, p->g.tiles_own));
         p->ws.tw_x = tx.tw; p->ws.twist_x = tx.twist; p->ws.tw_y = ty.tw; p->ws.tw_z = tz.tw;

@@ -56,10 +56,11 @@ template <class L> int conv_psf_spectrum(L& l, const ConvPlan& pl, const SlabGeo
     sp.n_src = pl.kdims[1]; sp.left = 0; sp.ext = EXT_ZERO;
     sp.in_tstride = T; sp.in_estride = kxc; sp.in_ostride = (long long)pl.kdims[1] * kxc;
     sp.out_tstride = (long long)pl.kdims[2] * ny * T; sp.out_estride = T; sp.out_ostride = ny * T;
-    sp.swap_grid = 0; sp.scale = 1.0f;
+    sp.swap_grid = 0; sp.scale = l.h_on_the_fly ? (float)pl.scale : 1.0f;
     sp.tile0 = g.tile0; sp.in_tile_global = 1; sp.out_tile_global = 0;
     err = l.launch_strided(false, pl.sy, sp, g.tiles_own, pl.kdims[2]);
     if (err) return err;
+    if (l.h_on_the_fly) return 0;       // the fused z pass transforms P2 along z itself: no H is written
 
     sp.in = ws.p2; sp.out = ws.h; sp.tw = ws.tw_z;   // z: P2 -> H, both tile-major, outer = ky
     sp.n_src = pl.kdims[2];
@@ -134,6 +135,9 @@ template <class L> int conv_middle_z(L& l, const ConvPlan& pl, const SlabGeom& g
     zp.u_tstride = (long long)g.z_local * ny * T; zp.seg_stride = (long long)g.tiles_own * g.z_local * ny * T;
     zp.h_tstride = (long long)pl.sz.n * ny * T;
     if (pl.dims[2] >= 65536) return 5;
+    if (l.h_on_the_fly) {
+        zp.h_mode = 1; zp.p2 = ws.p2; zp.k_src = pl.kdims[2]; zp.p2_tstride = (long long)pl.kdims[2] * ny * T;
+    }
     if (ws.n_peers > 1) {
         zp.n_peers = ws.n_peers;
         for (int r = 0; r < ws.n_peers; ++r) zp.out_peers[r] = ws.peers_y[r];

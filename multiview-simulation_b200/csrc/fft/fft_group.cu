@@ -25,6 +25,8 @@ template <class K> __global__ void __launch_bounds__(K::THREADS, min_blocks<K>()
     if constexpr (K::NPH > 3) { __syncthreads(); K::template phase<3>(q, blockIdx.x, blockIdx.y, threadIdx.x, sm, st); }
     if constexpr (K::NPH > 4) { __syncthreads(); K::template phase<4>(q, blockIdx.x, blockIdx.y, threadIdx.x, sm, st); }
     if constexpr (K::NPH > 5) { __syncthreads(); K::template phase<5>(q, blockIdx.x, blockIdx.y, threadIdx.x, sm, st); }
+    if constexpr (K::NPH > 6) { __syncthreads(); K::template phase<6>(q, blockIdx.x, blockIdx.y, threadIdx.x, sm, st); }
+    if constexpr (K::NPH > 7) { __syncthreads(); K::template phase<7>(q, blockIdx.x, blockIdx.y, threadIdx.x, sm, st); }
 }
 
 template <class K> static int launch(const void* params, unsigned gx, unsigned gy, cudaStream_t s)
@@ -51,6 +53,7 @@ template <int A, int B> static int launch_size(int kind, const void* params, uns
     case FFT_SFWD: return launch<StridedFwd<A, B, T>>(params, gx, gy, s);
     case FFT_SINV: return launch<StridedInv<A, B, T>>(params, gx, gy, s);
     case FFT_ZFUSED: return launch<ZFused<A, B, T>>(params, gx, gy, s);
+    case FFT_ZFUSED_OTF: return launch<ZFusedOTF<A, B, T>>(params, gx, gy, s);
     }
     return (int)cudaErrorInvalidValue;
 }

@@ -255,6 +255,13 @@ struct ZFusedParams {
     // instead of being written back in place; the all-to-all back is fused into the store.
     int n_peers;
     float2* out_peers[kMaxRanks];
+    // h_mode 1 (ZFusedOTF): the PSF spectrum is never materialised -- the kernel transforms the PSF's partial spectrum
+    // p2 = [tiles][KZ][Ny][T] (x and y transformed, z still spatial, zero extended, pre-scaled) along z itself and keeps the
+    // line's H values in shared memory.  Saves writing and re-reading Nz/KZ times more data per convolution.
+    int h_mode;
+    const float2* p2;
+    int k_src;              // KZ: valid z samples of the PSF
+    long long p2_tstride;   // kx-tile stride of p2 (= KZ*Ny*T)
     int use_tma;            // 1: the H tile is fetched by the TMA unit through h_tmap (device only), 0: cp.async per thread
     alignas(64) unsigned long long h_tmap[16];   // CUtensorMap over h as float32 [tiles][Nz][Ny][2T], box [1][128][1][2T]
 };
@@ -295,6 +302,9 @@ template <int A_, int B_, int T_> struct ZFused : LineShape<A_, B_> {
         uint64_t* bar = reinterpret_cast<uint64_t*>(smh + H_ROWS * T);
 #endif
         if (PH == 0) {
+            if (q.h_mode != 0) {
+                // H values were computed into smh by ZFusedOTF's PSF phases
+            } else
 #ifdef __CUDA_ARCH__
             if (q.use_tma) {
                 // one thread programs the TMA unit: ceil(N/128) boxes of 128 kz rows x 64 bytes, completion on the mbarrier
@@ -385,6 +395,49 @@ template <int A_, int B_, int T_> struct ZFused : LineShape<A_, B_> {
                 float2 s = make_float2(0.f, 0.f);
                 for (int j = 0; j < B; ++j) { s.x += sm[j * T + lane].x; s.y += sm[j * T + lane].y; }
                 q.u[tile * q.u_tstride + outer * q.ostride + lane + q.n_keep * q.estride] = s;
+            }
+        }
+    }
+};
+
+// Fused z pass with the PSF spectrum computed on the fly (h_mode 1): two PSF phases in front of ZFused's six.
+template <int A_, int B_, int T_> struct ZFusedOTF : ZFused<A_, B_, T_> {
+    using Z = ZFused<A_, B_, T_>;
+    using S = LineShape<A_, B_>;
+    static constexpr int A = A_, B = B_, T = T_;
+    static constexpr int NPH = 8;
+    using Params = ZFusedParams;
+    using State = typename Z::State;
+
+    template <int PH> static MVSIM_HD void phase(const Params& q, int bx, int by, int tid, float2* sm, State& st)
+    {
+        if (PH >= 2) {
+            Z::template phase<(PH >= 2 ? PH - 2 : 0)>(q, bx, by, tid, sm, st);
+            return;
+        }
+        const int lane = tid % T, p = tid / T;
+        const int tile = by, outer = bx;
+        const bool active = (tile + q.tile0) * T + lane < q.kx_count;
+        float2* smh = sm + Z::EXCH_ELEMS;
+        if (PH == 0) {
+            if (p < B && active) {
+                float2 x[A];
+                const float2* __restrict__ src = q.p2 + tile * q.p2_tstride + outer * q.ostride + lane;
+                MVSIM_UNROLL
+                for (int n1 = 0; n1 < A; ++n1) {
+                    const int n = p + n1 * B;
+                    const bool ok = n < q.k_src;
+                    const float2 v = src[(ok ? n : 0) * q.estride];      // clamped index + select keeps the loads batched
+                    x[n1] = ok ? v : make_float2(0.f, 0.f);              // (predicated loads measured slower: 3.39 vs 3.21 ms)
+                }
+                fwd_first<A, B, kPackedStrided>(p, x, sm, lane, T, q.tw);
+            }
+        } else {
+            if (p < A && active) {
+                float2 h[B];
+                fwd_second<A, B, kPackedStrided>(p, h, sm, lane, T);
+                MVSIM_UNROLL
+                for (int k2 = 0; k2 < B; ++k2) smh[(p + A * k2) * T + lane] = h[k2];     // read back by the same thread only
             }
         }
     }

@@ -26,6 +26,8 @@ template <class K> static void emulate(const typename K::Params& q, int gx, int 
             if (K::NPH > 3) for (int t = 0; t < K::THREADS; ++t) K::template phase<3>(q, bx, by, t, sm.data(), st[t]);
             if (K::NPH > 4) for (int t = 0; t < K::THREADS; ++t) K::template phase<4>(q, bx, by, t, sm.data(), st[t]);
             if (K::NPH > 5) for (int t = 0; t < K::THREADS; ++t) K::template phase<5>(q, bx, by, t, sm.data(), st[t]);
+            if (K::NPH > 6) for (int t = 0; t < K::THREADS; ++t) K::template phase<6>(q, bx, by, t, sm.data(), st[t]);
+            if (K::NPH > 7) for (int t = 0; t < K::THREADS; ++t) K::template phase<7>(q, bx, by, t, sm.data(), st[t]);
         }
 }
 
@@ -34,6 +36,7 @@ template <int A, int B> struct Rows { static constexpr int R = (256 / LineShape<
 
 struct EmuLauncher {
     int lanes = T;
+    bool h_on_the_fly = false;
     int x_blocks(const FftSize& s, int n_rows) const
     {
         const int p = s.a > s.b ? s.a : s.b;
@@ -62,6 +65,12 @@ struct EmuLauncher {
     }
     int launch_zfused(const FftSize& s, const ZFusedParams& q, int tiles, int n_outer)
     {
+        if (q.h_mode)
+            switch (s.n) {
+#define MVSIM_X(n_, a_, b_) case n_: emulate<ZFusedOTF<a_, b_, T>>(q, n_outer, tiles); return 0;
+                MVSIM_FFT_SIZES(MVSIM_X)
+#undef MVSIM_X
+            }
         switch (s.n) {
 #define MVSIM_X(n_, a_, b_) case n_: emulate<ZFused<a_, b_, T>>(q, n_outer, tiles); return 0;
             MVSIM_FFT_SIZES(MVSIM_X)
@@ -111,6 +120,7 @@ extern "C" int emu_convolve(const float* img, const int64_t dims[3], const float
     fill_twiddles(pl.sz.n, &twz[0].x);
     fill_twist(pl.sx.n, &twist[0].x);
     EmuLauncher l;
+    l.h_on_the_fly = getenv("MVSIM_EMU_OTF") != nullptr;
     std::vector<RankState> rk(world);
     for (int r = 0; r < world; ++r) {
         RankState& s = rk[r];
