@@ -259,3 +259,30 @@ def test_unsupported_and_invalid_shapes(mv, S):
     assert e.value.status == 5
     with pytest.raises(ValueError):
         S.convolve(np.ones((2, 2), dtype=np.float32), np.ones((1, 1, 3), dtype=np.float32))
+
+
+def test_two_threads_with_their_own_contexts(mv, S):
+    """The reference calls the path from two pool threads at once (S/SimulateTileStitching.java:85-117): contexts are
+    independent (own stream, own workspaces), results must equal the serial ones."""
+    import threading
+    gt = sphere_phantom((32, 40, 40), n_spheres=60)
+    psf = gaussian_psf((9, 7, 7), (2.0, 1.0, 1.0))
+    jobs = [(15, 3), (75, 4), (135, 5), (195, 6)]
+    serial = {d: S.simulateView(gt, psf.copy(), d, inc=2, poissonSNR=12.0, rnd=99, stream=st) for d, st in jobs}
+    out, errs = {}, []
+
+    def work(sub):
+        try:
+            ctx = mv.Context(0)
+            for _ in range(3):
+                for d, st in sub:
+                    out[d] = S.simulateView(gt, psf.copy(), d, inc=2, poissonSNR=12.0, rnd=99, ctx=ctx, stream=st)
+            ctx.close()
+        except Exception as e:      # pragma: no cover
+            errs.append(e)
+    ts = [threading.Thread(target=work, args=(jobs[:2],)), threading.Thread(target=work, args=(jobs[2:],))]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs, errs
+    for d, _ in jobs:
+        assert np.array_equal(out[d], serial[d])
