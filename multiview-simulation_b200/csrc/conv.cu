@@ -29,7 +29,7 @@ static EncodeTiledFn encode_tiled_fn()
 }
 
 // tensor map over the PSF spectrum h = [tiles][Nz][Ny][T] complex64 seen as float32 [tiles][Nz][Ny][2T]; box = 128 kz rows of one (tile, ky)
-static bool make_h_tensor_map(const ZFusedParams& q, int lanes, int tiles, int nz, int ny, unsigned long long out[16])
+static bool make_h_tensor_map(const float2* base, int lanes, int tiles, int nz, int ny, unsigned long long out[16])
 {
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc || getenv("MVSIM_NO_TMA")) return false;
@@ -39,7 +39,7 @@ static bool make_h_tensor_map(const ZFusedParams& q, int lanes, int tiles, int n
     const cuuint64_t strides[3] = { (cuuint64_t)lanes * 8, (cuuint64_t)ny * lanes * 8, (cuuint64_t)nz * ny * lanes * 8 };
     const cuuint32_t box[4] = { (cuuint32_t)(2 * lanes), 1, (cuuint32_t)kTmaBoxRows, 1 };
     const cuuint32_t estr[4] = { 1, 1, 1, 1 };
-    const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float2*>(q.h), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float2*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return false;
     memcpy(out, &m, sizeof(m));
@@ -88,10 +88,10 @@ struct CudaLauncher {
         const unsigned tiles = (unsigned)n_tiles;
         ZFusedParams q = q0;
         if (q.h_mode) {
-            q.use_tma = 0;
+            q.use_tma = make_h_tensor_map(q.p2, lanes, n_tiles, q.k_src, n_outer, q.h_tmap) ? 1 : 0;    // PSF tile [KZ rows] through the TMA unit
             return finish(fft_launch(FFT_ZFUSED_OTF, lanes, s.n, &q, (unsigned)n_outer, tiles, ctx->stream), "fused z pass (PSF spectrum on the fly)");
         }
-        q.use_tma = make_h_tensor_map(q, lanes, n_tiles, s.n, n_outer, q.h_tmap) ? 1 : 0;
+        q.use_tma = make_h_tensor_map(q.h, lanes, n_tiles, s.n, n_outer, q.h_tmap) ? 1 : 0;
         return finish(fft_launch(FFT_ZFUSED, lanes, s.n, &q, (unsigned)n_outer, tiles, ctx->stream), "fused z pass");
     }
 };

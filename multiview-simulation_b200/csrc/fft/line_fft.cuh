@@ -263,7 +263,7 @@ struct ZFusedParams {
     int k_src;              // KZ: valid z samples of the PSF
     long long p2_tstride;   // kx-tile stride of p2 (= KZ*Ny*T)
     int use_tma;            // 1: the H tile is fetched by the TMA unit through h_tmap (device only), 0: cp.async per thread
-    alignas(64) unsigned long long h_tmap[16];   // CUtensorMap over h as float32 [tiles][Nz][Ny][2T], box [1][128][1][2T]
+    alignas(64) unsigned long long h_tmap[16];   // CUtensorMap over h (or, h_mode 1, over p2) as float32 [tiles][rows][Ny][2T], box [1][128][1][2T]
 };
 
 constexpr int kTmaBoxRows = 128;    // kz rows per TMA box
@@ -420,6 +420,31 @@ template <int A_, int B_, int T_> struct ZFusedOTF : ZFused<A_, B_, T_> {
         const bool active = (tile + q.tile0) * T + lane < q.kx_count;
         float2* smh = sm + Z::EXCH_ELEMS;
         if (PH == 0) {
+#ifdef __CUDA_ARCH__
+            if (q.use_tma) {
+                // TMA-fed PSF tile: one thread programs ceil(KZ/128) box loads (128 kz rows x 64 bytes each, rows beyond KZ are
+                // zero filled by the unit) into the H area, everybody waits on the mbarrier and picks its samples from shared
+                // memory -- no per-thread address arithmetic, no loads for the zero extension.
+                uint64_t* bar = reinterpret_cast<uint64_t*>(smh + Z::H_ROWS * T);
+                const int nbox = (q.k_src + kTmaBoxRows - 1) / kTmaBoxRows;
+                if (tid == 0) {
+                    mbar_init(bar, 1);
+                    mbar_expect_tx(bar, (unsigned)(nbox * kTmaBoxRows * T * sizeof(float2)));
+                    for (int b = 0; b < nbox; ++b) tma_load_4d(smh + b * kTmaBoxRows * T, q.h_tmap, 0, outer, b * kTmaBoxRows, tile, bar);
+                }
+                __syncthreads();            // the init must be visible before anybody polls the barrier
+                mbar_wait(bar, 0);
+                if (p < B && active) {
+                    float2 x[A];
+                    MVSIM_UNROLL
+                    for (int n1 = 0; n1 < A; ++n1) {
+                        const int n = p + n1 * B;
+                        x[n1] = n < nbox * kTmaBoxRows ? smh[n * T + lane] : make_float2(0.f, 0.f);
+                    }
+                    fwd_first<A, B, kPackedStrided>(p, x, sm, lane, T, q.tw);
+                }
+            } else
+#endif
             if (p < B && active) {
                 float2 x[A];
                 const float2* __restrict__ src = q.p2 + tile * q.p2_tstride + outer * q.ostride + lane;
