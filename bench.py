@@ -252,14 +252,18 @@ def run_ours(args, rank, world, local_rank):
     value = world * nv * vox_per_view / (ms_step * 1e-3)
 
     # ---- end-to-end arm: host buffers through the C ABI ------------------------------------------------
+    # Serial: one caller thread, one context: every step = ground truth H2D, 6 views, results D2H (downloads overlap the
+    # next view inside the call).  Pipelined: THREE caller threads with one context each (the calling pattern of the
+    # reference's own S/SimulateTileStitching.java:85-117), steps dealt round-robin; the library's per-device upload / compute gates line the
+    # callers up so that the H2D of one step runs under the kernels of another and the D2H tail of a third (PCIe is full duplex).  Every step still moves all of its bytes inside the timed region.
     S = mv.SimulateMultiViewDataset
     e2e_steps = max(1, min(args.steps, 3))
 
-    def step_e2e():
+    def step_e2e(c=ctx, psfs=psf_pin, outs=out_pin):
         for v in range(nv):
-            psf_pin[v].array[...] = psf_raw[v]          # the call normalises the PSF in place
-        S.simulateViews(gt_pin.array, [p.array for p in psf_pin], degrees, inc=inc, poissonSNR=snr, rnd=464232194, ctx=ctx,
-                        outs=[o.array for o in out_pin], first_stream=rank * nv)
+            psfs[v].array[...] = psf_raw[v]          # the call normalises the PSF in place
+        S.simulateViews(gt_pin.array, [p.array for p in psfs], degrees, inc=inc, poissonSNR=snr, rnd=464232194, ctx=c,
+                        outs=[o.array for o in outs], first_stream=rank * nv)
     step_e2e()
     barrier()
     t0 = time.perf_counter()
@@ -269,10 +273,34 @@ def run_ours(args, rank, world, local_rank):
     e1.record(stream)
     barrier()
     wall = (time.perf_counter() - t0) / e2e_steps
-    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1) / e2e_steps, wall * 1e3))
+    serial_ms = max_over_ranks(max(e0.elapsed_time(e1) / e2e_steps, wall * 1e3))
     h2d = 4 * vox_per_view + nv * 4 * int(np.prod(kshape))
     d2h = nv * 4 * (int(np.prod(oshape)) + int(np.prod(kshape)))
     result_checksum = float(out_pin[0].array[::7, ::31, ::29].astype(np.float64).mean())
+
+    n_callers = 3
+    pipe_steps = 4 * n_callers
+    callers = [(ctx, psf_pin, out_pin)]
+    for _ in range(n_callers - 1):
+        callers.append((mv.Context(local_rank), [mv.PinnedBuffer(kshape) for _ in range(nv)], [mv.PinnedBuffer(oshape) for _ in range(nv)]))
+
+    def caller_loop(i, n):
+        for _ in range(n):
+            step_e2e(*callers[i])
+    for i in range(n_callers):              # warm the second context's workspaces
+        caller_loop(i, 1)
+    barrier()
+    threads = [threading.Thread(target=caller_loop, args=(i, pipe_steps // n_callers)) for i in range(n_callers)]
+    t0 = time.perf_counter()
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()                            # every call returns only after its results are in the host buffers
+    torch.cuda.synchronize()
+    pipe_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / pipe_steps)
+    barrier()
+    pipe_checksum = float(callers[-1][2][0].array[::7, ::31, ::29].astype(np.float64).mean())
+    e2e_ms = min(pipe_ms, serial_ms)
 
     if rank != 0:
         grp.close()
@@ -326,7 +354,11 @@ def run_ours(args, rank, world, local_rank):
             "views_per_s": world * nv / (ms_step * 1e-3), "ms_per_view": view_ms,
             "e2e": {"value": world * nv * vox_per_view / (e2e_ms * 1e-3), "unit": "voxels/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "views_per_s": world * nv / (e2e_ms * 1e-3),
-                    "api": "mvsim_simulate_views (pinned host buffers)", "steps": e2e_steps, "result_checksum": result_checksum},
+                    "api": "mvsim_simulate_views (pinned host buffers)", "steps": pipe_steps if pipe_ms <= serial_ms else e2e_steps,
+                    "mode": (f"{n_callers} caller threads x 1 context each, steps dealt round-robin (H2D of one step runs under the kernels and D2H of the others)"
+                             if pipe_ms <= serial_ms else "1 caller thread"),
+                    "serial_ms_per_step": serial_ms, "pipelined_ms_per_step": pipe_ms,
+                    "result_checksum": result_checksum, "result_checksum_second_caller": pipe_checksum},
             "gpu_launches": launches, "roofline": roofline, "stages": stages_ms, "fft_ms_per_launch": fft_passes,
             "fft_padded_xyz": [int(nfft[0]), int(ny), int(nz)], "cpu_baseline": cpu, "clocks": clk}
     print(json.dumps(line), flush=True)

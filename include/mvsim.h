@@ -135,6 +135,27 @@ int mvsim_weight_image(mvsim_ctx* ctx, const int64_t dims[3], float* out);
  * sum_out (nullable) receives the sum of the normalised weights (sum_weights.tif, :648-663) */
 int mvsim_normalize_weights(mvsim_ctx* ctx, float* const* weights, int n_views, const int64_t dims[3], float osem, float* sum_out);
 
+/* ---- input generators either side of the path ----------------------------------------
+ * java.util.Random is replayed bit-exactly (JDK specification), so the caller's seeds keep their meaning. */
+/* SimulateBeads.randomPoints (S/SimulateBeads.java:150-166), reference seed 535 (:69); host arithmetic; points = n x 3 (x, y, z) */
+int mvsim_random_points(int n, const int64_t range_min[3], const int64_t range_max[3], int64_t seed, double* points);
+/* SimulateBeads.transformPoints (:131-148) for one angle: axisRotation(range, axis, degrees) applied to every point; host arithmetic */
+int mvsim_transform_points(const double* points, int n, const int64_t range_min[3], const int64_t range_max[3], int axis, int degrees, double* out);
+/* SimulateBeads.renderPoints / addGaussian (:97-121, :168-205) for one point list.  As in the reference (:106) the image has
+ * max - min voxels per axis (one less than the interval's dimension); out has prod(max - min) floats.  Sums in point order. */
+int mvsim_render_beads(mvsim_ctx* ctx, const double* points, int n, const double sigma[3], const int64_t interval_min[3],
+                       const int64_t interval_max[3], float* out);
+/* drawSpheres (S/SimulateMultiViewDataset.java:436-522) into a zeroed volume of dims; reference seed 464232194 (:76), minValue 0,
+ * maxValue 1, scale 2.  n_small (nullable) receives the number of small spheres. */
+int mvsim_draw_spheres(mvsim_ctx* ctx, const int64_t dims[3], double min_value, double max_value, int scale, int half_pixel, int64_t seed,
+                       float* out, int64_t* n_small);
+/* downSample2x (:394-423): out has prod(dims/2 - 1) floats */
+int mvsim_downsample2x(mvsim_ctx* ctx, const float* in, const int64_t dims[3], float* out);
+/* simulate(halfPixelOffset, rnd) (:371-392): the size^3 ground truth (reference size 289), rendered at 2x and down-sampled on the device */
+int mvsim_simulate_phantom(mvsim_ctx* ctx, int size, int half_pixel, int64_t seed, float* out, int64_t* n_small);
+/* Tools.makeSquare (S/Tools.java:315-349): out is the cube of the largest dimension */
+int mvsim_make_square(mvsim_ctx* ctx, const float* in, const int64_t dims[3], float* out);
+
 /* ---- device-resident volumes (SNR sweeps a la S/SimulateTileStitching.java:131-189) ------- */
 int mvsim_volume_create(mvsim_ctx* ctx, const int64_t dims[3], mvsim_volume** vol);
 int mvsim_volume_free(mvsim_ctx* ctx, mvsim_volume* vol);
@@ -152,6 +173,10 @@ int mvsim_dev_adjust(mvsim_ctx* ctx, mvsim_volume* img, float min_value, float t
 int mvsim_dev_extract_slices(mvsim_ctx* ctx, const mvsim_volume* in, int inc, float snr, uint64_t seed, uint64_t stream, mvsim_volume* out);
 /* gt: ground truth, psf: raw PSF (normalised in place), out: X*Y*((Z-1)/inc+1) */
 int mvsim_dev_simulate_view(mvsim_ctx* ctx, const mvsim_view_params* p, const mvsim_volume* gt, mvsim_volume* psf, mvsim_volume* out);
+/* the generators writing straight into a device-resident volume (the ground truth never visits the host) */
+int mvsim_dev_render_beads(mvsim_ctx* ctx, const double* points, int n, const double sigma[3], const int64_t interval_min[3],
+                           const int64_t interval_max[3], mvsim_volume* out);
+int mvsim_dev_simulate_phantom(mvsim_ctx* ctx, int size, int half_pixel, int64_t seed, mvsim_volume* out, int64_t* n_small);
 
 /* ---- slab-decomposed convolution of one large volume across ranks (BASELINE config 5) -------
  * convolve (:253-264) for a volume that is distributed by z slabs over `world` GPUs (one process each).

@@ -5,7 +5,7 @@ repository root aliases it).  Everything computes through libmvsim.so; see inclu
 """
 from . import tiff                                     # noqa: F401
 from ._lib import LIB_PATH, MvsimError, ViewParams     # noqa: F401
-from .api import (Context, DeviceVolume, JavaRandom, PinnedBuffer, SimulateMultiViewDataset, Tools,   # noqa: F401
+from .api import (Context, DeviceVolume, JavaRandom, PinnedBuffer, SimulateBeads, SimulateMultiViewDataset, Tools,   # noqa: F401
                   default_context, make_view_params)
 from .distributed import Group                         # noqa: F401
 from .sharding import views_for_rank                   # noqa: F401

@@ -61,6 +61,15 @@ SYMBOLS = [
     ("mvsim_make_isotropic", C.c_int, [_vp, _fp, _i64p, C.c_int, _fp]),
     ("mvsim_weight_image", C.c_int, [_vp, _i64p, _fp]),
     ("mvsim_normalize_weights", C.c_int, [_vp, C.POINTER(_fp), C.c_int, _i64p, C.c_float, _fp]),
+    ("mvsim_random_points", C.c_int, [C.c_int, _i64p, _i64p, C.c_int64, _dp]),
+    ("mvsim_transform_points", C.c_int, [_dp, C.c_int, _i64p, _i64p, C.c_int, C.c_int, _dp]),
+    ("mvsim_render_beads", C.c_int, [_vp, _dp, C.c_int, _dp, _i64p, _i64p, _fp]),
+    ("mvsim_draw_spheres", C.c_int, [_vp, _i64p, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int64, _fp, _i64p]),
+    ("mvsim_downsample2x", C.c_int, [_vp, _fp, _i64p, _fp]),
+    ("mvsim_simulate_phantom", C.c_int, [_vp, C.c_int, C.c_int, C.c_int64, _fp, _i64p]),
+    ("mvsim_make_square", C.c_int, [_vp, _fp, _i64p, _fp]),
+    ("mvsim_dev_render_beads", C.c_int, [_vp, _dp, C.c_int, _dp, _i64p, _i64p, _vp]),
+    ("mvsim_dev_simulate_phantom", C.c_int, [_vp, C.c_int, C.c_int, C.c_int64, _vp, _i64p]),
     ("mvsim_volume_create", C.c_int, [_vp, _i64p, C.POINTER(_vp)]),
     ("mvsim_volume_free", C.c_int, [_vp, _vp]),
     ("mvsim_volume_dims", C.c_int, [_vp, _i64p]),

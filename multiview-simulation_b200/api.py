@@ -12,6 +12,10 @@ what the JNI facade in INTEGRATION.md does on the Java side.  There is no CPU im
     SimulateMultiViewDataset.extractSlices     S/SimulateMultiViewDataset.java:181,195
     SimulateMultiViewDataset.poissonProcess    S/SimulateMultiViewDataset.java:233
     Tools.normImage / adjustImage / poissonProcess   S/Tools.java:112,143,73
+Input generators either side of the path:
+    SimulateMultiViewDataset.simulate / drawSpheres / downSample2x   S/SimulateMultiViewDataset.java:366-522
+    SimulateBeads.randomPoints / transformPoints / renderPoints      S/SimulateBeads.java:97-205
+    Tools.makeSquare                                                 S/Tools.java:315
 """
 import ctypes as C
 import threading
@@ -216,8 +220,32 @@ class Tools:
         check(ctx._lib.mvsim_poisson(ctx.h, fptr(img), img.size, float(SNR), _seed_from(rnd), stream), ctx.h)
 
 
+def _phantom_seed(rnd):
+    """Seed whose fresh java.util.Random equals the caller's generator: an int is a seed, a JavaRandom contributes its
+    current state (the replay then continues the caller's stream; the caller's object itself is not advanced)."""
+    if rnd is None:
+        return 464232194                 # the class-static generator (:76), as on the first call of simulate()
+    if isinstance(rnd, JavaRandom):
+        return rnd._s ^ 0x5DEECE66D
+    return int(rnd)
+
+
+def _tools_make_square(img, ctx=None):
+    """Tools.makeSquare (S/Tools.java:315-349): centre-pad to the cube of the largest dimension with the minimum."""
+    ctx = ctx or default_context()
+    img = _vol(img)
+    m = max(img.shape)
+    out = np.empty((m, m, m), dtype=np.float32)
+    check(ctx._lib.mvsim_make_square(ctx.h, fptr(img), dims3(img.shape), fptr(out)), ctx.h)
+    return out
+
+
+Tools.makeSquare = staticmethod(_tools_make_square)
+
+
 class SimulateMultiViewDataset:
-    rnd = JavaRandom(464232194)     # static generator of the reference (:76)
+    seed = 464232194
+    rnd = JavaRandom(seed)          # static generator of the reference (:76)
     minValue = 0.0001               # :77
     avgIntensity = 1.0              # :78
 
@@ -323,6 +351,40 @@ class SimulateMultiViewDataset:
         return s
 
     @staticmethod
+    def simulate(halfPixelOffset=False, rnd=None, size=289, ctx=None):
+        """The sphere-phantom ground truth (:366-392): drawSpheres at 2x, then downSample2x, on the device.  `rnd` is the
+        seed of the java.util.Random the reference passes (class-static generator: 464232194, :76); its draws are replayed
+        bit-exactly.  `size` is the reference's hard-coded 289."""
+        ctx = ctx or default_context()
+        seed = _phantom_seed(rnd)
+        out = np.empty((size, size, size), dtype=np.float32)
+        n = C.c_int64(0)
+        check(ctx._lib.mvsim_simulate_phantom(ctx.h, size, int(bool(halfPixelOffset)), seed, fptr(out), C.byref(n)), ctx.h)
+        return out
+
+    @staticmethod
+    def drawSpheres(shape_zyx, minValue=0.0, maxValue=1.0, scale=2, halfPixelOffset=False, rnd=None, ctx=None, return_count=False):
+        """drawSpheres (:436-522) into a new zero volume of `shape_zyx` (the reference draws into its argument)."""
+        ctx = ctx or default_context()
+        seed = _phantom_seed(rnd)
+        out = np.empty(tuple(shape_zyx), dtype=np.float32)
+        n = C.c_int64(0)
+        check(ctx._lib.mvsim_draw_spheres(ctx.h, dims3(out.shape), minValue, maxValue, scale, int(bool(halfPixelOffset)), seed,
+                                          fptr(out), C.byref(n)), ctx.h)
+        return (out, n.value) if return_count else out
+
+    @staticmethod
+    def downSample2x(img, ctx=None):
+        """downSample2x (:394-423): dims/2 - 1, n-linear at 2l + 0.5."""
+        ctx = ctx or default_context()
+        img = _vol(img)
+        if min(img.shape) < 4:
+            raise MvsimError(_lib.MVSIM_EINVAL, "downSample2x: dims must be >= 4")
+        out = np.empty(tuple(s // 2 - 1 for s in img.shape), dtype=np.float32)
+        check(ctx._lib.mvsim_downsample2x(ctx.h, fptr(img), dims3(img.shape), fptr(out)), ctx.h)
+        return out
+
+    @staticmethod
     def simulateViews(gt, psfs, degrees, axis=0, delta=0.01, inc=3, poissonSNR=25.0, rnd=None, ctx=None, outs=None,
                       first_stream=0, strict_reference=True):
         """The view loop of main() (:567-613) for the acquisition stages: one ground truth, one PSF and
@@ -352,3 +414,75 @@ class SimulateMultiViewDataset:
         oarr = (fpp * n)(*[fptr(o) for o in outs])
         check(ctx._lib.mvsim_simulate_views(ctx.h, n, params, fptr(gt), parr, oarr), ctx.h)
         return outs
+
+
+
+class SimulateBeads:
+    """Mirror of S/SimulateBeads.java: random points (java.util.Random(535), :69), one rotated copy per angle
+    (axisRotation about `axis`), each rendered as analytic Gaussians x 1000 (:168-205).  Intervals are (min_xyz, max_xyz)
+    pairs like ImgLib2's FinalInterval; `FinalInterval(dims)` is ((0,0,0), dims-1)."""
+
+    seed = 535
+
+    def __init__(self, angles, axis, numPoints, rangeSimulation, intervalRender, sigma, ctx=None):
+        self.angles = [int(a) for a in angles]
+        self.axis = axis
+        self.numPoints = numPoints
+        self.rangeSimulation = rangeSimulation
+        self.intervalRender = intervalRender
+        self.sigma = [float(v) for v in sigma]
+        self.ctx = ctx
+        self.imgs = None
+
+    @staticmethod
+    def interval(dims_xyz):
+        """new FinalInterval(dims): min 0, max dims - 1."""
+        return (0, 0, 0), tuple(int(d) - 1 for d in dims_xyz)
+
+    @staticmethod
+    def randomPoints(numPoints, rangeInterval, rnd=535):
+        """(:150-166) -> (numPoints, 3) float64 array of (x, y, z)."""
+        mn, mx = rangeInterval
+        pts = np.empty((numPoints, 3), dtype=np.float64)
+        i3 = C.c_int64 * 3
+        check(_lib.load().mvsim_random_points(numPoints, i3(*mn), i3(*mx), int(rnd), pts.ctypes.data_as(C.POINTER(C.c_double))))
+        return pts
+
+    @staticmethod
+    def transformPoints(points, angles, axis, rangeInterval):
+        """(:131-148) -> one transformed (n, 3) array per angle."""
+        mn, mx = rangeInterval
+        points = np.ascontiguousarray(points, dtype=np.float64)
+        dp = C.POINTER(C.c_double)
+        i3 = C.c_int64 * 3
+        res = []
+        for a in angles:
+            out = np.empty_like(points)
+            check(_lib.load().mvsim_transform_points(points.ctypes.data_as(dp), len(points), i3(*mn), i3(*mx), axis, int(a),
+                                                     out.ctypes.data_as(dp)))
+            res.append(out)
+        return res
+
+    @staticmethod
+    def renderPoints(lists, interval, sigma, ctx=None):
+        """(:97-121) -> one (z, y, x) float32 image per point list; like the reference the image has max - min voxels per axis."""
+        ctx = ctx or default_context()
+        mn, mx = interval
+        shape = tuple(int(mx[d] - mn[d]) for d in (2, 1, 0))
+        dp = C.POINTER(C.c_double)
+        i3 = C.c_int64 * 3
+        imgs = []
+        for pts in lists:
+            pts = np.ascontiguousarray(pts, dtype=np.float64)
+            out = np.empty(shape, dtype=np.float32)
+            check(ctx._lib.mvsim_render_beads(ctx.h, pts.ctypes.data_as(dp), len(pts), (C.c_double * 3)(*sigma), i3(*mn), i3(*mx),
+                                              fptr(out)), ctx.h)
+            imgs.append(out)
+        return imgs
+
+    def getImgs(self):
+        if self.imgs is None:
+            points = self.randomPoints(self.numPoints, self.rangeSimulation, self.seed)
+            lists = self.transformPoints(points, self.angles, self.axis, self.rangeSimulation)
+            self.imgs = self.renderPoints(lists, self.intervalRender, self.sigma, ctx=self.ctx)
+        return self.imgs

@@ -23,7 +23,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", CSRC, "-I", os.path.join(ROOT, "include"),
          f"-DMVSIM_PACKED_FFT={1 if PACKED else 0}"]
 
-UNITS = [("stages", "stages.cu", []), ("conv", "conv.cu", []), ("capi", "capi.cu", [])] + \
+UNITS = [("stages", "stages.cu", []), ("phantom", "phantom.cu", []), ("conv", "conv.cu", []), ("capi", "capi.cu", [])] + \
         [(f"fft_g{g}_t{t}", os.path.join("fft", "fft_group.cu"), [f"-DMVSIM_GROUP={g}", f"-DMVSIM_LANES={t}"])
          for g in (4, 3, 2, 1, 0) for t in (8,)]
 

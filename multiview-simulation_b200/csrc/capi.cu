@@ -5,6 +5,10 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <chrono>
+#include <mutex>
+#include <stdlib.h>
+
 #include "ctx.h"
 #include "fft/conv_plan.h"
 
@@ -50,7 +54,7 @@ StageTimer::~StageTimer()
 int dev_alloc(mvsim_ctx* ctx, void** p, size_t bytes)
 {
     if (bytes == 0) bytes = 16;
-    cudaError_t e = cudaMallocAsync(p, bytes, ctx->stream);
+    cudaError_t e = ctx->mempool ? cudaMallocFromPoolAsync(p, bytes, ctx->mempool, ctx->stream) : cudaMallocAsync(p, bytes, ctx->stream);
     if (e != cudaSuccess) { *p = nullptr; return cuda_fail(ctx, e, "cudaMallocAsync"); }
     return MVSIM_OK;
 }
@@ -300,6 +304,7 @@ static int ctx_create(int device, bool own, void* cuda_stream, mvsim_ctx** out)
     ctx->stream = nullptr;
     ctx->own_stream = false;
     ctx->copy_stream = nullptr;
+    ctx->mempool = nullptr;
     ctx->d_scalars = nullptr;
     ctx->launches = 0;
     ctx->profiling = false;
@@ -316,15 +321,22 @@ static int ctx_create(int device, bool own, void* cuda_stream, mvsim_ctx** out)
             ctx->own_stream = true;
         }
         if ((e = cudaMalloc((void**)&ctx->d_scalars, 8 * sizeof(double))) != cudaSuccess) { st = cuda_fail(nullptr, e, "cudaMalloc"); break; }
-        // keep freed workspaces cached in the stream-ordered pool (no per-call cudaMalloc)
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-            uint64_t keep = ~0ull;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        }
+        // freed workspaces stay cached in a stream-ordered pool owned by this context (no per-call cudaMalloc, and no
+        // cross-stream reuse dependencies between contexts that run concurrently)
+        cudaMemPoolProps props;
+        memset(&props, 0, sizeof(props));
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        if ((e = cudaMemPoolCreate(&ctx->mempool, &props)) != cudaSuccess) { st = cuda_fail(nullptr, e, "cudaMemPoolCreate"); ctx->mempool = nullptr; break; }
+        uint64_t keep = ~0ull;
+        cudaMemPoolSetAttribute(ctx->mempool, cudaMemPoolAttrReleaseThreshold, &keep);
     } while (0);
     if (prev >= 0) cudaSetDevice(prev);
     if (st != MVSIM_OK) {
+        if (ctx->mempool) cudaMemPoolDestroy(ctx->mempool);
+        if (ctx->d_scalars) cudaFree(ctx->d_scalars);
         if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
         delete ctx;
         return st;
@@ -346,6 +358,7 @@ int mvsim_ctx_destroy(mvsim_ctx* ctx)
     for (auto& ev : ctx->pool) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
     cudaFree(ctx->d_scalars);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->mempool) cudaMemPoolDestroy(ctx->mempool);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return MVSIM_OK;
@@ -574,6 +587,17 @@ int mvsim_simulate_view(mvsim_ctx* ctx, const mvsim_view_params* p, const float*
     return sync(ctx);
 }
 
+// Per-device phase gates of the batch call: callers that run contexts concurrently on one GPU (the reference's tile
+// stitching driver does, S/SimulateTileStitching.java:85-117) fall into a pipeline -- one uploads while the other computes.
+namespace {
+struct DeviceGates { std::mutex upload, compute; };
+DeviceGates& gates_for(int device)
+{
+    static DeviceGates gates[64];
+    return gates[(unsigned)device % 64];
+}
+}  // namespace
+
 int mvsim_simulate_views(mvsim_ctx* ctx, int n_views, const mvsim_view_params* params, const float* gt,
                          float* const* psfs, float* const* outs)
 {
@@ -588,38 +612,69 @@ int mvsim_simulate_views(mvsim_ctx* ctx, int n_views, const mvsim_view_params* p
     }
     if (!ctx->copy_stream) MVSIM_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     const size_t bytes = elems(params[0].dims) * sizeof(float);
-    DevBuf g(ctx);
-    MVSIM_TRY(g.alloc(bytes));
-    MVSIM_TRY(h2d(ctx, g.p, gt, bytes));
-    std::vector<void*> held;            // per-view device buffers stay alive until their download is done
+    DeviceGates& gates = gates_for(ctx->device);
+    static const bool trace = getenv("MVSIM_TRACE") != nullptr;
+    auto stamp = [&](const char* what) {
+        if (trace) fprintf(stderr, "[mvsim %p] %10.3f ms %s\n", (void*)ctx, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(), what);
+    };
+    stamp("enter");
     cudaEvent_t done = nullptr, copied = nullptr;
-    int st = MVSIM_OK;
     if (cudaEventCreateWithFlags(&done, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&copied, cudaEventDisableTiming) != cudaSuccess)
-        st = set_error(ctx, MVSIM_ECUDA, "simulate_views: cannot create events");
+        cudaEventCreateWithFlags(&copied, cudaEventDisableTiming) != cudaSuccess) {
+        if (done) cudaEventDestroy(done);
+        return set_error(ctx, MVSIM_ECUDA, "simulate_views: cannot create events");
+    }
+    DevBuf g(ctx);
+    int st = g.alloc(bytes);
+    std::vector<void*> held;            // per-view device buffers (psf, out) stay alive until their download is done
     for (int v = 0; v < n_views && st == MVSIM_OK; ++v) {
-        const mvsim_view_params* p = &params[v];
-        const size_t kbytes = elems(p->kdims) * sizeof(float);
-        const size_t obytes = (size_t)(p->dims[0] * p->dims[1] * ((p->dims[2] - 1) / p->inc + 1)) * sizeof(float);
         void *k = nullptr, *o = nullptr;
-        if ((st = dev_alloc(ctx, &k, kbytes)) != MVSIM_OK) break;
+        if ((st = dev_alloc(ctx, &k, elems(params[v].kdims) * sizeof(float))) != MVSIM_OK) break;
         held.push_back(k);
+        const size_t obytes = (size_t)(params[v].dims[0] * params[v].dims[1] * ((params[v].dims[2] - 1) / params[v].inc + 1)) * sizeof(float);
         if ((st = dev_alloc(ctx, &o, obytes)) != MVSIM_OK) break;
         held.push_back(o);
-        if ((st = h2d(ctx, k, psfs[v], kbytes)) != MVSIM_OK) break;
-        if ((st = dev_simulate_view(ctx, p, g.f(), static_cast<float*>(k), static_cast<float*>(o))) != MVSIM_OK) break;
-        cudaError_t e = cudaEventRecord(done, ctx->stream);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, done, 0);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(psfs[v], k, kbytes, cudaMemcpyDeviceToHost, ctx->copy_stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(outs[v], o, obytes, cudaMemcpyDeviceToHost, ctx->copy_stream);
-        if (e != cudaSuccess) st = cuda_fail(ctx, e, "simulate_views: download");
+    }
+    if (st == MVSIM_OK) {
+        // upload gate: two contexts never share the host->device link, so the second caller's upload runs at full rate
+        // under the first caller's kernels instead of both uploads at half rate followed by both kernel phases.  ALL of
+        // this call's uploads happen here: a PSF upload issued later would queue on the copy engine behind the other
+        // caller's 2 GB ground truth and stall this context's kernels for the length of that transfer.
+        std::lock_guard<std::mutex> lk(gates.upload);
+        stamp("upload gate");
+        st = h2d(ctx, g.p, gt, bytes);
+        for (int v = 0; v < n_views && st == MVSIM_OK; ++v) st = h2d(ctx, held[2 * v], psfs[v], elems(params[v].kdims) * sizeof(float));
+        if (st == MVSIM_OK && (cudaEventRecord(done, ctx->stream) != cudaSuccess || cudaEventSynchronize(done) != cudaSuccess))
+            st = set_error(ctx, MVSIM_ECUDA, "simulate_views: upload failed");
+    }
+    if (st == MVSIM_OK) {
+        stamp("upload done");
+        std::lock_guard<std::mutex> lk(gates.compute);
+        stamp("compute gate");
+        for (int v = 0; v < n_views && st == MVSIM_OK; ++v) {
+            const mvsim_view_params* p = &params[v];
+            const size_t kbytes = elems(p->kdims) * sizeof(float);
+            const size_t obytes = (size_t)(p->dims[0] * p->dims[1] * ((p->dims[2] - 1) / p->inc + 1)) * sizeof(float);
+            void *k = held[2 * v], *o = held[2 * v + 1];
+            if ((st = dev_simulate_view(ctx, p, g.f(), static_cast<float*>(k), static_cast<float*>(o))) != MVSIM_OK) break;
+            cudaError_t e = cudaEventRecord(done, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, done, 0);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(psfs[v], k, kbytes, cudaMemcpyDeviceToHost, ctx->copy_stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(outs[v], o, obytes, cudaMemcpyDeviceToHost, ctx->copy_stream);
+            if (e != cudaSuccess) st = cuda_fail(ctx, e, "simulate_views: download");
+        }
+        // the gate opens when the last kernel has run; the tail of the downloads overlaps the next caller's kernels
+        stamp("enqueued");
+        if (st == MVSIM_OK && cudaEventSynchronize(done) != cudaSuccess) st = set_error(ctx, MVSIM_ECUDA, "simulate_views: kernels failed");
+        stamp("kernels done");
     }
     // the main stream waits for the copy stream before the buffers go back to the pool
-    if (copied && cudaEventRecord(copied, ctx->copy_stream) == cudaSuccess) cudaStreamWaitEvent(ctx->stream, copied, 0);
+    if (cudaEventRecord(copied, ctx->copy_stream) == cudaSuccess) cudaStreamWaitEvent(ctx->stream, copied, 0);
     for (void* q : held) dev_free(ctx, q);
     const int st2 = sync(ctx);
-    if (done) cudaEventDestroy(done);
-    if (copied) cudaEventDestroy(copied);
+    stamp("downloads done");
+    cudaEventDestroy(done);
+    cudaEventDestroy(copied);
     return st != MVSIM_OK ? st : st2;
 }
 
@@ -682,6 +737,210 @@ int mvsim_normalize_weights(mvsim_ctx* ctx, float* const* weights, int n_views, 
     const int st2 = sync(ctx);
     for (void* q : held) dev_free(ctx, q);
     return st != MVSIM_OK ? st : st2;
+}
+
+// ---- input generators either side of the path -------------------------
+namespace mvsim {
+// java.util.Random (JDK specification): 48-bit LCG.  The reference draws bead positions (S/SimulateBeads.java:69,150-166)
+// and the sphere phantom (S/SimulateMultiViewDataset.java:76,485,506,512) from it; replaying it keeps the caller's seeds.
+struct JavaRandom {
+    uint64_t s;
+    explicit JavaRandom(int64_t seed) : s(((uint64_t)seed ^ 0x5DEECE66DULL) & ((1ULL << 48) - 1)) {}
+    int32_t next(int bits)
+    {
+        s = (s * 0x5DEECE66DULL + 0xBULL) & ((1ULL << 48) - 1);
+        return (int32_t)(int64_t)(s >> (48 - bits));
+    }
+    double next_double() { const int64_t a = next(26), b = next(27); return (double)((a << 27) + b) * 0x1.0p-53; }
+    int32_t next_int(int32_t bound)
+    {
+        int32_t r = next(31);
+        const int32_t m = bound - 1;
+        if ((bound & m) == 0) return (int32_t)(((int64_t)bound * (int64_t)r) >> 31);
+        for (int32_t u = r; (int32_t)((uint32_t)u - (uint32_t)(r = u % bound) + (uint32_t)m) < 0; u = next(31)) {}
+        return r;
+    }
+};
+
+// drawSpheres (:436-522): walk the large sphere in HyperSphereCursor order (z, y, x ascending, nested integer radii),
+// two draws per voxel, a third for the one voxel in ~2900 that gets a small sphere.  Only this replay is sequential.
+static void replay_draw_spheres(const int64_t dims[3], double minv, double maxv, int scale, int half_pixel, int64_t seed,
+                                std::vector<int>& rec, std::vector<float>& val)
+{
+    JavaRandom rnd(seed);
+    int64_t c[3], min_size = dims[0];
+    for (int d = 0; d < 3; ++d) { c[d] = dims[d] / 2; min_size = dims[d] < min_size ? dims[d] : min_size; }
+    const int64_t R = min_size / 2 - 47 * scale - 1;                                         // :462
+    const int max_radius = 10 * scale;                                                        // :458
+    const int64_t mod = (int64_t)(7 * scale) * (7 * scale) * (7 * scale);                     // Util.pow(7*scale, 3), :509
+    for (int64_t dz = -R; dz <= R; ++dz) {
+        const int64_t ry = (int64_t)sqrt((double)(R * R - dz * dz));
+        for (int64_t dy = -ry; dy <= ry; ++dy) {
+            const int64_t rx = (int64_t)sqrt((double)(ry * ry - dy * dy));
+            for (int64_t dx = -rx; dx <= rx; ++dx) {
+                const int radius = rnd.next_int(max_radius) + 1;                              // :485
+                const double rv = rnd.next_double();                                          // :506
+                if ((int64_t)floor(rv * 10000 + 0.5) % mod != 0) continue;                    // Math.round, :509
+                const double v = rnd.next_double() * (maxv - minv) + minv;                    // :512
+                const int shift = half_pixel ? 1 : 0;                                         // :496-499, all but the last dimension
+                rec.push_back((int)(c[0] + dx + shift));
+                rec.push_back((int)(c[1] + dy + shift));
+                rec.push_back((int)(c[2] + dz));
+                rec.push_back(radius);
+                val.push_back((float)v);
+            }
+        }
+    }
+}
+
+static int dev_draw_spheres(mvsim_ctx* ctx, const int64_t dims[3], double minv, double maxv, int scale, int half_pixel, int64_t seed,
+                            float* d_out, int64_t* n_small)
+{
+    if (scale < 1 || scale > 64) return set_error(ctx, MVSIM_EINVAL, "draw_spheres: scale must be in 1..64");
+    if (!(minv >= 0.0) || !(maxv >= minv)) return set_error(ctx, MVSIM_EINVAL, "draw_spheres: need 0 <= minValue <= maxValue");
+    std::vector<int> rec;
+    std::vector<float> val;
+    replay_draw_spheres(dims, minv, maxv, scale, half_pixel, seed, rec, val);
+    if (n_small) *n_small = (int64_t)val.size();
+    return k_paint_spheres(ctx, d_out, dims, rec.data(), val.data(), (int)val.size());
+}
+
+// simulate(halfPixelOffset, rnd) (:371-392): (size+1)*2 cube rendered, then downSample2x -> size^3
+static int dev_simulate_phantom(mvsim_ctx* ctx, int size, int half_pixel, int64_t seed, float* d_out, int64_t* n_small)
+{
+    const int scale = 2;
+    const int64_t big = (int64_t)(size + 1) * scale;
+    const int64_t dims[3] = { big, big, big };
+    DevBuf a(ctx);
+    MVSIM_TRY(a.alloc((size_t)(big * big * big) * sizeof(float)));
+    MVSIM_TRY(dev_draw_spheres(ctx, dims, 0.0, 1.0, scale, half_pixel, seed, a.f(), n_small));
+    return k_downsample2x(ctx, a.f(), dims, d_out);
+}
+}  // namespace mvsim
+using namespace mvsim;
+
+int mvsim_random_points(int n, const int64_t range_min[3], const int64_t range_max[3], int64_t seed, double* points)
+{
+    if (n < 0 || !range_min || !range_max || (n > 0 && !points)) return set_error(nullptr, MVSIM_EINVAL, "random_points: bad argument");
+    JavaRandom rnd(seed);
+    for (int i = 0; i < n; ++i)
+        for (int d = 0; d < 3; ++d)
+            points[3 * i + d] = rnd.next_double() * (double)(range_max[d] - range_min[d]) + (double)range_min[d];     // :161
+    return MVSIM_OK;
+}
+
+int mvsim_transform_points(const double* points, int n, const int64_t range_min[3], const int64_t range_max[3], int axis, int degrees, double* out)
+{
+    if (n < 0 || !range_min || !range_max || (n > 0 && (!points || !out))) return set_error(nullptr, MVSIM_EINVAL, "transform_points: bad argument");
+    int64_t dims[3];
+    for (int d = 0; d < 3; ++d) dims[d] = range_max[d] - range_min[d] + 1;          // axisRotation uses (max - min) / 2
+    double m[12];
+    if (axis_rotation(dims, axis, degrees, m, nullptr)) return set_error(nullptr, MVSIM_EINVAL, "transform_points: axis must be 0, 1 or 2");
+    for (int i = 0; i < n; ++i) {
+        const double p0 = points[3 * i], p1 = points[3 * i + 1], p2 = points[3 * i + 2];
+        for (int r = 0; r < 3; ++r) out[3 * i + r] = p0 * m[4 * r] + p1 * m[4 * r + 1] + p2 * m[4 * r + 2] + m[4 * r + 3];
+    }
+    return MVSIM_OK;
+}
+
+static int check_bead_args(mvsim_ctx* ctx, const double* points, int n, const double sigma[3], const int64_t imin[3], const int64_t imax[3], int64_t dims[3])
+{
+    if (n < 0 || (n > 0 && !points) || !sigma || !imin || !imax) return set_error(ctx, MVSIM_EINVAL, "render_beads: null argument");
+    for (int d = 0; d < 3; ++d) {
+        if (!(sigma[d] > 0) || sigma[d] > 1000) return set_error(ctx, MVSIM_EINVAL, "render_beads: sigma must be in (0, 1000]");
+        dims[d] = imax[d] - imin[d];
+    }
+    return check_dims(ctx, dims, "render_beads (image dims = max - min)");
+}
+
+int mvsim_render_beads(mvsim_ctx* ctx, const double* points, int n, const double sigma[3], const int64_t imin[3], const int64_t imax[3], float* out)
+{
+    MVSIM_ENTER(ctx);
+    int64_t dims[3];
+    MVSIM_TRY(check_bead_args(ctx, points, n, sigma, imin, imax, dims));
+    if (!out) return set_error(ctx, MVSIM_EINVAL, "render_beads: null buffer");
+    DevBuf a(ctx);
+    MVSIM_TRY(a.alloc(elems(dims) * sizeof(float)));
+    MVSIM_TRY(k_render_beads(ctx, points, n, sigma, imin, imax, a.f()));
+    MVSIM_TRY(d2h(ctx, out, a.p, elems(dims) * sizeof(float)));
+    return sync(ctx);
+}
+
+int mvsim_dev_render_beads(mvsim_ctx* ctx, const double* points, int n, const double sigma[3], const int64_t imin[3], const int64_t imax[3], mvsim_volume* out)
+{
+    MVSIM_ENTER(ctx);
+    int64_t dims[3];
+    MVSIM_TRY(check_bead_args(ctx, points, n, sigma, imin, imax, dims));
+    if (!out || out->dims[0] != dims[0] || out->dims[1] != dims[1] || out->dims[2] != dims[2])
+        return set_error(ctx, MVSIM_EINVAL, "render_beads: output volume must have dims max - min");
+    return k_render_beads(ctx, points, n, sigma, imin, imax, out->d);
+}
+
+int mvsim_draw_spheres(mvsim_ctx* ctx, const int64_t dims[3], double min_value, double max_value, int scale, int half_pixel, int64_t seed,
+                       float* out, int64_t* n_small)
+{
+    MVSIM_ENTER(ctx);
+    if (!out) return set_error(ctx, MVSIM_EINVAL, "draw_spheres: null buffer");
+    MVSIM_TRY(check_dims(ctx, dims, "draw_spheres"));
+    DevBuf a(ctx);
+    MVSIM_TRY(a.alloc(elems(dims) * sizeof(float)));
+    MVSIM_TRY(dev_draw_spheres(ctx, dims, min_value, max_value, scale, half_pixel, seed, a.f(), n_small));
+    MVSIM_TRY(d2h(ctx, out, a.p, elems(dims) * sizeof(float)));
+    return sync(ctx);
+}
+
+int mvsim_downsample2x(mvsim_ctx* ctx, const float* in, const int64_t dims[3], float* out)
+{
+    MVSIM_ENTER(ctx);
+    if (!in || !out) return set_error(ctx, MVSIM_EINVAL, "downsample2x: null buffer");
+    MVSIM_TRY(check_dims(ctx, dims, "downsample2x"));
+    if (dims[0] < 4 || dims[1] < 4 || dims[2] < 4) return set_error(ctx, MVSIM_EINVAL, "downsample2x: dims must be >= 4 (output is dims/2 - 1)");
+    const size_t obytes = (size_t)((dims[0] / 2 - 1) * (dims[1] / 2 - 1) * (dims[2] / 2 - 1)) * sizeof(float);
+    DevBuf a(ctx), b(ctx);
+    MVSIM_TRY(a.alloc(elems(dims) * sizeof(float)));
+    MVSIM_TRY(b.alloc(obytes));
+    MVSIM_TRY(h2d(ctx, a.p, in, elems(dims) * sizeof(float)));
+    MVSIM_TRY(k_downsample2x(ctx, a.f(), dims, b.f()));
+    MVSIM_TRY(d2h(ctx, out, b.p, obytes));
+    return sync(ctx);
+}
+
+int mvsim_simulate_phantom(mvsim_ctx* ctx, int size, int half_pixel, int64_t seed, float* out, int64_t* n_small)
+{
+    MVSIM_ENTER(ctx);
+    if (!out) return set_error(ctx, MVSIM_EINVAL, "simulate_phantom: null buffer");
+    if (size < 1 || size > 2047) return set_error(ctx, MVSIM_EINVAL, "simulate_phantom: size must be in 1..2047");
+    const size_t obytes = (size_t)size * size * size * sizeof(float);
+    DevBuf b(ctx);
+    MVSIM_TRY(b.alloc(obytes));
+    MVSIM_TRY(dev_simulate_phantom(ctx, size, half_pixel, seed, b.f(), n_small));
+    MVSIM_TRY(d2h(ctx, out, b.p, obytes));
+    return sync(ctx);
+}
+
+int mvsim_dev_simulate_phantom(mvsim_ctx* ctx, int size, int half_pixel, int64_t seed, mvsim_volume* out, int64_t* n_small)
+{
+    MVSIM_ENTER(ctx);
+    if (size < 1 || size > 2047) return set_error(ctx, MVSIM_EINVAL, "simulate_phantom: size must be in 1..2047");
+    if (!out || out->dims[0] != size || out->dims[1] != size || out->dims[2] != size)
+        return set_error(ctx, MVSIM_EINVAL, "simulate_phantom: output volume must be size^3");
+    return dev_simulate_phantom(ctx, size, half_pixel, seed, out->d, n_small);
+}
+
+int mvsim_make_square(mvsim_ctx* ctx, const float* in, const int64_t dims[3], float* out)
+{
+    MVSIM_ENTER(ctx);
+    if (!in || !out) return set_error(ctx, MVSIM_EINVAL, "make_square: null buffer");
+    MVSIM_TRY(check_dims(ctx, dims, "make_square"));
+    const int64_t m = dims[0] > dims[1] ? (dims[0] > dims[2] ? dims[0] : dims[2]) : (dims[1] > dims[2] ? dims[1] : dims[2]);
+    if (m > 4096) return set_error(ctx, MVSIM_EINVAL, "make_square: dims too large");
+    DevBuf a(ctx), b(ctx);
+    MVSIM_TRY(a.alloc(elems(dims) * sizeof(float)));
+    MVSIM_TRY(b.alloc((size_t)(m * m * m) * sizeof(float)));
+    MVSIM_TRY(h2d(ctx, a.p, in, elems(dims) * sizeof(float)));
+    MVSIM_TRY(k_make_square(ctx, a.f(), dims, b.f()));
+    MVSIM_TRY(d2h(ctx, out, b.p, (size_t)(m * m * m) * sizeof(float)));
+    return sync(ctx);
 }
 
 // ---- device-resident volumes ------------------------------------------------------------------

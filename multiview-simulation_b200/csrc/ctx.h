@@ -23,6 +23,8 @@ struct mvsim_ctx {
     cudaStream_t stream;
     bool own_stream;
     cudaStream_t copy_stream;                // lazily created: result downloads overlapping the next view
+    cudaMemPool_t mempool;                   // this context's own stream-ordered pool: workspaces are never traded between
+                                             // the streams of two contexts (callers run contexts concurrently)
     std::string err;
     double* d_scalars;                       // [8] device doubles: sums, corrections
     std::map<int, mvsim_tables> tables;      // by complex line length
@@ -80,6 +82,12 @@ int k_make_isotropic(mvsim_ctx* ctx, const float* in, const int64_t dims[3], int
 int k_weight_image(mvsim_ctx* ctx, const int64_t dims[3], float* out);
 int k_normalize_weights(mvsim_ctx* ctx, float* const* d_weights, int n_views, size_t n, float osem, float* d_sum_out);
 int k_poisson(mvsim_ctx* ctx, float* inout, size_t n, double snr, uint64_t seed, uint64_t stream);
+
+// input generators (phantom.cu).  points / host_rec / host_val are HOST arrays (consumed before return), the rest device pointers
+int k_render_beads(mvsim_ctx* ctx, const double* points, int n, const double sigma[3], const int64_t imin[3], const int64_t imax[3], float* d_out);
+int k_paint_spheres(mvsim_ctx* ctx, float* d_img, const int64_t dims[3], const int* host_rec /* n x (cx, cy, cz, radius) */, const float* host_val, int n);
+int k_downsample2x(mvsim_ctx* ctx, const float* in, const int64_t dims[3], float* out);
+int k_make_square(mvsim_ctx* ctx, const float* in, const int64_t dims[3], float* out);
 
 // convolution driver (conv.cu): psf normalised, device pointers; sum of the output voxels -> d_sum when non-null.
 // keep_inc > 1: out receives *out_planes planes -- the slices z = 0, inc, ... and one plane with the sum of the rest

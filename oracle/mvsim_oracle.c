@@ -18,6 +18,7 @@
  *
  * Layout everywhere: ImgLib2 ArrayImg order, x fastest: idx = x + X*(y + Y*z).
  */
+#include <float.h>
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -83,6 +84,16 @@ double orc_jrandom_next_double(orc_jrandom* r)
     int64_t a = (int64_t)jnext(r, 26);
     int64_t b = (int64_t)jnext(r, 27);
     return (double)((a << 27) + b) * 0x1.0p-53;
+}
+
+/* Random.nextInt(int bound), JDK specification (power-of-two shortcut, rejection loop otherwise) */
+int32_t orc_jrandom_next_int_bound(orc_jrandom* r, int32_t bound)
+{
+    int32_t v = jnext(r, 31);
+    const int32_t m = bound - 1;
+    if ((bound & m) == 0) return (int32_t)(((int64_t)bound * (int64_t)v) >> 31);
+    for (int32_t u = v; (int32_t)((uint32_t)u - (uint32_t)(v = u % bound) + (uint32_t)m) < 0; u = jnext(r, 31)) {}
+    return v;
 }
 
 /* ------------------------------------------------------------------------ */
@@ -594,6 +605,198 @@ int orc_normalize_weights(float** w, int n_views, size_t n, float osem, float* s
         }
         if (sum_out) sum_out[i] = s2;
     }
+    return ORC_OK;
+}
+
+/* ------------------------------------------------------------------------ */
+/* "next" row f-2: bead phantom renderer  S/SimulateBeads.java:97-205          */
+/* randomPoints (:150-166), transformPoints = axisRotation applied to points   */
+/* (:131-148), renderPoints/addGaussian (:97-121,168-205): every point inside  */
+/* the interval adds (float)prod_d exp(-x_d^2 / 2 sigma_d^2) * 1000f over a box */
+/* of 2*getSuggestedKernelDiameter(sigma_d) voxels per axis, in point order.    */
+/* ------------------------------------------------------------------------ */
+static int suggested_kernel_diameter(double sigma)
+{
+    /* imglib2 Util.getSuggestedKernelDiameter: max(3, 2*(int)(3 sigma + 0.5) + 1) */
+    int size = 3;
+    if (sigma > 0) size = 2 * (int)(3.0 * sigma + 0.5) + 1;
+    return size < 3 ? 3 : size;
+}
+
+void orc_random_points(int n, const int64_t range_dims[3], int64_t seed, double* points /* n*3 */)
+{
+    orc_jrandom r;
+    orc_jrandom_init(&r, seed);
+    for (int i = 0; i < n; ++i)
+        for (int d = 0; d < 3; ++d)     /* range.min = 0, range.max = dim - 1  (FinalInterval(dims)) */
+            points[3 * i + d] = orc_jrandom_next_double(&r) * (double)(range_dims[d] - 1) + 0.0;
+}
+
+int orc_transform_points(const double* points, int n, const int64_t range_dims[3], int axis, int degrees, double* out)
+{
+    double m[12];
+    if (orc_axis_rotation(range_dims, axis, degrees, m)) return ORC_EINVAL;
+    for (int i = 0; i < n; ++i) {
+        const double* p = points + 3 * i;
+        for (int r = 0; r < 3; ++r) out[3 * i + r] = p[0] * m[4 * r] + p[1] * m[4 * r + 1] + p[2] * m[4 * r + 2] + m[4 * r + 3];
+    }
+    return ORC_OK;
+}
+
+/* renderPoints (:97-121): image dims = interval.max - interval.min (ONE LESS than the interval's dimension, as written
+ * at :106), a point is kept when 0 <= p - min <= interval.dimension - 1 = max - min (isInsideAdjust :123-135, which also
+ * shifts the point by -min).  out has prod(max - min) floats. */
+int orc_render_beads(const double* points, int n, const double sigma[3], const int64_t imin[3], const int64_t imax[3], float* out)
+{
+    int64_t dims[3];
+    for (int d = 0; d < 3; ++d) { dims[d] = imax[d] - imin[d]; if (dims[d] < 1) return ORC_EINVAL; }
+    const int64_t X = dims[0], Y = dims[1], Z = dims[2];
+    memset(out, 0, sizeof(float) * (size_t)(X * Y * Z));
+    int size[3];
+    double two_sq[3];
+    for (int d = 0; d < 3; ++d) { size[d] = suggested_kernel_diameter(sigma[d]) * 2; two_sq[d] = 2 * sigma[d] * sigma[d]; }
+    for (int i = 0; i < n; ++i) {
+        double p[3];
+        int inside = 1;
+        for (int d = 0; d < 3; ++d) {
+            p[d] = points[3 * i + d] - (double)imin[d];
+            if (p[d] < 0 || p[d] > (double)(imax[d] - imin[d] + 1 - 1)) { inside = 0; break; }
+        }
+        if (!inside) continue;
+        int64_t mn[3];
+        for (int d = 0; d < 3; ++d) mn[d] = (int64_t)(int)floor(p[d] + 0.5) - size[d] / 2;     /* (int)Math.round(location) */
+        for (int64_t z = mn[2]; z < mn[2] + size[2]; ++z)
+            for (int64_t y = mn[1]; y < mn[1] + size[1]; ++y)
+                for (int64_t x = mn[0]; x < mn[0] + size[0]; ++x) {
+                    if (x < 0 || y < 0 || z < 0 || x >= X || y >= Y || z >= Z) continue;      /* Views.extendZero: writes outside are lost */
+                    double value = 1;
+                    const double dx = p[0] - (double)x, dy = p[1] - (double)y, dz = p[2] - (double)z;
+                    value *= exp(-(dx * dx) / two_sq[0]);
+                    value *= exp(-(dy * dy) / two_sq[1]);
+                    value *= exp(-(dz * dz) / two_sq[2]);
+                    float* o = out + x + X * (y + Y * z);
+                    *o = *o + ((float)value * 1000.0f);
+                }
+    }
+    return ORC_OK;
+}
+
+/* ------------------------------------------------------------------------ */
+/* "next" row f-3: sphere phantom  S/SimulateMultiViewDataset.java:366-522     */
+/* imglib2-algorithm HyperSphereCursor (third party, not under the reference  */
+/* tree; restated from the published source): z, then y, then x ascending;    */
+/* NESTED integer radii  ry = (long)sqrt(R^2 - dz^2), rx = (long)sqrt(ry^2 - dy^2). */
+/* ------------------------------------------------------------------------ */
+typedef void (*sphere_visit)(int64_t x, int64_t y, int64_t z, void* user);
+
+static void hypersphere_for_each(const int64_t c[3], int64_t R, sphere_visit fn, void* user)
+{
+    for (int64_t dz = -R; dz <= R; ++dz) {
+        const int64_t ry = (int64_t)sqrt((double)(R * R - dz * dz));
+        for (int64_t dy = -ry; dy <= ry; ++dy) {
+            const int64_t rx = (int64_t)sqrt((double)(ry * ry - dy * dy));
+            for (int64_t dx = -rx; dx <= rx; ++dx) fn(c[0] + dx, c[1] + dy, c[2] + dz, user);
+        }
+    }
+}
+
+typedef struct { float* img; int64_t dims[3]; float v; } paint_ctx;
+
+static void paint_max(int64_t x, int64_t y, int64_t z, void* user)
+{
+    paint_ctx* c = (paint_ctx*)user;
+    if (x < 0 || y < 0 || z < 0 || x >= c->dims[0] || y >= c->dims[1] || z >= c->dims[2]) return;   /* cannot happen for the reference sizes */
+    float* o = c->img + x + c->dims[0] * (y + c->dims[1] * z);
+    /* value.setReal(Math.max(randomValue, value.getRealDouble())) (:517): float store of a double max == max of the float roundings */
+    if (c->v > *o) *o = c->v;
+}
+
+typedef struct { orc_jrandom* rnd; paint_ctx paint; int scale; int half_pixel; double minv, maxv; int64_t mod; int64_t n_small; float* list; int64_t list_cap; } draw_ctx;
+
+static void draw_visit(int64_t x, int64_t y, int64_t z, void* user)
+{
+    draw_ctx* d = (draw_ctx*)user;
+    const int radius = orc_jrandom_next_int_bound(d->rnd, 10 * d->scale) + 1;                 /* :485 */
+    double rv = orc_jrandom_next_double(d->rnd);                                              /* :506 */
+    const int64_t rounded = (int64_t)floor(rv * 10000 + 0.5);                                 /* Math.round */
+    if (rounded % d->mod != 0) return;                                                        /* :509 */
+    rv = orc_jrandom_next_double(d->rnd) * (d->maxv - d->minv) + d->minv;                     /* :512 */
+    int64_t c[3] = { x, y, z };
+    if (d->half_pixel) { c[0] += 1; c[1] += 1; }                                              /* :496-499: all but the last dimension */
+    if (d->list && d->n_small < d->list_cap) {
+        float* e = d->list + 5 * d->n_small;
+        e[0] = (float)c[0]; e[1] = (float)c[1]; e[2] = (float)c[2]; e[3] = (float)radius; e[4] = (float)rv;
+    }
+    d->n_small++;
+    d->paint.v = (float)rv;
+    hypersphere_for_each(c, radius, paint_max, &d->paint);
+}
+
+/* drawSpheres (:436-522) into a zeroed img of dims; returns the number of small spheres drawn.  list (nullable) receives
+ * up to list_cap records (cx, cy, cz, radius, value). */
+int64_t orc_draw_spheres(float* img, const int64_t dims[3], double minv, double maxv, int scale, int half_pixel, int64_t seed,
+                         float* list, int64_t list_cap)
+{
+    orc_jrandom r;
+    orc_jrandom_init(&r, seed);
+    int64_t c[3], min_size = dims[0];
+    for (int d = 0; d < 3; ++d) { c[d] = dims[d] / 2; if (dims[d] < min_size) min_size = dims[d]; }
+    const int64_t R = min_size / 2 - 47 * scale - 1;                                          /* :462 */
+    draw_ctx d;
+    d.rnd = &r; d.paint.img = img; memcpy(d.paint.dims, dims, sizeof(d.paint.dims)); d.scale = scale; d.half_pixel = half_pixel;
+    d.minv = minv; d.maxv = maxv; d.mod = (int64_t)(7 * scale) * (7 * scale) * (7 * scale);  /* Util.pow(7*scale, 3) */
+    d.n_small = 0; d.list = list; d.list_cap = list_cap;
+    if (R < 0) return 0;
+    hypersphere_for_each(c, R, draw_visit, &d);
+    return d.n_small;
+}
+
+/* downSample2x (:394-423): dims/2 - 1, n-linear at 2l + 0.5 over the mirror-single extension */
+int orc_downsample2x(const float* in, const int64_t dims[3], float* out)
+{
+    int64_t od[3];
+    for (int d = 0; d < 3; ++d) { od[d] = dims[d] / 2 - 1; if (od[d] < 1) return ORC_EINVAL; }
+    const int nt = stage_threads();
+#pragma omp parallel for num_threads(nt) schedule(static)
+    for (int64_t z = 0; z < od[2]; ++z)
+        for (int64_t y = 0; y < od[1]; ++y)
+            for (int64_t x = 0; x < od[0]; ++x) {
+                const double p[3] = { (double)x * 2.0 + 0.5, (double)y * 2.0 + 0.5, (double)z * 2.0 + 0.5 };
+                out[x + od[0] * (y + od[1] * z)] = nlinear3(in, dims, p, 1);
+            }
+    return ORC_OK;
+}
+
+/* simulate(halfPixelOffset, rnd) (:371-392) for a given final size (reference: 289); out has size^3 floats */
+int64_t orc_simulate_phantom(int size, int half_pixel, int64_t seed, float* out)
+{
+    const int scale = 2;
+    const int64_t big = (int64_t)(size + 1) * scale;
+    const int64_t dims[3] = { big, big, big };
+    float* img = (float*)calloc((size_t)(big * big * big), sizeof(float));
+    if (!img) return -1;
+    const int64_t n = orc_draw_spheres(img, dims, 0.0, 1.0, scale, half_pixel, seed, NULL, 0);
+    const int st = orc_downsample2x(img, dims, out);
+    free(img);
+    return st == ORC_OK ? n : -1;
+}
+
+/* Tools.makeSquare (S/Tools.java:315-349): cube of the largest dimension, input centred with the offset
+ * -square/2 + dim/2 (integer divisions), padded with the input's minimum */
+int orc_make_square(const float* in, const int64_t dims[3], float* out)
+{
+    int64_t m = 0;
+    for (int d = 0; d < 3; ++d) if (dims[d] > m) m = dims[d];
+    float mn = FLT_MAX;
+    const size_t n = (size_t)(dims[0] * dims[1] * dims[2]);
+    for (size_t i = 0; i < n; ++i) mn = in[i] < mn ? in[i] : mn;
+    for (int64_t z = 0; z < m; ++z)
+        for (int64_t y = 0; y < m; ++y)
+            for (int64_t x = 0; x < m; ++x) {
+                const int64_t sx = x - m / 2 + dims[0] / 2, sy = y - m / 2 + dims[1] / 2, sz = z - m / 2 + dims[2] / 2;
+                const int inside = sx >= 0 && sy >= 0 && sz >= 0 && sx < dims[0] && sy < dims[1] && sz < dims[2];
+                out[x + m * (y + m * z)] = inside ? in[sx + dims[0] * (sy + dims[1] * sz)] : mn;
+            }
     return ORC_OK;
 }
 

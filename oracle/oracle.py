@@ -62,6 +62,18 @@ def lib():
         L.orc_make_isotropic.argtypes = [fp, i64p, C.c_int, fp]
         L.orc_weight_image.argtypes = [i64p, fp]
         L.orc_normalize_weights.argtypes = [C.POINTER(fp), C.c_int, C.c_size_t, C.c_float, fp]
+        L.orc_random_points.argtypes = [C.c_int, i64p, C.c_int64, dp]
+        L.orc_random_points.restype = None
+        L.orc_transform_points.argtypes = [dp, C.c_int, i64p, C.c_int, C.c_int, dp]
+        L.orc_render_beads.argtypes = [dp, C.c_int, dp, i64p, i64p, fp]
+        L.orc_draw_spheres.argtypes = [fp, i64p, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int64, fp, C.c_int64]
+        L.orc_draw_spheres.restype = C.c_int64
+        L.orc_downsample2x.argtypes = [fp, i64p, fp]
+        L.orc_simulate_phantom.argtypes = [C.c_int, C.c_int, C.c_int64, fp]
+        L.orc_simulate_phantom.restype = C.c_int64
+        L.orc_make_square.argtypes = [fp, i64p, fp]
+        L.orc_jrandom_next_int_bound.argtypes = [C.c_void_p, C.c_int32]
+        L.orc_jrandom_next_int_bound.restype = C.c_int32
         L.orc_simulate_view.argtypes = [fp, i64p, fp, i64p, C.c_int, C.c_int, C.c_double, C.c_float,
                                         C.c_float, C.c_int, C.c_float, C.c_int64, C.c_int, C.c_int,
                                         fp, fp, dp]
@@ -104,6 +116,9 @@ class JavaRandom:
 
     def next_double(self):
         return lib().orc_jrandom_next_double(C.byref(self._s))
+
+    def next_int_bound(self, bound):
+        return lib().orc_jrandom_next_int_bound(C.byref(self._s), int(bound))
 
     @property
     def ptr(self):
@@ -225,3 +240,66 @@ def normalize_weights(weights, osem):
     s = np.empty_like(weights[0])
     _check(lib().orc_normalize_weights(arr, n, weights[0].size, osem, _f(s)), "normalize_weights")
     return s
+
+
+def random_points(n, dims_xyz, seed=535):
+    """SimulateBeads.randomPoints with new Random(535) (S/SimulateBeads.java:69,150-166); returns (n, 3) xyz doubles."""
+    pts = np.empty((n, 3), dtype=np.float64)
+    lib().orc_random_points(n, (C.c_int64 * 3)(*dims_xyz), seed, pts.ctypes.data_as(C.POINTER(C.c_double)))
+    return pts
+
+
+def transform_points(points, dims_xyz, axis, degrees):
+    points = np.ascontiguousarray(points, dtype=np.float64)
+    out = np.empty_like(points)
+    dp = C.POINTER(C.c_double)
+    _check(lib().orc_transform_points(points.ctypes.data_as(dp), len(points), (C.c_int64 * 3)(*dims_xyz), axis, degrees,
+                                      out.ctypes.data_as(dp)), "transform_points")
+    return out
+
+
+def render_beads(points, sigma_xyz, interval_min_xyz, interval_max_xyz):
+    """SimulateBeads.renderPoints for one point list (S/SimulateBeads.java:97-121,168-205).  The image has
+    max - min voxels per axis (the reference's own off-by-one at :106); returns it as a (z, y, x) array."""
+    points = np.ascontiguousarray(points, dtype=np.float64)
+    shape = tuple(int(interval_max_xyz[d] - interval_min_xyz[d]) for d in (2, 1, 0))
+    out = np.empty(shape, dtype=np.float32)
+    dp = C.POINTER(C.c_double)
+    _check(lib().orc_render_beads(points.ctypes.data_as(dp), len(points), (C.c_double * 3)(*sigma_xyz),
+                                  (C.c_int64 * 3)(*interval_min_xyz), (C.c_int64 * 3)(*interval_max_xyz), _f(out)), "render_beads")
+    return out
+
+
+def draw_spheres(shape_zyx, scale=2, half_pixel=False, seed=464232194, min_value=0.0, max_value=1.0, max_list=1 << 20):
+    """drawSpheres (S/SimulateMultiViewDataset.java:436-522) into a zero volume; returns (volume, list of
+    (cx, cy, cz, radius, value) records of the small spheres that were drawn)."""
+    img = np.zeros(shape_zyx, dtype=np.float32)
+    lst = np.zeros((max_list, 5), dtype=np.float32)
+    n = lib().orc_draw_spheres(_f(img), _dims(img), min_value, max_value, scale, int(half_pixel), seed, _f(lst), max_list)
+    return img, lst[:min(n, max_list)]
+
+
+def downsample2x(vol):
+    """downSample2x (:394-423)."""
+    vol = np.ascontiguousarray(vol, dtype=np.float32)
+    out = np.empty(tuple(s // 2 - 1 for s in vol.shape), dtype=np.float32)
+    _check(lib().orc_downsample2x(_f(vol), _dims(vol), _f(out)), "downsample2x")
+    return out
+
+
+def simulate_phantom(size=289, half_pixel=False, seed=464232194):
+    """simulate(halfPixelOffset, rnd) (:371-392): size^3 ground truth; returns (volume, number of small spheres)."""
+    out = np.empty((size, size, size), dtype=np.float32)
+    n = lib().orc_simulate_phantom(size, int(half_pixel), seed, _f(out))
+    if n < 0:
+        raise RuntimeError("oracle simulate_phantom failed")
+    return out, int(n)
+
+
+def make_square(vol):
+    """Tools.makeSquare (S/Tools.java:315-349)."""
+    vol = np.ascontiguousarray(vol, dtype=np.float32)
+    m = max(vol.shape)
+    out = np.empty((m, m, m), dtype=np.float32)
+    _check(lib().orc_make_square(_f(vol), _dims(vol), _f(out)), "make_square")
+    return out
