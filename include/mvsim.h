@@ -158,6 +158,9 @@ int mvsim_make_square(mvsim_ctx* ctx, const float* in, const int64_t dims[3], fl
 
 /* ---- device-resident volumes (SNR sweeps a la S/SimulateTileStitching.java:131-189) ------- */
 int mvsim_volume_create(mvsim_ctx* ctx, const int64_t dims[3], mvsim_volume** vol);
+/* non-owning handle over device memory the caller allocated (16-byte aligned; e.g. a buffer an NCCL broadcast fills); freeing the
+ * handle leaves the memory alone */
+int mvsim_volume_wrap(mvsim_ctx* ctx, const int64_t dims[3], void* device_ptr, mvsim_volume** vol);
 int mvsim_volume_free(mvsim_ctx* ctx, mvsim_volume* vol);
 int mvsim_volume_dims(const mvsim_volume* vol, int64_t dims[3]);
 void* mvsim_volume_device_ptr(mvsim_volume* vol);
@@ -173,6 +176,10 @@ int mvsim_dev_adjust(mvsim_ctx* ctx, mvsim_volume* img, float min_value, float t
 int mvsim_dev_extract_slices(mvsim_ctx* ctx, const mvsim_volume* in, int inc, float snr, uint64_t seed, uint64_t stream, mvsim_volume* out);
 /* gt: ground truth, psf: raw PSF (normalised in place), out: X*Y*((Z-1)/inc+1) */
 int mvsim_dev_simulate_view(mvsim_ctx* ctx, const mvsim_view_params* p, const mvsim_volume* gt, mvsim_volume* psf, mvsim_volume* out);
+/* the view loop (:567-613) on a ground truth that is already resident (uploaded once, generated on the device, or received from
+ * another GPU over NVLink when views are sharded across ranks); PSFs and results are host buffers as in mvsim_simulate_views */
+int mvsim_dev_simulate_views(mvsim_ctx* ctx, int n_views, const mvsim_view_params* params, const mvsim_volume* gt,
+                             float* const* psfs, float* const* outs);
 /* the generators writing straight into a device-resident volume (the ground truth never visits the host) */
 int mvsim_dev_render_beads(mvsim_ctx* ctx, const double* points, int n, const double sigma[3], const int64_t interval_min[3],
                            const int64_t interval_max[3], mvsim_volume* out);

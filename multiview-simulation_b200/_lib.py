@@ -71,6 +71,7 @@ SYMBOLS = [
     ("mvsim_dev_render_beads", C.c_int, [_vp, _dp, C.c_int, _dp, _i64p, _i64p, _vp]),
     ("mvsim_dev_simulate_phantom", C.c_int, [_vp, C.c_int, C.c_int, C.c_int64, _vp, _i64p]),
     ("mvsim_volume_create", C.c_int, [_vp, _i64p, C.POINTER(_vp)]),
+    ("mvsim_volume_wrap", C.c_int, [_vp, _i64p, _vp, C.POINTER(_vp)]),
     ("mvsim_volume_free", C.c_int, [_vp, _vp]),
     ("mvsim_volume_dims", C.c_int, [_vp, _i64p]),
     ("mvsim_volume_device_ptr", _vp, [_vp]),
@@ -83,6 +84,7 @@ SYMBOLS = [
     ("mvsim_dev_adjust", C.c_int, [_vp, _vp, C.c_float, C.c_float, _dp]),
     ("mvsim_dev_extract_slices", C.c_int, [_vp, _vp, C.c_int, C.c_float, C.c_uint64, C.c_uint64, _vp]),
     ("mvsim_dev_simulate_view", C.c_int, [_vp, C.POINTER(ViewParams), _vp, _vp, _vp]),
+    ("mvsim_dev_simulate_views", C.c_int, [_vp, C.c_int, C.POINTER(ViewParams), _vp, C.POINTER(_fp), C.POINTER(_fp)]),
     ("mvsim_slabconv_create", C.c_int, [_vp, _i64p, _i64p, C.c_int, C.c_int, C.POINTER(_vp)]),
     ("mvsim_slabconv_destroy", C.c_int, [_vp, _vp]),
     ("mvsim_slabconv_info", C.c_int, [_vp, _i64p]),

@@ -156,6 +156,18 @@ class DeviceVolume:
         if host is not None:
             self.upload(host)
 
+    @classmethod
+    def wrap(cls, ctx, shape_zyx, device_ptr, keepalive=None):
+        """Non-owning handle over device memory of the caller (mvsim_volume_wrap), e.g. `tensor.data_ptr()` of a torch tensor
+        that an NCCL broadcast fills; `keepalive` holds the owner."""
+        self = cls.__new__(cls)
+        self.ctx = ctx
+        self.shape = tuple(int(s) for s in shape_zyx)
+        self.h = C.c_void_p()
+        self._keepalive = keepalive
+        check(ctx._lib.mvsim_volume_wrap(ctx.h, dims3(self.shape), C.c_void_p(int(device_ptr)), C.byref(self.h)), ctx.h)
+        return self
+
     def upload(self, host):
         host = _vol(host)
         if host.shape != self.shape:
@@ -391,7 +403,9 @@ class SimulateMultiViewDataset:
         one angle per view.  Ground truth is uploaded once, downloads overlap the next view.  `psfs`
         are normalised in place.  Returns the list of acquired volumes (written into `outs` if given)."""
         ctx = ctx or default_context()
-        gt = _vol(gt, "gt")
+        resident = isinstance(gt, DeviceVolume)       # ground truth already in HBM (uploaded once, generated there, or broadcast)
+        if not resident:
+            gt = _vol(gt, "gt")
         n = len(degrees)
         if len(psfs) != n:
             raise ValueError("one PSF per view")
@@ -412,7 +426,10 @@ class SimulateMultiViewDataset:
         fpp = C.POINTER(C.c_float)
         parr = (fpp * n)(*[fptr(p) for p in psfs])
         oarr = (fpp * n)(*[fptr(o) for o in outs])
-        check(ctx._lib.mvsim_simulate_views(ctx.h, n, params, fptr(gt), parr, oarr), ctx.h)
+        if resident:
+            check(ctx._lib.mvsim_dev_simulate_views(ctx.h, n, params, gt.h, parr, oarr), ctx.h)
+        else:
+            check(ctx._lib.mvsim_simulate_views(ctx.h, n, params, fptr(gt), parr, oarr), ctx.h)
         return outs
 
 

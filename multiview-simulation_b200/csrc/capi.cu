@@ -598,11 +598,11 @@ DeviceGates& gates_for(int device)
 }
 }  // namespace
 
-int mvsim_simulate_views(mvsim_ctx* ctx, int n_views, const mvsim_view_params* params, const float* gt,
-                         float* const* psfs, float* const* outs)
+// gt: host ground truth (uploaded under the upload gate) or, when d_gt is given, already resident on the device
+static int simulate_views_impl(mvsim_ctx* ctx, int n_views, const mvsim_view_params* params, const float* gt, const float* d_gt,
+                               float* const* psfs, float* const* outs)
 {
-    MVSIM_ENTER(ctx);
-    if (n_views < 0 || (n_views > 0 && (!params || !gt || !psfs || !outs))) return set_error(ctx, MVSIM_EINVAL, "simulate_views: null argument");
+    if (n_views < 0 || (n_views > 0 && (!params || (!gt && !d_gt) || !psfs || !outs))) return set_error(ctx, MVSIM_EINVAL, "simulate_views: null argument");
     if (n_views == 0) return MVSIM_OK;
     for (int v = 0; v < n_views; ++v) {
         MVSIM_TRY(check_view(ctx, &params[v]));
@@ -625,7 +625,8 @@ int mvsim_simulate_views(mvsim_ctx* ctx, int n_views, const mvsim_view_params* p
         return set_error(ctx, MVSIM_ECUDA, "simulate_views: cannot create events");
     }
     DevBuf g(ctx);
-    int st = g.alloc(bytes);
+    int st = d_gt ? MVSIM_OK : g.alloc(bytes);
+    const float* gt_dev = d_gt ? d_gt : g.f();
     std::vector<void*> held;            // per-view device buffers (psf, out) stay alive until their download is done
     for (int v = 0; v < n_views && st == MVSIM_OK; ++v) {
         void *k = nullptr, *o = nullptr;
@@ -642,7 +643,7 @@ int mvsim_simulate_views(mvsim_ctx* ctx, int n_views, const mvsim_view_params* p
         // caller's 2 GB ground truth and stall this context's kernels for the length of that transfer.
         std::lock_guard<std::mutex> lk(gates.upload);
         stamp("upload gate");
-        st = h2d(ctx, g.p, gt, bytes);
+        if (!d_gt) st = h2d(ctx, g.p, gt, bytes);
         for (int v = 0; v < n_views && st == MVSIM_OK; ++v) st = h2d(ctx, held[2 * v], psfs[v], elems(params[v].kdims) * sizeof(float));
         if (st == MVSIM_OK && (cudaEventRecord(done, ctx->stream) != cudaSuccess || cudaEventSynchronize(done) != cudaSuccess))
             st = set_error(ctx, MVSIM_ECUDA, "simulate_views: upload failed");
@@ -656,7 +657,7 @@ int mvsim_simulate_views(mvsim_ctx* ctx, int n_views, const mvsim_view_params* p
             const size_t kbytes = elems(p->kdims) * sizeof(float);
             const size_t obytes = (size_t)(p->dims[0] * p->dims[1] * ((p->dims[2] - 1) / p->inc + 1)) * sizeof(float);
             void *k = held[2 * v], *o = held[2 * v + 1];
-            if ((st = dev_simulate_view(ctx, p, g.f(), static_cast<float*>(k), static_cast<float*>(o))) != MVSIM_OK) break;
+            if ((st = dev_simulate_view(ctx, p, gt_dev, static_cast<float*>(k), static_cast<float*>(o))) != MVSIM_OK) break;
             cudaError_t e = cudaEventRecord(done, ctx->stream);
             if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, done, 0);
             if (e == cudaSuccess) e = cudaMemcpyAsync(psfs[v], k, kbytes, cudaMemcpyDeviceToHost, ctx->copy_stream);
@@ -676,6 +677,25 @@ int mvsim_simulate_views(mvsim_ctx* ctx, int n_views, const mvsim_view_params* p
     cudaEventDestroy(done);
     cudaEventDestroy(copied);
     return st != MVSIM_OK ? st : st2;
+}
+
+int mvsim_simulate_views(mvsim_ctx* ctx, int n_views, const mvsim_view_params* params, const float* gt,
+                         float* const* psfs, float* const* outs)
+{
+    MVSIM_ENTER(ctx);
+    if (n_views > 0 && !gt) return set_error(ctx, MVSIM_EINVAL, "simulate_views: null ground truth");
+    return simulate_views_impl(ctx, n_views, params, gt, nullptr, psfs, outs);
+}
+
+int mvsim_dev_simulate_views(mvsim_ctx* ctx, int n_views, const mvsim_view_params* params, const mvsim_volume* gt,
+                             float* const* psfs, float* const* outs)
+{
+    MVSIM_ENTER(ctx);
+    if (n_views > 0 && !gt) return set_error(ctx, MVSIM_EINVAL, "simulate_views: null ground truth");
+    if (n_views > 0 && params)
+        for (int d = 0; d < 3; ++d)
+            if (gt->dims[d] != params[0].dims[d]) return set_error(ctx, MVSIM_EINVAL, "simulate_views: ground truth volume dims differ from the view params");
+    return simulate_views_impl(ctx, n_views, params, nullptr, gt ? gt->d : nullptr, psfs, outs);
 }
 
 // ---- post-acquisition chain ---------------------------------------------------------------------
@@ -959,12 +979,28 @@ int mvsim_volume_create(mvsim_ctx* ctx, const int64_t dims[3], mvsim_volume** vo
     return MVSIM_OK;
 }
 
+int mvsim_volume_wrap(mvsim_ctx* ctx, const int64_t dims[3], void* device_ptr, mvsim_volume** vol)
+{
+    MVSIM_ENTER(ctx);
+    if (!vol || !device_ptr) return set_error(ctx, MVSIM_EINVAL, "volume_wrap: null argument");
+    *vol = nullptr;
+    MVSIM_TRY(check_dims(ctx, dims, "volume_wrap"));
+    if (reinterpret_cast<uintptr_t>(device_ptr) % 16) return set_error(ctx, MVSIM_EINVAL, "volume_wrap: device pointer must be 16-byte aligned");
+    mvsim_volume* v = new mvsim_volume();
+    v->device = ctx->device;
+    memcpy(v->dims, dims, sizeof(v->dims));
+    v->d = static_cast<float*>(device_ptr);
+    v->borrowed = true;
+    *vol = v;
+    return MVSIM_OK;
+}
+
 int mvsim_volume_free(mvsim_ctx* ctx, mvsim_volume* vol)
 {
     if (!vol) return MVSIM_OK;
     MVSIM_ENTER(ctx);
     cudaStreamSynchronize(ctx->stream);
-    cudaFree(vol->d);
+    if (!vol->borrowed) cudaFree(vol->d);
     delete vol;
     return MVSIM_OK;
 }

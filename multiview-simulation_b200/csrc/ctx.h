@@ -13,6 +13,7 @@ struct mvsim_volume {
     float* d;
     int64_t dims[3];
     int device;
+    bool borrowed = false;      // mvsim_volume_wrap: memory owned by the caller (e.g. a torch tensor filled by an NCCL broadcast)
     size_t elems() const { return (size_t)(dims[0] * dims[1] * dims[2]); }
 };
 

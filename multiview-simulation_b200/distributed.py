@@ -43,6 +43,9 @@ class Group:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
+    def min(self, value):
+        return -self.max(-float(value))
+
     def sum(self, value):
         if self.dist is None:
             return int(value)
@@ -50,6 +53,22 @@ class Group:
         t = self._tensor([int(value)], torch.int64)
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
         return int(t.item())
+
+    def broadcast_ground_truth(self, ctx, shape_zyx, host=None, src=0, tensor=None):
+        """One dataset, views sharded over the ranks: rank `src` uploads the ground truth ONCE from (pinned) host memory and
+        NCCL broadcasts it over NVLink; every rank gets a DeviceVolume over the received buffer.  This replaces world_size
+        uploads through the shared host link by one upload plus an on-fabric copy.  `tensor` (optional)
+        is a reusable float32 CUDA tensor of that shape.  Returns (volume, tensor)."""
+        import torch
+        from .api import DeviceVolume
+        if tensor is None:
+            tensor = torch.empty(tuple(shape_zyx), dtype=torch.float32, device=self.device)
+        if self.rank == src:
+            h = torch.from_numpy(host)
+            tensor.copy_(h, non_blocking=True)
+        if self.dist is not None:
+            self.dist.broadcast(tensor, src=src)
+        return DeviceVolume.wrap(ctx, shape_zyx, tensor.data_ptr(), keepalive=tensor), tensor
 
     def my_views(self, n_views):
         return views_for_rank(n_views, self.rank, self.world)

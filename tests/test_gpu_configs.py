@@ -125,3 +125,27 @@ def test_bead_volume_snr_sweep_on_device_resident_view(mv):
     for v in (d_gt, d_rot, d_att, d_con, d_psf, d_out):
         v.free()
     ctx.close()
+
+
+def test_view_loop_on_resident_and_wrapped_ground_truth(mv):
+    """mvsim_dev_simulate_views: the view loop on a ground truth that is already in HBM (uploaded once / broadcast over
+    NVLink when views are sharded), through an owned volume and through a non-owning mvsim_volume_wrap handle."""
+    S = mv.SimulateMultiViewDataset
+    ctx = mv.Context(0)
+    gt = sphere_phantom((24, 40, 40), n_spheres=60)
+    psfs = [gaussian_psf((9, 7, 7), (2.0 + 0.1 * v, 1.0, 1.1), threshold=1e-3) for v in range(3)]
+    degrees = [15, 135, 255]
+    ref = S.simulateViews(gt, [p.copy() for p in psfs], degrees, inc=3, poissonSNR=25.0, rnd=7, ctx=ctx)
+    vol = mv.DeviceVolume(ctx, gt.shape, gt)
+    got = S.simulateViews(vol, [p.copy() for p in psfs], degrees, inc=3, poissonSNR=25.0, rnd=7, ctx=ctx)
+    alias = mv.DeviceVolume.wrap(ctx, gt.shape, vol.device_ptr, keepalive=vol)
+    got2 = S.simulateViews(alias, [p.copy() for p in psfs], degrees, inc=3, poissonSNR=25.0, rnd=7, ctx=ctx)
+    for a, b, c in zip(ref, got, got2):
+        assert np.array_equal(a, b) and np.array_equal(a, c)
+    alias.free()                                   # frees the handle only
+    assert np.array_equal(vol.download(), gt)      # the memory is still the owner's
+    with pytest.raises(ValueError):
+        S.simulateViews(mv.DeviceVolume(ctx, (24, 40, 44)), [p.copy() for p in psfs], degrees, inc=3, ctx=ctx,
+                        outs=[np.empty((8, 40, 40), dtype=np.float32) for _ in range(3)])
+    vol.free()
+    ctx.close()
