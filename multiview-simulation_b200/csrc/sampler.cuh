@@ -59,6 +59,43 @@ MVSIM_HD PoissonKey make_poisson_key(uint64_t seed, uint64_t stream)
     return k;
 }
 
+// Approximate float division / square root / exp / log on the paths where a relative error of ~1e-7 only perturbs a
+// probability by as much (MUFU on the device, libm on the host emulation)
+MVSIM_HD float fast_div(float a, float b)
+{
+#ifdef __CUDA_ARCH__
+    return __fdividef(a, b);
+#else
+    return a / b;
+#endif
+}
+MVSIM_HD float fast_sqrt(float a)
+{
+#ifdef __CUDA_ARCH__
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+    return r;
+#else
+    return sqrtf(a);
+#endif
+}
+MVSIM_HD float fast_exp(float a)
+{
+#ifdef __CUDA_ARCH__
+    return __expf(a);
+#else
+    return expf(a);
+#endif
+}
+MVSIM_HD float fast_log(float a)
+{
+#ifdef __CUDA_ARCH__
+    return __logf(a);
+#else
+    return logf(a);
+#endif
+}
+
 // (0,1) float uniform from 32 random bits (24 significant)
 MVSIM_HD float u01f(uint32_t x) { return ((float)(x >> 8) + 0.5f) * 0x1.0p-24f; }
 
@@ -69,9 +106,9 @@ MVSIM_HD PtrsParams ptrs_params(float lam)
 {
     PtrsParams q;
     q.lam = lam;
-    q.b = 0.931f + 2.53f * sqrtf(lam);
+    q.b = 0.931f + 2.53f * fast_sqrt(lam);
     q.a = -0.059f + 0.02483f * q.b;
-    q.vr = 0.9277f - 3.6224f / (q.b - 2.0f);
+    q.vr = 0.9277f - fast_div(3.6224f, q.b - 2.0f);
     return q;
 }
 
@@ -82,7 +119,7 @@ MVSIM_HD int ptrs_propose(const PtrsParams& q, uint32_t ru, uint32_t rv, float& 
     const float U = u01f(ru) - 0.5f;
     V = u01f(rv);
     us = 0.5f - fabsf(U);
-    kf = floorf((2.0f * q.a / us + q.b) * U + q.lam + 0.43f);
+    kf = floorf((fast_div(2.0f * q.a, us) + q.b) * U + q.lam + 0.43f);
     if (us >= 0.07f && V <= q.vr) return 1;
     if (kf < 0.0f || (us < 0.013f && V > us)) return 0;
     return 2;
@@ -93,9 +130,9 @@ MVSIM_HD int ptrs_propose(const PtrsParams& q, uint32_t ru, uint32_t rv, float& 
 // cancel analytically:  rhs = d - k log1p(d/lam) - log(2 pi k)/2 - (1/(12k) - 1/(360k^3) + ...)
 MVSIM_HD bool ptrs_accept(const PtrsParams& q, double lam_d, float kf, float us, float V)
 {
-    const float invalpha = 1.1239f + 1.1328f / (q.b - 3.4f);
+    const float invalpha = 1.1239f + fast_div(1.1328f, q.b - 3.4f);
     if (q.lam <= 3.0e4f) {
-        const float lhs = logf(V * invalpha / (q.a / (us * us) + q.b));
+        const float lhs = fast_log(fast_div(V * invalpha, fast_div(q.a, us * us) + q.b));
         float rhs;
         if (kf < 10.0f) {
             rhs = -q.lam + kf * logf(q.lam) - lgammaf(kf + 1.0f);
@@ -111,23 +148,33 @@ MVSIM_HD bool ptrs_accept(const PtrsParams& q, double lam_d, float kf, float us,
     return lhs <= rhs;
 }
 
-// Finishes a voxel whose first proposal (ru, rv) was not accepted by the squeeze: exact test for it, then fresh
-// proposals from the voxel's own counter (index, attempt >= 2) until one is accepted.
+// One attempt at a voxel whose first proposal (ru, rv) was not accepted by the squeeze.  Attempt 0 applies the exact test
+// to that first proposal; attempt >= 1 draws a fresh proposal from the voxel's own counter (index, attempt + 1).
+// Returns true when a variate was accepted (kf valid).
+MVSIM_HD bool ptrs_attempt(const PtrsParams& q, double lam_d, uint32_t ru, uint32_t rv, uint64_t index, PoissonKey key, uint32_t attempt, float& kf)
+{
+    if (attempt > 0) {
+        Philox4 c;
+        c.x = (uint32_t)index; c.y = (uint32_t)(index >> 32); c.z = key.stream_lo; c.w = attempt + 1;
+        const Philox4 r = philox4x32_10(c, key.k0, key.k1);
+        ru = r.x; rv = r.y;
+    }
+    float us, V;
+    const int st = ptrs_propose(q, ru, rv, kf, us, V);
+    return st == 1 || (st == 2 && ptrs_accept(q, lam_d, kf, us, V));
+}
+
+constexpr uint32_t kPtrsMaxAttempts = 64;      // unreachable in practice (acceptance ~ 0.9 per proposal)
+MVSIM_HD float ptrs_give_up(double lam_d) { return floorf((float)lam_d + 0.5f); }
+
+// Finishes a voxel by itself: attempts until one is accepted.
 MVSIM_HD float ptrs_resolve(double lam_d, uint32_t ru, uint32_t rv, uint64_t index, PoissonKey key)
 {
     const PtrsParams q = ptrs_params((float)lam_d);
-    float kf, us, V;
-    for (uint32_t attempt = 0; attempt < 64; ++attempt) {
-        if (attempt > 0) {
-            Philox4 c;
-            c.x = (uint32_t)index; c.y = (uint32_t)(index >> 32); c.z = key.stream_lo; c.w = attempt + 1;
-            const Philox4 r = philox4x32_10(c, key.k0, key.k1);
-            ru = r.x; rv = r.y;
-        }
-        const int st = ptrs_propose(q, ru, rv, kf, us, V);
-        if (st == 1 || (st == 2 && ptrs_accept(q, lam_d, kf, us, V))) return kf;
-    }
-    return floorf((float)lam_d + 0.5f);      // unreachable in practice (acceptance ~ 0.9 per proposal)
+    float kf;
+    for (uint32_t attempt = 0; attempt < kPtrsMaxAttempts; ++attempt)
+        if (ptrs_attempt(q, lam_d, ru, rv, index, key, attempt, kf)) return kf;
+    return ptrs_give_up(lam_d);
 }
 
 // Fast part of one variate.  Returns true when done (out valid); false when the voxel needs ptrs_resolve.
@@ -141,9 +188,9 @@ MVSIM_HD bool poisson_fast(double lam_d, uint32_t ru, uint32_t rv, float& out)
         // inversion by sequential search: k = min { k : u <= sum_{j<=k} e^-lam lam^j / j! }
         const float lam = (float)lam_d;
         const float u = u01f(ru);
-        float p = expf(-lam), s = p;
+        float p = fast_exp(-lam), s = p;
         int k = 0;
-        while (u > s && k < 64) { ++k; p *= lam / (float)k; s += p; }
+        while (u > s && k < 64) { ++k; p *= fast_div(lam, (float)k); s += p; }
         out = (float)k;
         return true;
     }

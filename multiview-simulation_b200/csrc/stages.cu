@@ -454,20 +454,29 @@ int k_adjust_apply(mvsim_ctx* ctx, float* inout, size_t n, const double* d_corr,
 // slice cz*inc of the input (:206, integer, bit exact).  lambda = v * mul, mul = (SNR/sqrt 5)^2
 // (S/Tools.java:76); the output is the raw count (S/Tools.java:84).
 // ---------------------------------------------------------------------------------------------
-// Warp-cooperative finish of the voxels whose first PTRS proposal was not accepted by the squeeze (about 15 % of the
+// Block-cooperative finish of the voxels whose first PTRS proposal was not accepted by the squeeze (about 20 % of the
 // voxels with lambda >= 10).  Left to each thread, a warp would run the slow code up to four times with a handful of
-// active lanes; instead the warp compacts its pending voxels into shared memory (exclusive prefix sum of the per-lane
-// counts), all lanes work through the compact list, and the owners read their results back.  The result of a voxel
-// still depends on (seed, stream, voxel index) only.
+// active lanes; compacted per warp, the slow code still ran with ~9 of 32 lanes (ncu: 35 % of the kernel's instructions).
+// So the whole CTA compacts its pending voxels into shared memory (warp scans + a scan over the warp totals), all threads
+// work through the compact list with full warps, and the owners read their results back.  (Re-compacting the survivors
+// after every attempt was measured slower: 1.39 vs 1.00 ms, the extra block barriers cost more than the idle lanes.)
+// The result of a voxel still depends on (seed, stream, voxel index) only.  Every thread of the CTA must call this.
 struct PendingItem { double lam; unsigned long long index; uint32_t ru, rv; };
-constexpr int kSamplerThreads = 256;
+#ifndef MVSIM_SAMPLER_THREADS
+#define MVSIM_SAMPLER_THREADS 64       // measured on B200 (config 3): 256 -> 1.00 ms, 128 -> 0.94, 64 -> 0.93 (fewer warps per block barrier)
+#endif
+constexpr int kSamplerThreads = MVSIM_SAMPLER_THREADS;
+struct SamplerShared {
+    PendingItem items[kSamplerThreads * 4];
+    float results[kSamplerThreads * 4];
+    int warp_total[kSamplerThreads / 32];
+};
 
-__device__ __forceinline__ void poisson_group4_warp(const double (&lam)[4], uint64_t group, PoissonKey key, float (&out)[4],
-                                                    PendingItem* warp_items, float* warp_results)
+__device__ __forceinline__ void poisson_group4_block(const double (&lam)[4], uint64_t group, PoissonKey key, float (&out)[4], SamplerShared& sh)
 {
     Philox4 r0, r1;
     const unsigned pending = poisson_group4_fast(lam, group, key, out, r0, r1);
-    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
     const int cnt = __popc(pending);
     int incl = cnt;
 #pragma unroll
@@ -475,9 +484,17 @@ __device__ __forceinline__ void poisson_group4_warp(const double (&lam)[4], uint
         const int v = __shfl_up_sync(0xffffffffu, incl, d);
         if ((int)lane >= d) incl += v;
     }
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    if (total == 0) return;                 // warp uniform
-    const int first = incl - cnt;
+    if (lane == 31) sh.warp_total[w] = incl;
+    __syncthreads();
+    int base = 0, total = 0;
+#pragma unroll
+    for (int i = 0; i < kSamplerThreads / 32; ++i) {
+        const int t = sh.warp_total[i];
+        if (i < (int)w) base += t;
+        total += t;
+    }
+    if (total == 0) return;                 // block uniform (most background blocks)
+    const int first = base + incl - cnt;
     int pos = first;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -487,19 +504,18 @@ __device__ __forceinline__ void poisson_group4_warp(const double (&lam)[4], uint
             it.index = 4ull * group + (unsigned)i;
             it.ru = i == 0 ? r0.x : i == 1 ? r0.y : i == 2 ? r0.z : r0.w;
             it.rv = i == 0 ? r1.x : i == 1 ? r1.y : i == 2 ? r1.z : r1.w;
-            warp_items[pos++] = it;
+            sh.items[pos++] = it;
         }
-    __syncwarp();
-    for (int j = (int)lane; j < total; j += 32) {
-        const PendingItem it = warp_items[j];
-        warp_results[j] = ptrs_resolve(it.lam, it.ru, it.rv, it.index, key);
+    __syncthreads();
+    for (int j = (int)threadIdx.x; j < total; j += kSamplerThreads) {
+        const PendingItem it = sh.items[j];
+        sh.results[j] = ptrs_resolve(it.lam, it.ru, it.rv, it.index, key);
     }
-    __syncwarp();
+    __syncthreads();
     pos = first;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
-        if (pending & (1u << i)) out[i] = warp_results[pos++];
-    __syncwarp();                           // the lists are reused by the caller's next group (grid-stride free here, but safe)
+        if (pending & (1u << i)) out[i] = sh.results[pos++];
 }
 
 // One thread = four consecutive output voxels (one Philox block pair, float4 traffic when the plane size
@@ -532,13 +548,11 @@ template <bool VEC4> __global__ void __launch_bounds__(kSamplerThreads) extract_
         }
     }
     if (noise) {
-        __shared__ PendingItem items[kSamplerThreads * 4];
-        __shared__ float results[kSamplerThreads * 4];
+        __shared__ SamplerShared sh;
         double lam[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) lam[k] = valid ? __dmul_rn((double)v[k], mul) : 0.0;
-        const int w = threadIdx.x >> 5;
-        poisson_group4_warp(lam, (uint64_t)g, key, v, items + w * 128, results + w * 128);
+        poisson_group4_block(lam, (uint64_t)g, key, v, sh);
     }
     if (!valid) return;
     if (VEC4) {
@@ -560,11 +574,11 @@ int k_extract(mvsim_ctx* ctx, const float* in, const int64_t dims[3], int inc, c
     const long long n_out = plane * nz;
     const int noise = snr >= 0.0f ? 1 : 0;
     const bool vec4 = plane % 4 == 0 && (reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) % 16 == 0;
-    const unsigned blocks = blocks_for((size_t)((n_out + 3) / 4), 256);
+    const unsigned blocks = blocks_for((size_t)((n_out + 3) / 4), kSamplerThreads);
     const double mul = snr_to_mul((double)snr);
     const PoissonKey key = make_poisson_key(seed, stream);
-    if (vec4) extract_kernel<true><<<blocks, 256, 0, ctx->stream>>>(in, out, plane, n_out, inc, d_corr, min_value, noise, mul, key);
-    else extract_kernel<false><<<blocks, 256, 0, ctx->stream>>>(in, out, plane, n_out, inc, d_corr, min_value, noise, mul, key);
+    if (vec4) extract_kernel<true><<<blocks, kSamplerThreads, 0, ctx->stream>>>(in, out, plane, n_out, inc, d_corr, min_value, noise, mul, key);
+    else extract_kernel<false><<<blocks, kSamplerThreads, 0, ctx->stream>>>(in, out, plane, n_out, inc, d_corr, min_value, noise, mul, key);
     MVSIM_LAUNCH_CHECK(ctx);
     return MVSIM_OK;
 }
