@@ -75,8 +75,10 @@ struct CudaLauncher {
         StageTimer t(ctx, psf_phase ? MVSIM_T_PSF : (inverse ? MVSIM_T_FFT_XINV : MVSIM_T_FFT_XFWD));
         return finish(fft_launch(inverse ? FFT_XINV : FFT_XFWD, lanes, s.n, &q, (unsigned)x_blocks(s, q.n_rows), 1, ctx->stream), "x pass");
     }
-    int launch_strided(bool inverse, const FftSize& s, const StridedParams& q, int n_tiles, int n_outer)
+    int launch_strided(bool inverse, const FftSize& s, const StridedParams& q0, int n_tiles, int n_outer)
     {
+        StridedParams q = q0;
+        strided_fill_e32(q, s.n);
         StageTimer t(ctx, psf_phase ? MVSIM_T_PSF : (inverse ? MVSIM_T_FFT_YINV : MVSIM_T_FFT_YFWD));
         const unsigned tiles = (unsigned)n_tiles;
         const unsigned gx = q.swap_grid ? (unsigned)n_outer : tiles, gy = q.swap_grid ? tiles : (unsigned)n_outer;

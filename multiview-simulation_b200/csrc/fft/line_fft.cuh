@@ -87,7 +87,9 @@ template <int A, int B, bool PK = false> MVSIM_HD void inv_second(int p, float2 
 
 // Gathers x[n1] = ext(line)[p + n1*B - left], n1 < A, from a strided line.  All index arithmetic is done
 // before the first load so the A loads of a thread are in flight together.
-template <int A, int B> MVSIM_HD void gather_line(float2 (&x)[A], const float2* __restrict__ src, long long estride, int p, int left,
+// e32 != 0: every element offset of the line (index * estride) fits 32 bits, so one 32-bit multiply + one widening
+// address add per element replaces the 64-bit multiply (the integer pipe is ~40 % of these kernels' instructions).
+template <int A, int B> MVSIM_HD void gather_line(float2 (&x)[A], const float2* __restrict__ src, long long estride, unsigned e32, int p, int left,
                                                  int n_src, int ext)
 {
     // `left` already includes the block offset of overlap-save blocks (padded index q holds source q - left)
@@ -95,15 +97,30 @@ template <int A, int B> MVSIM_HD void gather_line(float2 (&x)[A], const float2* 
         int idx[A];
         MVSIM_UNROLL
         for (int n1 = 0; n1 < A; ++n1) idx[n1] = mirror_once(p + n1 * B - left, n_src);
-        MVSIM_UNROLL
-        for (int n1 = 0; n1 < A; ++n1) x[n1] = src[idx[n1] * estride];
+        if (e32) {
+            MVSIM_UNROLL
+            for (int n1 = 0; n1 < A; ++n1) x[n1] = src[(unsigned)idx[n1] * e32];
+        } else {
+            MVSIM_UNROLL
+            for (int n1 = 0; n1 < A; ++n1) x[n1] = src[idx[n1] * estride];
+        }
     } else if (ext == EXT_ZERO) {
-        MVSIM_UNROLL
-        for (int n1 = 0; n1 < A; ++n1) {
-            const int n = p + n1 * B - left;
-            const bool ok = (unsigned)n < (unsigned)n_src;
-            const float2 v = src[(ok ? n : 0) * estride];
-            x[n1] = ok ? v : make_float2(0.f, 0.f);
+        if (e32) {
+            MVSIM_UNROLL
+            for (int n1 = 0; n1 < A; ++n1) {
+                const int n = p + n1 * B - left;
+                const bool ok = (unsigned)n < (unsigned)n_src;
+                const float2 v = src[(unsigned)(ok ? n : 0) * e32];      // clamped index + select keeps the loads batched
+                x[n1] = ok ? v : make_float2(0.f, 0.f);
+            }
+        } else {
+            MVSIM_UNROLL
+            for (int n1 = 0; n1 < A; ++n1) {
+                const int n = p + n1 * B - left;
+                const bool ok = (unsigned)n < (unsigned)n_src;
+                const float2 v = src[(ok ? n : 0) * estride];
+                x[n1] = ok ? v : make_float2(0.f, 0.f);
+            }
         }
     } else {
         MVSIM_UNROLL
@@ -129,6 +146,7 @@ struct StridedParams {
     int ext;                // EXT_MIRROR1 / EXT_ZERO / EXT_MIRROR_GENERAL (fft_defs.cuh)
     int crop0, n_out;       // inverse: store padded indices [crop0, crop0 + n_out)
     long long in_estride, in_ostride, out_estride, out_ostride;   // in float2 units
+    unsigned in_e32, out_e32;   // != 0: the element stride again, when every offset inside a line fits 32 bits (set by strided_fill_e32)
     long long in_tstride, out_tstride;  // stride between kx tiles: T for row-major [..][KXc], Z*N*T for tile-major [KT][..][..][T]
     int swap_grid;          // 0: blockIdx.x = kx tile, .y = outer; 1: blockIdx.x = outer (neighbouring CTAs share DRAM pages)
     int tile0;              // global index of this launch's tile 0 (slab decomposition: a rank owns tiles [tile0, tile0 + n))
@@ -145,6 +163,16 @@ struct StridedParams {
 };
 
 struct NoState {};
+
+// host side: enable the 32-bit element offsets of a strided pass over lines of padded length n when they cannot overflow
+inline void strided_fill_e32(StridedParams& q, int n)
+{
+    long long top = n;
+    if (q.n_src > top) top = q.n_src;
+    if ((long long)q.n_out + q.out_offset > top) top = (long long)q.n_out + q.out_offset;
+    q.in_e32 = (q.in_estride > 0 && top * q.in_estride < 0x7fffffffLL) ? (unsigned)q.in_estride : 0u;
+    q.out_e32 = (q.out_estride > 0 && top * q.out_estride < 0x7fffffffLL) ? (unsigned)q.out_estride : 0u;
+}
 
 template <int A_, int B_, int T_> struct StridedFwd : LineShape<A_, B_> {
     using S = LineShape<A_, B_>;
@@ -165,7 +193,7 @@ template <int A_, int B_, int T_> struct StridedFwd : LineShape<A_, B_> {
             if (p < B && active) {
                 float2 x[A];
                 const float2* src = q.in + tin * q.in_tstride + outer * q.in_ostride + lane;
-                gather_line<A, B>(x, src, q.in_estride, p, q.left, q.n_src, q.ext);
+                gather_line<A, B>(x, src, q.in_estride, q.in_e32, p, q.left, q.n_src, q.ext);
                 fwd_first<A, B, kPackedStrided>(p, x, sm, lane, T, q.tw);
             }
         } else {
@@ -179,9 +207,15 @@ template <int A_, int B_, int T_> struct StridedFwd : LineShape<A_, B_> {
                 } else {
                     dst = q.out + tout * q.out_tstride + outer * q.out_ostride + lane;
                 }
-                MVSIM_UNROLL
-                for (int k2 = 0; k2 < B; ++k2)
-                    dst[(p + A * k2) * q.out_estride] = make_float2(y[k2].x * q.scale, y[k2].y * q.scale);
+                if (q.out_e32) {
+                    MVSIM_UNROLL
+                    for (int k2 = 0; k2 < B; ++k2)
+                        dst[(unsigned)(p + A * k2) * q.out_e32] = make_float2(y[k2].x * q.scale, y[k2].y * q.scale);
+                } else {
+                    MVSIM_UNROLL
+                    for (int k2 = 0; k2 < B; ++k2)
+                        dst[(p + A * k2) * q.out_estride] = make_float2(y[k2].x * q.scale, y[k2].y * q.scale);
+                }
             }
         }
     }
@@ -207,8 +241,13 @@ template <int A_, int B_, int T_> struct StridedInv : LineShape<A_, B_> {
             if (p < A && active) {
                 float2 y[B];
                 const float2* src = q.in + tin * q.in_tstride + outer * q.in_ostride + lane;
-                MVSIM_UNROLL
-                for (int k2 = 0; k2 < B; ++k2) y[k2] = src[(p + A * k2) * q.in_estride];
+                if (q.in_e32) {
+                    MVSIM_UNROLL
+                    for (int k2 = 0; k2 < B; ++k2) y[k2] = src[(unsigned)(p + A * k2) * q.in_e32];
+                } else {
+                    MVSIM_UNROLL
+                    for (int k2 = 0; k2 < B; ++k2) y[k2] = src[(p + A * k2) * q.in_estride];
+                }
                 inv_first<A, B, kPackedStrided>(p, y, sm, lane, T, q.tw);
             }
         } else {
@@ -216,10 +255,18 @@ template <int A_, int B_, int T_> struct StridedInv : LineShape<A_, B_> {
                 float2 x[A];
                 inv_second<A, B, kPackedStrided>(p, x, sm, lane, T);
                 float2* dst = q.out + tout * q.out_tstride + outer * q.out_ostride + lane;
-                MVSIM_UNROLL
-                for (int n1 = 0; n1 < A; ++n1) {
-                    const int o = p + n1 * B - q.crop0;
-                    if ((unsigned)o < (unsigned)q.n_out) dst[(o + q.out_offset) * q.out_estride] = x[n1];
+                if (q.out_e32) {
+                    MVSIM_UNROLL
+                    for (int n1 = 0; n1 < A; ++n1) {
+                        const int o = p + n1 * B - q.crop0;
+                        if ((unsigned)o < (unsigned)q.n_out) dst[(unsigned)(o + q.out_offset) * q.out_e32] = x[n1];
+                    }
+                } else {
+                    MVSIM_UNROLL
+                    for (int n1 = 0; n1 < A; ++n1) {
+                        const int o = p + n1 * B - q.crop0;
+                        if ((unsigned)o < (unsigned)q.n_out) dst[(o + q.out_offset) * q.out_estride] = x[n1];
+                    }
                 }
             }
         }
@@ -246,6 +293,8 @@ struct ZFusedParams {
                             // 0..n_keep-1 and the SUM of all other cropped z in plane n_keep (enough for extractSlices + the
                             // mean of adjustImage)
     long long estride;      // z stride inside a segment (= Ny*T), also the kz stride of h
+    int estride32;          // != 0: one segment (single GPU) and every in-line offset z*estride fits 32 bits: the loaders and storers
+                            // then spend one 32-bit multiply per element instead of the segmented 64-bit address arithmetic
     long long ostride;      // ky stride (= T), same for u and h
     long long u_tstride;    // kx-tile stride of u inside a segment (= zg*Ny*T)
     long long seg_stride;   // segment stride of u (= tiles*zg*Ny*T)
@@ -337,8 +386,14 @@ template <int A_, int B_, int T_> struct ZFused : LineShape<A_, B_> {
                     MVSIM_UNROLL
                     for (int n1 = 0; n1 < A; ++n1) idx[n1] = mirror_single(p + n1 * B - q.left, q.n_src);
                 }
-                MVSIM_UNROLL
-                for (int n1 = 0; n1 < A; ++n1) x[n1] = src[zfused_plane_offset(q, idx[n1])];
+                if (q.estride32) {
+                    const unsigned e = (unsigned)q.estride32;
+                    MVSIM_UNROLL
+                    for (int n1 = 0; n1 < A; ++n1) x[n1] = src[(unsigned)idx[n1] * e];
+                } else {
+                    MVSIM_UNROLL
+                    for (int n1 = 0; n1 < A; ++n1) x[n1] = src[zfused_plane_offset(q, idx[n1])];
+                }
                 fwd_first<A, B, kPackedStrided>(p, x, sm, lane, T, q.tw);
             }
             cp_async_wait_all();
@@ -359,7 +414,18 @@ template <int A_, int B_, int T_> struct ZFused : LineShape<A_, B_> {
                 float2 x[A];
                 inv_second<A, B, kPackedStrided>(p, x, sm, lane, T);
                 float2* dst = q.u + tile * q.u_tstride + outer * q.ostride + lane;
-                if (q.keep_inc > 1) {
+                if (q.keep_inc > 1 && q.estride32) {
+                    const unsigned e = (unsigned)q.estride32;
+                    MVSIM_UNROLL
+                    for (int n1 = 0; n1 < A; ++n1) {
+                        const int o = p + n1 * B - q.crop0;
+                        if ((unsigned)o < (unsigned)q.n_src) {
+                            const unsigned kz = umulhi32((uint32_t)o, q.keep_magic);
+                            if ((int)kz * q.keep_inc == o) dst[kz * e] = x[n1];
+                            else { st.acc.x += x[n1].x; st.acc.y += x[n1].y; }
+                        }
+                    }
+                } else if (q.keep_inc > 1) {
                     MVSIM_UNROLL
                     for (int n1 = 0; n1 < A; ++n1) {
                         const int o = p + n1 * B - q.crop0;
@@ -380,10 +446,19 @@ template <int A_, int B_, int T_> struct ZFused : LineShape<A_, B_> {
                         }
                     }
                 } else {
-                    MVSIM_UNROLL
-                    for (int n1 = 0; n1 < A; ++n1) {
-                        const int o = p + n1 * B - q.crop0;
-                        if ((unsigned)o < (unsigned)q.n_src) dst[zfused_plane_offset(q, o)] = x[n1];
+                    if (q.estride32) {
+                        const unsigned e = (unsigned)q.estride32;
+                        MVSIM_UNROLL
+                        for (int n1 = 0; n1 < A; ++n1) {
+                            const int o = p + n1 * B - q.crop0;
+                            if ((unsigned)o < (unsigned)q.n_src) dst[(unsigned)o * e] = x[n1];
+                        }
+                    } else {
+                        MVSIM_UNROLL
+                        for (int n1 = 0; n1 < A; ++n1) {
+                            const int o = p + n1 * B - q.crop0;
+                            if ((unsigned)o < (unsigned)q.n_src) dst[zfused_plane_offset(q, o)] = x[n1];
+                        }
                     }
                 }
             }

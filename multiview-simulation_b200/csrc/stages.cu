@@ -7,6 +7,8 @@
 //   extract    S/SimulateMultiViewDataset.java:195-231 + Poisson S/Tools.java:73-86
 // All of them are HBM-bound; threads map to x (the contiguous axis) so every warp access is a
 // full 128-byte line (float4 where the row length allows).
+#include <type_traits>
+
 #include "ctx.h"
 #include "sampler.cuh"
 
@@ -156,7 +158,9 @@ template <int VEC> __device__ __forceinline__ void vload(float (&d)[VEC], const 
     }
 }
 
-template <int VEC, int U> __global__ void __launch_bounds__(128) rotate_attenuate_kernel(const float* __restrict__ in, float* __restrict__ out,
+// IDX32: the volume has < 2^31 voxels (every volume an ImgLib2 ArrayImg can hold), element offsets are 32-bit (wrapping unsigned
+// arithmetic: offsets of taps that are masked off may wrap, the ones that are dereferenced are exact)
+template <int VEC, int U, bool IDX32> __global__ void __launch_bounds__(128) rotate_attenuate_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                                                         const RowTaps* __restrict__ tab, int X, int Y, int Z,
                                                                                         double delta, int steps)
 {
@@ -165,9 +169,10 @@ template <int VEC, int U> __global__ void __launch_bounds__(128) rotate_attenuat
     const long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= (long long)XV * Z) return;
     const int x0 = (int)(col % XV) * VEC, z = (int)(col / XV);
-    const long long sy = X, sz = (long long)X * Y;
+    using Off = typename std::conditional<IDX32, unsigned, long long>::type;
+    const Off sy = (Off)X, sz = (Off)X * (Off)Y;
     const RowTaps* trow = tab + (long long)Y * z;
-    float* o = out + x0 + sz * z;
+    const Off obase = (Off)x0 + sz * (Off)z;
     double n[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) n[i] = 1.0;
@@ -182,11 +187,11 @@ template <int VEC, int U> __global__ void __launch_bounds__(128) rotate_attenuat
             const int iy = tp[j].iy, iz = tp[j].iz;
             const bool y0 = (unsigned)iy < (unsigned)Y, y1 = (unsigned)(iy + 1) < (unsigned)Y;
             const bool z0 = (unsigned)iz < (unsigned)Z, z1 = (unsigned)(iz + 1) < (unsigned)Z;
-            const float* r = in + x0 + sy * iy + sz * iz;
-            vload<VEC>(t00[j], r, y0 && z0);
-            vload<VEC>(t10[j], r + sy, y1 && z0);
-            vload<VEC>(t11[j], r + sy + sz, y1 && z1);
-            vload<VEC>(t01[j], r + sz, y0 && z1);
+            const Off r = (Off)x0 + sy * (Off)iy + sz * (Off)iz;
+            vload<VEC>(t00[j], in + r, y0 && z0);
+            vload<VEC>(t10[j], in + (Off)(r + sy), y1 && z0);
+            vload<VEC>(t11[j], in + (Off)(r + sy + sz), y1 && z1);
+            vload<VEC>(t01[j], in + (Off)(r + sz), y0 && z1);
         }
 #pragma unroll
         for (int j = 0; j < U; ++j) {
@@ -200,19 +205,19 @@ template <int VEC, int U> __global__ void __launch_bounds__(128) rotate_attenuat
                 n[i] = fmax(__dsub_rn(n[i], phi), 0.0);
                 res[i] = (float)__dmul_rn(dv, n[i]);
             }
-            *reinterpret_cast<V*>(o + sy * (y - j)) = *reinterpret_cast<V*>(res);
+            *reinterpret_cast<V*>(out + (Off)(obase + sy * (Off)(y - j))) = *reinterpret_cast<V*>(res);
         }
     }
     for (; s < steps; ++s, --y) {
         const RowTaps t = trow[y];
         const bool y0 = (unsigned)t.iy < (unsigned)Y, y1 = (unsigned)(t.iy + 1) < (unsigned)Y;
         const bool z0 = (unsigned)t.iz < (unsigned)Z, z1 = (unsigned)(t.iz + 1) < (unsigned)Z;
-        const float* r = in + x0 + sy * t.iy + sz * t.iz;
+        const Off r = (Off)x0 + sy * (Off)t.iy + sz * (Off)t.iz;
         float a00[VEC], a10[VEC], a11[VEC], a01[VEC], res[VEC];
-        vload<VEC>(a00, r, y0 && z0);
-        vload<VEC>(a10, r + sy, y1 && z0);
-        vload<VEC>(a11, r + sy + sz, y1 && z1);
-        vload<VEC>(a01, r + sz, y0 && z1);
+        vload<VEC>(a00, in + r, y0 && z0);
+        vload<VEC>(a10, in + (Off)(r + sy), y1 && z0);
+        vload<VEC>(a11, in + (Off)(r + sy + sz), y1 && z1);
+        vload<VEC>(a01, in + (Off)(r + sz), y0 && z1);
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
             const float v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a00[i], t.w00), __fmul_rn(a10[i], t.w10)), __fmul_rn(a11[i], t.w11)),
@@ -222,12 +227,12 @@ template <int VEC, int U> __global__ void __launch_bounds__(128) rotate_attenuat
             n[i] = fmax(__dsub_rn(n[i], phi), 0.0);
             res[i] = (float)__dmul_rn(dv, n[i]);
         }
-        *reinterpret_cast<V*>(o + sy * y) = *reinterpret_cast<V*>(res);
+        *reinterpret_cast<V*>(out + (Off)(obase + sy * (Off)y)) = *reinterpret_cast<V*>(res);
     }
     float zero[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) zero[i] = 0.f;
-    for (; y >= 0; --y) *reinterpret_cast<V*>(o + sy * y) = *reinterpret_cast<V*>(zero);
+    for (; y >= 0; --y) *reinterpret_cast<V*>(out + (Off)(obase + sy * (Off)y)) = *reinterpret_cast<V*>(zero);
 }
 
 // returns MVSIM_EUNSUPPORTED when the fused path does not apply (caller falls back to the two kernels)
@@ -246,15 +251,17 @@ int k_rotate_attenuate(mvsim_ctx* ctx, const float* in, float* out, const int64_
     const bool aligned = (reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) % 16 == 0;
     // the march along y is sequential per column, so the grid is small (X*Z/VEC threads): pick the widest
     // vector whose single wave still fits the machine (config 3: 131072 threads x float4, 2 rows in flight)
+    const bool idx32 = (double)X * Y * Z < 2147483648.0;
     if (X % 4 == 0 && aligned) {
         const size_t cols = (size_t)(X / 4) * Z;
-        rotate_attenuate_kernel<4, 2><<<blocks_for(cols, 128), 128, 0, ctx->stream>>>(in, out, tab, X, Y, Z, delta, steps);
+        if (idx32) rotate_attenuate_kernel<4, 2, true><<<blocks_for(cols, 128), 128, 0, ctx->stream>>>(in, out, tab, X, Y, Z, delta, steps);
+        else rotate_attenuate_kernel<4, 2, false><<<blocks_for(cols, 128), 128, 0, ctx->stream>>>(in, out, tab, X, Y, Z, delta, steps);
     } else if (X % 2 == 0 && aligned) {
         const size_t cols = (size_t)(X / 2) * Z;
-        rotate_attenuate_kernel<2, 4><<<blocks_for(cols, 128), 128, 0, ctx->stream>>>(in, out, tab, X, Y, Z, delta, steps);
+        rotate_attenuate_kernel<2, 4, false><<<blocks_for(cols, 128), 128, 0, ctx->stream>>>(in, out, tab, X, Y, Z, delta, steps);
     } else {
         const size_t cols = (size_t)X * Z;
-        rotate_attenuate_kernel<1, 4><<<blocks_for(cols, 128), 128, 0, ctx->stream>>>(in, out, tab, X, Y, Z, delta, steps);
+        rotate_attenuate_kernel<1, 4, false><<<blocks_for(cols, 128), 128, 0, ctx->stream>>>(in, out, tab, X, Y, Z, delta, steps);
     }
     ctx->launches++;
     cudaError_t e = cudaGetLastError();

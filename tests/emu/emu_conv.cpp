@@ -53,8 +53,10 @@ struct EmuLauncher {
         }
         return 5;
     }
-    int launch_strided(bool inverse, const FftSize& s, const StridedParams& q, int tiles, int n_outer)
+    int launch_strided(bool inverse, const FftSize& s, const StridedParams& q0, int tiles, int n_outer)
     {
+        StridedParams q = q0;
+        strided_fill_e32(q, s.n);
         const int gx = q.swap_grid ? n_outer : tiles, gy = q.swap_grid ? tiles : n_outer;
         switch (s.n) {
 #define MVSIM_X(n_, a_, b_) case n_: if (inverse) emulate<StridedInv<a_, b_, T>>(q, gx, gy); else emulate<StridedFwd<a_, b_, T>>(q, gx, gy); return 0;
