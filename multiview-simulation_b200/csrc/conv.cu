@@ -90,7 +90,8 @@ struct CudaLauncher {
         const unsigned tiles = (unsigned)n_tiles;
         ZFusedParams q = q0;
         if (q.h_mode) {
-            q.use_tma = make_h_tensor_map(q.p2, lanes, n_tiles, q.k_src, n_outer, q.h_tmap) ? 1 : 0;    // PSF tile [KZ rows] through the TMA unit
+            // PSF tile [KZ rows] through the TMA unit into its own shared-memory area
+            q.use_tma = (zfused_otf_tma_fits(s.a, s.b, lanes, q.k_src) && make_h_tensor_map(q.p2, lanes, n_tiles, q.k_src, n_outer, q.h_tmap)) ? 1 : 0;
             return finish(fft_launch(FFT_ZFUSED_OTF, lanes, s.n, &q, (unsigned)n_outer, tiles, ctx->stream), "fused z pass (PSF spectrum on the fly)");
         }
         q.use_tma = make_h_tensor_map(q.h, lanes, n_tiles, s.n, n_outer, q.h_tmap) ? 1 : 0;

@@ -1,4 +1,6 @@
 // Instantiates the line-FFT kernels (line_fft.cuh) for one group of sizes: -DMVSIM_GROUP=0..4.
+#include <type_traits>
+
 #include "fft_launch.h"
 
 #if !defined(MVSIM_GROUP) || !defined(MVSIM_LANES)
@@ -29,15 +31,26 @@ template <class K> __global__ void __launch_bounds__(K::THREADS, min_blocks<K>()
     if constexpr (K::NPH > 7) { __syncthreads(); K::template phase<7>(q, blockIdx.x, blockIdx.y, threadIdx.x, sm, st); }
 }
 
+// dynamic shared memory of a launch: K::SMEM_BYTES, or K::smem_bytes(params) where the kernel sizes an area at run time
+template <class K, class = void> struct SmemOf {
+    static int bytes(const typename K::Params&) { return K::SMEM_BYTES; }
+    static int max_bytes() { return K::SMEM_BYTES; }
+};
+template <class K> struct SmemOf<K, std::void_t<decltype(&K::smem_bytes_max)>> {
+    static int bytes(const typename K::Params& q) { return K::smem_bytes(q); }
+    static int max_bytes() { return K::smem_bytes_max(); }
+};
+
 template <class K> static int launch(const void* params, unsigned gx, unsigned gy, cudaStream_t s)
 {
     static bool configured = false;     // per instantiation; idempotent, so a race only repeats the call
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(fft_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(fft_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemOf<K>::max_bytes());
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
-    fft_kernel<K><<<dim3(gx, gy), K::THREADS, K::SMEM_BYTES, s>>>(*static_cast<const typename K::Params*>(params));
+    const typename K::Params& q = *static_cast<const typename K::Params*>(params);
+    fft_kernel<K><<<dim3(gx, gy), K::THREADS, SmemOf<K>::bytes(q), s>>>(q);
     return (int)cudaGetLastError();
 }
 

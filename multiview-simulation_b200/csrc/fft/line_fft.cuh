@@ -324,7 +324,7 @@ MVSIM_HD long long zfused_plane_offset(const ZFusedParams& q, int z)
     return seg * q.seg_stride + (z - seg * q.zg) * q.estride;
 }
 
-template <int B> struct RegState { float2 y[B]; float2 acc; };
+template <int B> struct RegState { float2 y[B]; };
 
 template <int A_, int B_, int T_> struct ZFused : LineShape<A_, B_> {
     using S = LineShape<A_, B_>;
@@ -409,32 +409,16 @@ template <int A_, int B_, int T_> struct ZFused : LineShape<A_, B_> {
         } else if (PH == 2) {
             if (p < A && active) inv_first<A, B, kPackedStrided>(p, st.y, sm, lane, T, q.tw);
         } else if (PH == 3) {
-            st.acc = make_float2(0.f, 0.f);
             if (p < B && active) {
                 float2 x[A];
                 inv_second<A, B, kPackedStrided>(p, x, sm, lane, T);
                 float2* dst = q.u + tile * q.u_tstride + outer * q.ostride + lane;
-                if (q.keep_inc > 1 && q.estride32) {
-                    const unsigned e = (unsigned)q.estride32;
+                if (q.keep_inc > 1) {
+                    // whole-view call: the line goes to the (now free) H area in natural order; the next phase picks the kept
+                    // planes and sums the rest with a fixed trip count per thread (the per-element keep test in registers cost
+                    // 20 instructions per output: a sixth of the kernel)
                     MVSIM_UNROLL
-                    for (int n1 = 0; n1 < A; ++n1) {
-                        const int o = p + n1 * B - q.crop0;
-                        if ((unsigned)o < (unsigned)q.n_src) {
-                            const unsigned kz = umulhi32((uint32_t)o, q.keep_magic);
-                            if ((int)kz * q.keep_inc == o) dst[kz * e] = x[n1];
-                            else { st.acc.x += x[n1].x; st.acc.y += x[n1].y; }
-                        }
-                    }
-                } else if (q.keep_inc > 1) {
-                    MVSIM_UNROLL
-                    for (int n1 = 0; n1 < A; ++n1) {
-                        const int o = p + n1 * B - q.crop0;
-                        if ((unsigned)o < (unsigned)q.n_src) {
-                            const int kz = (int)umulhi32((uint32_t)o, q.keep_magic);
-                            if (kz * q.keep_inc == o) dst[kz * q.estride] = x[n1];
-                            else { st.acc.x += x[n1].x; st.acc.y += x[n1].y; }
-                        }
-                    }
+                    for (int n1 = 0; n1 < A; ++n1) smh[(p + n1 * B) * T + lane] = x[n1];
                 } else if (q.n_peers > 1) {
                     const long long tile_off = (long long)(q.tile0 + tile) * q.u_tstride + outer * q.ostride + lane;
                     MVSIM_UNROLL
@@ -463,19 +447,63 @@ template <int A_, int B_, int T_> struct ZFused : LineShape<A_, B_> {
                 }
             }
         } else if (PH == 4) {
-            // (barrier before: every thread is done reading the exchange area) per-line reduction of the dropped planes
-            if (q.keep_inc > 1 && p < B) sm[p * T + lane] = st.acc;
+            // (barrier before: the line is complete in the H area and nobody reads the exchange area any more)
+            // thread (p, lane): sum of the cropped rows p, p+P, ... minus the kept ones among kz = p, p+P, ..., which it stores
+            if (q.keep_inc > 1) {
+                float2 acc = make_float2(0.f, 0.f);
+                if (active) {
+                    const float2* row = smh + q.crop0 * T + lane;
+                    for (int j = p; j < q.n_src; j += S::P) { const float2 v = row[j * T]; acc.x += v.x; acc.y += v.y; }
+                    float2* dst = q.u + tile * q.u_tstride + outer * q.ostride + lane;
+                    const int kstep = q.keep_inc * T;
+                    if (q.estride32) {
+                        const unsigned e = (unsigned)q.estride32;
+                        for (int kz = p; kz < q.n_keep; kz += S::P) {
+                            const float2 v = row[kz * kstep];
+                            dst[(unsigned)kz * e] = v;
+                            acc.x -= v.x; acc.y -= v.y;
+                        }
+                    } else {
+                        for (int kz = p; kz < q.n_keep; kz += S::P) {
+                            const float2 v = row[kz * kstep];
+                            dst[kz * q.estride] = v;
+                            acc.x -= v.x; acc.y -= v.y;
+                        }
+                    }
+                }
+                sm[p * T + lane] = acc;
+            }
         } else {
             if (q.keep_inc > 1 && p == 0 && active) {
                 float2 s = make_float2(0.f, 0.f);
-                for (int j = 0; j < B; ++j) { s.x += sm[j * T + lane].x; s.y += sm[j * T + lane].y; }
+                for (int j = 0; j < S::P; ++j) { s.x += sm[j * T + lane].x; s.y += sm[j * T + lane].y; }
                 q.u[tile * q.u_tstride + outer * q.ostride + lane + q.n_keep * q.estride] = s;
             }
         }
     }
 };
 
-// Fused z pass with the PSF spectrum computed on the fly (h_mode 1): two PSF phases in front of ZFused's six.
+// Shared memory of ZFusedOTF (host side needs it without the template): exchange area + H area + 128 B for the mbarrier,
+// plus, on the TMA path, the PSF tile.
+constexpr int kSmemLimit = 227 * 1024;      // per CTA, sm_100
+constexpr int zfused_otf_smem_base(int a, int b, int t)
+{
+    return ((a * (b | 1) * t + 15) / 16 * 16 + (a * b + kTmaBoxRows - 1) / kTmaBoxRows * kTmaBoxRows * t + 16) * (int)sizeof(float2);
+}
+constexpr int zfused_otf_psf_tile_bytes(int k_src, int t) { return (k_src + kTmaBoxRows - 1) / kTmaBoxRows * kTmaBoxRows * t * (int)sizeof(float2); }
+// the TMA-fed PSF tile is used when it fits and does not cost a resident CTA (228 KB per SM, 1 KB reserved per CTA)
+inline bool zfused_otf_tma_fits(int a, int b, int t, int k_src)
+{
+    const int base = zfused_otf_smem_base(a, b, t), with = base + zfused_otf_psf_tile_bytes(k_src, t);
+    if (with > kSmemLimit) return false;
+    const int c0 = 233472 / (base + 1024), c1 = 233472 / (with + 1024);
+    return c1 >= (c0 < 4 ? c0 : 4);
+}
+
+// Fused z pass with the PSF spectrum computed on the fly (h_mode 1).  Phase order: the IMAGE line is transformed first and its
+// spectrum parked in the H area, then the PSF line (P2, zero extended) is transformed and multiplied in, then ZFused's inverse
+// half.  The PSF tile is requested from the TMA unit by one thread at CTA start and lands in its own small area while the
+// image phases run, so only one DRAM round trip (the image gather) is exposed per CTA instead of two.
 template <int A_, int B_, int T_> struct ZFusedOTF : ZFused<A_, B_, T_> {
     using Z = ZFused<A_, B_, T_>;
     using S = LineShape<A_, B_>;
@@ -483,11 +511,19 @@ template <int A_, int B_, int T_> struct ZFusedOTF : ZFused<A_, B_, T_> {
     static constexpr int NPH = 8;
     using Params = ZFusedParams;
     using State = typename Z::State;
+    // [exchange][H area: parked image spectrum][mbarrier, padded to 128 B][PSF tile: ceil(KZ/128) TMA boxes of 128 rows x T]
+    static constexpr int BAR_ELEMS = Z::EXCH_ELEMS + Z::H_ROWS * T;
+    static constexpr int PSF_ELEMS0 = BAR_ELEMS + 16;
+    static constexpr int SMEM_BYTES = PSF_ELEMS0 * (int)sizeof(float2);         // without the PSF tile (per-thread loads)
+    static int smem_bytes(const Params& q) { return SMEM_BYTES + (q.use_tma ? zfused_otf_psf_tile_bytes(q.k_src, T) : 0); }
+    static int smem_bytes_max() { const int m = SMEM_BYTES + Z::H_ROWS * T * (int)sizeof(float2); return m < kSmemLimit ? m : kSmemLimit; }
+    static_assert(SMEM_BYTES == zfused_otf_smem_base(A_, B_, T_), "host-side shared memory formula out of sync");
 
     template <int PH> static MVSIM_HD void phase(const Params& q, int bx, int by, int tid, float2* sm, State& st)
     {
-        if (PH >= 2) {
-            Z::template phase<(PH >= 2 ? PH - 2 : 0)>(q, bx, by, tid, sm, st);
+        if (PH >= 3) {
+            // multiply (the registers hold the PSF line's spectrum, the H area the image line's), inverse half, stores
+            Z::template phase<(PH >= 3 ? PH - 2 : 1)>(q, bx, by, tid, sm, st);
             return;
         }
         const int lane = tid % T, p = tid / T;
@@ -496,25 +532,36 @@ template <int A_, int B_, int T_> struct ZFusedOTF : ZFused<A_, B_, T_> {
         float2* smh = sm + Z::EXCH_ELEMS;
         if (PH == 0) {
 #ifdef __CUDA_ARCH__
-            if (q.use_tma) {
-                // TMA-fed PSF tile: one thread programs ceil(KZ/128) box loads (128 kz rows x 64 bytes each, rows beyond KZ are
-                // zero filled by the unit) into the H area, everybody waits on the mbarrier and picks its samples from shared
-                // memory -- no per-thread address arithmetic, no loads for the zero extension.
-                uint64_t* bar = reinterpret_cast<uint64_t*>(smh + Z::H_ROWS * T);
+            if (q.use_tma && tid == 0) {
+                // one thread programs ceil(KZ/128) box loads (128 kz rows x 64 bytes each; rows beyond KZ are zero filled by the
+                // unit); the tile is first read two barriers later
+                uint64_t* bar = reinterpret_cast<uint64_t*>(sm + BAR_ELEMS);
                 const int nbox = (q.k_src + kTmaBoxRows - 1) / kTmaBoxRows;
-                if (tid == 0) {
-                    mbar_init(bar, 1);
-                    mbar_expect_tx(bar, (unsigned)(nbox * kTmaBoxRows * T * sizeof(float2)));
-                    for (int b = 0; b < nbox; ++b) tma_load_4d(smh + b * kTmaBoxRows * T, q.h_tmap, 0, outer, b * kTmaBoxRows, tile, bar);
-                }
-                __syncthreads();            // the init must be visible before anybody polls the barrier
-                mbar_wait(bar, 0);
+                mbar_init(bar, 1);
+                mbar_expect_tx(bar, (unsigned)(nbox * kTmaBoxRows * T * sizeof(float2)));
+                for (int b = 0; b < nbox; ++b) tma_load_4d(sm + PSF_ELEMS0 + b * kTmaBoxRows * T, q.h_tmap, 0, outer, b * kTmaBoxRows, tile, bar);
+            }
+#endif
+            Z::template phase<0>(q, bx, by, tid, sm, st);       // image line: gather (mirror extension) + first half
+        } else if (PH == 1) {
+            if (p < A && active) {
+                float2 y[B];
+                fwd_second<A, B, kPackedStrided>(p, y, sm, lane, T);
+                MVSIM_UNROLL
+                for (int k2 = 0; k2 < B; ++k2) smh[(p + A * k2) * T + lane] = y[k2];     // read back by the same thread only
+            }
+        } else {
+#ifdef __CUDA_ARCH__
+            if (q.use_tma) {
+                mbar_wait(reinterpret_cast<uint64_t*>(sm + BAR_ELEMS), 0);      // (two barriers since the init)
                 if (p < B && active) {
+                    const float2* tilep = sm + PSF_ELEMS0;
+                    const int rows = (q.k_src + kTmaBoxRows - 1) / kTmaBoxRows * kTmaBoxRows;
                     float2 x[A];
                     MVSIM_UNROLL
                     for (int n1 = 0; n1 < A; ++n1) {
                         const int n = p + n1 * B;
-                        x[n1] = n < nbox * kTmaBoxRows ? smh[n * T + lane] : make_float2(0.f, 0.f);
+                        x[n1] = n < rows ? tilep[n * T + lane] : make_float2(0.f, 0.f);
                     }
                     fwd_first<A, B, kPackedStrided>(p, x, sm, lane, T, q.tw);
                 }
@@ -531,13 +578,6 @@ template <int A_, int B_, int T_> struct ZFusedOTF : ZFused<A_, B_, T_> {
                     x[n1] = ok ? v : make_float2(0.f, 0.f);              // (predicated loads measured slower: 3.39 vs 3.21 ms)
                 }
                 fwd_first<A, B, kPackedStrided>(p, x, sm, lane, T, q.tw);
-            }
-        } else {
-            if (p < A && active) {
-                float2 h[B];
-                fwd_second<A, B, kPackedStrided>(p, h, sm, lane, T);
-                MVSIM_UNROLL
-                for (int k2 = 0; k2 < B; ++k2) smh[(p + A * k2) * T + lane] = h[k2];     // read back by the same thread only
             }
         }
     }
