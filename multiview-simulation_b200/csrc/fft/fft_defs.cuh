@@ -8,9 +8,11 @@
 #include <cuda_runtime.h>
 #define MVSIM_HD __host__ __device__ __forceinline__
 #define MVSIM_UNROLL _Pragma("unroll")
+#define MVSIM_UNROLL4 _Pragma("unroll 4")
 #else
 #define MVSIM_HD inline
 #define MVSIM_UNROLL
+#define MVSIM_UNROLL4
 #ifndef MVSIM_HOST_FLOAT2
 #define MVSIM_HOST_FLOAT2
 struct float2 { float x, y; };

@@ -33,6 +33,20 @@ namespace mvsim {
 template <int N, int DIR, bool PK> struct RegSel { static MVSIM_HD void run(float2 (&x)[N]) { RegFFT<N, DIR>::run(x); } };
 template <int N, int DIR> struct RegSel<N, DIR, true> { static MVSIM_HD void run(float2 (&x)[N]) { RegFFTP<N, DIR>::run(x); } };
 constexpr bool kPackedStrided = MVSIM_PACKED_FFT != 0;
+// forward transform of x[0..K) with x[K..N) == 0 (not read), K = RegFFTPZ<N>::K: generated with the zero terms removed
+template <int N, bool PK> struct RegSelZ {
+    static constexpr int K = RegFFTPZ<N>::K;
+    static MVSIM_HD void run(float2 (&x)[N])
+    {
+        MVSIM_UNROLL
+        for (int i = K; i < N; ++i) x[i] = make_float2(0.f, 0.f);
+        RegFFT<N, -1>::run(x);
+    }
+};
+template <int N> struct RegSelZ<N, true> {
+    static constexpr int K = RegFFTPZ<N>::K;
+    static MVSIM_HD void run(float2 (&x)[N]) { RegFFTPZ<N>::run(x); }
+};
 
 template <int A_, int B_> struct LineShape {
     static constexpr int A = A_, B = B_;
@@ -49,6 +63,17 @@ template <int A, int B, bool PK = false> MVSIM_HD void fwd_first(int p, float2 (
 {
     constexpr int BP = B | 1;
     RegSel<A, -1, PK>::run(x);
+    MVSIM_UNROLL
+    for (int k1 = 0; k1 < A; ++k1) {
+        const float2 v = k1 == 0 ? x[0] : cmul(x[k1], tw[k1 * p]);
+        sm[base + (k1 * BP + p) * ls] = v;
+    }
+}
+// the same for a zero-extended line of which only x[0..K) carries data, K = RegSelZ<A, PK>::K
+template <int A, int B, bool PK = false> MVSIM_HD void fwd_first_zext(int p, float2 (&x)[A], float2* sm, int base, int ls, const float2* __restrict__ tw)
+{
+    constexpr int BP = B | 1;
+    RegSelZ<A, PK>::run(x);
     MVSIM_UNROLL
     for (int k1 = 0; k1 < A; ++k1) {
         const float2 v = k1 == 0 ? x[0] : cmul(x[k1], tw[k1 * p]);
@@ -453,6 +478,7 @@ template <int A_, int B_, int T_> struct ZFused : LineShape<A_, B_> {
                 float2 acc = make_float2(0.f, 0.f);
                 if (active) {
                     const float2* row = smh + q.crop0 * T + lane;
+                    MVSIM_UNROLL4
                     for (int j = p; j < q.n_src; j += S::P) { const float2 v = row[j * T]; acc.x += v.x; acc.y += v.y; }
                     float2* dst = q.u + tile * q.u_tstride + outer * q.ostride + lane;
                     const int kstep = q.keep_inc * T;
@@ -558,26 +584,49 @@ template <int A_, int B_, int T_> struct ZFusedOTF : ZFused<A_, B_, T_> {
                     const float2* tilep = sm + PSF_ELEMS0;
                     const int rows = (q.k_src + kTmaBoxRows - 1) / kTmaBoxRows * kTmaBoxRows;
                     float2 x[A];
-                    MVSIM_UNROLL
-                    for (int n1 = 0; n1 < A; ++n1) {
-                        const int n = p + n1 * B;
-                        x[n1] = n < rows ? tilep[n * T + lane] : make_float2(0.f, 0.f);
+                    constexpr int K = RegSelZ<A, kPackedStrided>::K;
+                    if (q.k_src <= K * B) {
+                        // the usual case (PSF no longer than a fifth of the padded line): only x[0..K) carry data
+                        MVSIM_UNROLL
+                        for (int n1 = 0; n1 < K; ++n1) {
+                            const int n = p + n1 * B;
+                            x[n1] = n < rows ? tilep[n * T + lane] : make_float2(0.f, 0.f);
+                        }
+                        fwd_first_zext<A, B, kPackedStrided>(p, x, sm, lane, T, q.tw);
+                    } else {
+                        MVSIM_UNROLL
+                        for (int n1 = 0; n1 < A; ++n1) {
+                            const int n = p + n1 * B;
+                            x[n1] = n < rows ? tilep[n * T + lane] : make_float2(0.f, 0.f);
+                        }
+                        fwd_first<A, B, kPackedStrided>(p, x, sm, lane, T, q.tw);
                     }
-                    fwd_first<A, B, kPackedStrided>(p, x, sm, lane, T, q.tw);
                 }
             } else
 #endif
             if (p < B && active) {
                 float2 x[A];
                 const float2* __restrict__ src = q.p2 + tile * q.p2_tstride + outer * q.ostride + lane;
-                MVSIM_UNROLL
-                for (int n1 = 0; n1 < A; ++n1) {
-                    const int n = p + n1 * B;
-                    const bool ok = n < q.k_src;
-                    const float2 v = src[(ok ? n : 0) * q.estride];      // clamped index + select keeps the loads batched
-                    x[n1] = ok ? v : make_float2(0.f, 0.f);              // (predicated loads measured slower: 3.39 vs 3.21 ms)
+                constexpr int K = RegSelZ<A, kPackedStrided>::K;
+                if (q.k_src <= K * B) {
+                    MVSIM_UNROLL
+                    for (int n1 = 0; n1 < K; ++n1) {
+                        const int n = p + n1 * B;
+                        const bool ok = n < q.k_src;
+                        const float2 v = src[(ok ? n : 0) * q.estride];
+                        x[n1] = ok ? v : make_float2(0.f, 0.f);
+                    }
+                    fwd_first_zext<A, B, kPackedStrided>(p, x, sm, lane, T, q.tw);
+                } else {
+                    MVSIM_UNROLL
+                    for (int n1 = 0; n1 < A; ++n1) {
+                        const int n = p + n1 * B;
+                        const bool ok = n < q.k_src;
+                        const float2 v = src[(ok ? n : 0) * q.estride];      // clamped index + select keeps the loads batched
+                        x[n1] = ok ? v : make_float2(0.f, 0.f);              // (predicated loads measured slower: 3.39 vs 3.21 ms)
+                    }
+                    fwd_first<A, B, kPackedStrided>(p, x, sm, lane, T, q.tw);
                 }
-                fwd_first<A, B, kPackedStrided>(p, x, sm, lane, T, q.tw);
             }
         }
     }

@@ -6,6 +6,8 @@
 #define MVSIM_PACKED_FFT 1
 #include "fft/conv_driver.h"
 
+#include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -178,4 +180,37 @@ extern "C" int emu_convolve(const float* img, const int64_t dims[3], const float
     }
     if (sum_out) *sum_out = total;
     return 0;
+}
+
+// Pruned forward sub-transforms (RegFFTPZ: inputs x[K..N) known to be zero) against the full ones, every generated size.
+// Returns the largest |difference| relative to the largest output magnitude.
+template <int N> static double check_pruned_one()
+{
+    float2 a[N], b[N];
+    unsigned s = 12345u + N;
+    for (int i = 0; i < N; ++i) {
+        s = s * 1664525u + 1013904223u; const float re = (float)(s >> 8) / 16777216.f - 0.5f;
+        s = s * 1664525u + 1013904223u; const float im = (float)(s >> 8) / 16777216.f - 0.5f;
+        const bool live = i < RegFFTPZ<N>::K;
+        a[i] = make_float2(live ? re : 0.f, live ? im : 0.f);
+        b[i] = live ? a[i] : make_float2(777.f, -777.f);        // must not be read
+    }
+    RegFFTP<N, -1>::run(a);
+    RegFFTPZ<N>::run(b);
+    double err = 0, mag = 0;
+    for (int i = 0; i < N; ++i) {
+        err = std::max(err, (double)std::max(std::fabs(a[i].x - b[i].x), std::fabs(a[i].y - b[i].y)));
+        mag = std::max(mag, (double)std::max(std::fabs(a[i].x), std::fabs(a[i].y)));
+    }
+    return err / mag;
+}
+
+extern "C" double emu_check_pruned_ffts()
+{
+    double e = 0;
+#define MVSIM_CHK(n) e = std::max(e, check_pruned_one<n>());
+    MVSIM_CHK(2) MVSIM_CHK(3) MVSIM_CHK(4) MVSIM_CHK(5) MVSIM_CHK(6) MVSIM_CHK(8) MVSIM_CHK(9) MVSIM_CHK(10) MVSIM_CHK(12) MVSIM_CHK(15)
+    MVSIM_CHK(16) MVSIM_CHK(18) MVSIM_CHK(20) MVSIM_CHK(24) MVSIM_CHK(25) MVSIM_CHK(27) MVSIM_CHK(30) MVSIM_CHK(32) MVSIM_CHK(36) MVSIM_CHK(40)
+#undef MVSIM_CHK
+    return e;
 }

@@ -128,3 +128,19 @@ def test_slab_decomposed_convolution_with_host_all_to_all(emu, oracle, world, sh
     # peer-to-peer variant: no exchange pass, the y and z passes store into the owners' buffers
     p2p, _ = _run(emu, vol, psf, world=world, max_line=max_line, p2p=1)
     assert np.array_equal(p2p, one)
+
+
+def test_pruned_sub_transforms_match_the_full_ones(emu):
+    """RegFFTPZ<N> (forward transform of a zero-extended line: inputs x[K..N) are never read) for every generated size."""
+    emu.emu_check_pruned_ffts.restype = C.c_double
+    assert emu.emu_check_pruned_ffts() < 2e-6
+
+
+def test_zero_extended_psf_line_takes_the_pruned_path(emu, oracle):
+    """PSF no longer than a fifth of the padded z line: the fused z pass transforms it with the pruned sub-transform."""
+    rng = np.random.default_rng(5)
+    vol = rng.random((26, 9, 10), dtype=np.float32)          # z = 26, kz = 5 -> 30 = 5 x 6 points, K * B = 6 >= 5
+    psf = rng.random((5, 3, 4), dtype=np.float32)
+    ref = oracle.convolve(vol, psf, "direct")
+    out, _ = _run(emu, vol, psf)
+    assert rel_err(out, ref) < 5e-6

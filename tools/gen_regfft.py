@@ -195,6 +195,69 @@ class GenPacked(Gen):
         return self.emit(f"fma2({self.swap(a)}, {self.pair(-sn, sn)}, mul2({a}, {self.pair(c, c)}))")
 
 
+class GenPackedZ(GenPacked):
+    """GenPacked with zero propagation: a value that is known to be zero is None and emits nothing.  Used for the forward
+    transform of a zero-extended line (the PSF along z): only the first K inputs of the sub-transform carry data."""
+
+    def neg(self, a):
+        return self.emit(f"mul2({a}, {self.pair(-1.0, -1.0)})")
+
+    def add(self, a, b):
+        if a is None:
+            return b
+        if b is None:
+            return a
+        return super().add(a, b)
+
+    def sub(self, a, b):
+        if b is None:
+            return a
+        if a is None:
+            return self.neg(b)
+        return super().sub(a, b)
+
+    def scale(self, a, c):
+        return None if a is None else super().scale(a, c)
+
+    def add_i(self, a, b, s):
+        if b is None:
+            return a
+        if a is None:
+            return self.emit(f"mul2({self.swap(b)}, {self.pair(-s, s)})")
+        return super().add_i(a, b, s)
+
+    def fma2(self, a, b, cb, c=None, cc=None):
+        terms = [(b, cb)] + ([(c, cc)] if c is not None or cc is not None else [])
+        terms = [(v, k) for v, k in terms if v is not None]
+        acc = a
+        for v, k in terms:
+            acc = self.emit(f"mul2({v}, {self.pair(k, k)})") if acc is None else self.emit(f"fma2({v}, {self.pair(k, k)}, {acc})")
+        return acc
+
+    def lin2(self, b, cb, c, cc):
+        return self.fma2(None, b, cb, c, cc)
+
+    def twiddle(self, a, num, den):
+        return None if a is None else super().twiddle(a, num, den)
+
+
+def pruned_inputs(n):
+    """number of leading inputs the pruned forward variant reads: ceil(n / 5)"""
+    return (n + 4) // 5
+
+
+def gen_size_packed_pruned(n):
+    g = GenPackedZ(-1)
+    k = pruned_inputs(n)
+    x = [f"x[{i}]" if i < k else None for i in range(n)]
+    out = g.fft(n, x)
+    body = ["    " + l for l in g.lines]
+    for i, v in enumerate(out):
+        body.append(f"    x[{i}] = {v if v is not None else 'make_float2(0.f, 0.f)'};")
+    return (f"template <> struct RegFFTPZ<{n}> {{\n  static constexpr int K = {k};\n"
+            f"  static MVSIM_HD void run(float2 (&x)[{n}]) {{\n" + "\n".join(body) + "\n  }\n};\n")
+
+
 def gen_size_packed(n, sign):
     g = GenPacked(sign)
     x = [f"x[{i}]" for i in range(n)]
@@ -229,6 +292,12 @@ def main_packed(path):
         for sign in (-1, 1):
             parts.append(gen_size_packed(n, sign))
             parts.append("\n")
+    parts.append("// Forward transforms of lines whose inputs x[K..N) are zero (K = ceil(N/5)): zero terms propagated away at generation time.\n"
+                 "// x[K..N) is not read; all N outputs are written.\n"
+                 "template <int N> struct RegFFTPZ;\n\n")
+    for n in SIZES:
+        parts.append(gen_size_packed_pruned(n))
+        parts.append("\n")
     parts.append("}  // namespace mvsim\n")
     with open(path, "w") as f:
         f.write("".join(parts))
