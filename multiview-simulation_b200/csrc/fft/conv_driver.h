@@ -132,7 +132,7 @@ template <class L> int conv_middle_z(L& l, const ConvPlan& pl, const SlabGeom& g
     zp.tile0 = g.tile0; zp.zg = g.z_local; zp.zg_magic = div_magic((uint32_t)g.z_local);
     zp.keep_inc = pruned ? keep_inc : 1; zp.n_keep = planes - 1; zp.keep_magic = div_magic((uint32_t)zp.keep_inc);
     zp.estride = ny * T; zp.ostride = T;
-    zp.estride32 = (g.world == 1 && ws.n_peers <= 1 && (long long)pl.sz.n * ny * T < 0x7fffffffLL) ? (int)(ny * T) : 0;
+    zp.estride32 = (g.world == 1 && ws.n_peers <= 1 && (long long)pl.sz.n * ny * T < 0x0fffffffLL) ? (int)(ny * T) : 0;
     zp.u_tstride = (long long)g.z_local * ny * T; zp.seg_stride = (long long)g.tiles_own * g.z_local * ny * T;
     zp.h_tstride = (long long)pl.sz.n * ny * T;
     if (pl.dims[2] >= 65536) return 5;

@@ -110,6 +110,17 @@ template <int A, int B, bool PK = false> MVSIM_HD void inv_second(int p, float2 
     RegSel<A, 1, PK>::run(x);
 }
 
+// Element `idx` of a strided line through its 32-bit element stride e (host side guarantees n * e < 2^28, so the byte
+// stride fits 32 bits too): ONE widening multiply-add (IMAD.WIDE.U32) instead of multiply + 64-bit add + scaled 64-bit add.
+MVSIM_HD const float2* at32(const float2* base, unsigned idx, unsigned e)
+{
+    return reinterpret_cast<const float2*>(reinterpret_cast<const char*>(base) + (unsigned long long)idx * (unsigned long long)(e * 8u));
+}
+MVSIM_HD float2* at32(float2* base, unsigned idx, unsigned e)
+{
+    return reinterpret_cast<float2*>(reinterpret_cast<char*>(base) + (unsigned long long)idx * (unsigned long long)(e * 8u));
+}
+
 // Gathers x[n1] = ext(line)[p + n1*B - left], n1 < A, from a strided line.  All index arithmetic is done
 // before the first load so the A loads of a thread are in flight together.
 // e32 != 0: every element offset of the line (index * estride) fits 32 bits, so one 32-bit multiply + one widening
@@ -124,7 +135,7 @@ template <int A, int B> MVSIM_HD void gather_line(float2 (&x)[A], const float2* 
         for (int n1 = 0; n1 < A; ++n1) idx[n1] = mirror_once(p + n1 * B - left, n_src);
         if (e32) {
             MVSIM_UNROLL
-            for (int n1 = 0; n1 < A; ++n1) x[n1] = src[(unsigned)idx[n1] * e32];
+            for (int n1 = 0; n1 < A; ++n1) x[n1] = *at32(src, (unsigned)idx[n1], e32);
         } else {
             MVSIM_UNROLL
             for (int n1 = 0; n1 < A; ++n1) x[n1] = src[idx[n1] * estride];
@@ -135,7 +146,7 @@ template <int A, int B> MVSIM_HD void gather_line(float2 (&x)[A], const float2* 
             for (int n1 = 0; n1 < A; ++n1) {
                 const int n = p + n1 * B - left;
                 const bool ok = (unsigned)n < (unsigned)n_src;
-                const float2 v = src[(unsigned)(ok ? n : 0) * e32];      // clamped index + select keeps the loads batched
+                const float2 v = *at32(src, (unsigned)(ok ? n : 0), e32);      // clamped index + select keeps the loads batched
                 x[n1] = ok ? v : make_float2(0.f, 0.f);
             }
         } else {
@@ -195,8 +206,8 @@ inline void strided_fill_e32(StridedParams& q, int n)
     long long top = n;
     if (q.n_src > top) top = q.n_src;
     if ((long long)q.n_out + q.out_offset > top) top = (long long)q.n_out + q.out_offset;
-    q.in_e32 = (q.in_estride > 0 && top * q.in_estride < 0x7fffffffLL) ? (unsigned)q.in_estride : 0u;
-    q.out_e32 = (q.out_estride > 0 && top * q.out_estride < 0x7fffffffLL) ? (unsigned)q.out_estride : 0u;
+    q.in_e32 = (q.in_estride > 0 && top * q.in_estride < 0x0fffffffLL) ? (unsigned)q.in_estride : 0u;
+    q.out_e32 = (q.out_estride > 0 && top * q.out_estride < 0x0fffffffLL) ? (unsigned)q.out_estride : 0u;
 }
 
 template <int A_, int B_, int T_> struct StridedFwd : LineShape<A_, B_> {
@@ -284,7 +295,7 @@ template <int A_, int B_, int T_> struct StridedInv : LineShape<A_, B_> {
                     MVSIM_UNROLL
                     for (int n1 = 0; n1 < A; ++n1) {
                         const int o = p + n1 * B - q.crop0;
-                        if ((unsigned)o < (unsigned)q.n_out) dst[(unsigned)(o + q.out_offset) * q.out_e32] = x[n1];
+                        if ((unsigned)o < (unsigned)q.n_out) *at32(dst, (unsigned)(o + q.out_offset), q.out_e32) = x[n1];
                     }
                 } else {
                     MVSIM_UNROLL
@@ -414,7 +425,7 @@ template <int A_, int B_, int T_> struct ZFused : LineShape<A_, B_> {
                 if (q.estride32) {
                     const unsigned e = (unsigned)q.estride32;
                     MVSIM_UNROLL
-                    for (int n1 = 0; n1 < A; ++n1) x[n1] = src[(unsigned)idx[n1] * e];
+                    for (int n1 = 0; n1 < A; ++n1) x[n1] = *at32(src, (unsigned)idx[n1], e);
                 } else {
                     MVSIM_UNROLL
                     for (int n1 = 0; n1 < A; ++n1) x[n1] = src[zfused_plane_offset(q, idx[n1])];
@@ -460,7 +471,7 @@ template <int A_, int B_, int T_> struct ZFused : LineShape<A_, B_> {
                         MVSIM_UNROLL
                         for (int n1 = 0; n1 < A; ++n1) {
                             const int o = p + n1 * B - q.crop0;
-                            if ((unsigned)o < (unsigned)q.n_src) dst[(unsigned)o * e] = x[n1];
+                            if ((unsigned)o < (unsigned)q.n_src) *at32(dst, (unsigned)o, e) = x[n1];
                         }
                     } else {
                         MVSIM_UNROLL
@@ -486,7 +497,7 @@ template <int A_, int B_, int T_> struct ZFused : LineShape<A_, B_> {
                         const unsigned e = (unsigned)q.estride32;
                         for (int kz = p; kz < q.n_keep; kz += S::P) {
                             const float2 v = row[kz * kstep];
-                            dst[(unsigned)kz * e] = v;
+                            *at32(dst, (unsigned)kz, e) = v;
                             acc.x -= v.x; acc.y -= v.y;
                         }
                     } else {
