@@ -46,6 +46,45 @@ static bool make_h_tensor_map(const float2* base, int lanes, int tiles, int nz, 
     return true;
 }
 
+// tensor map over a row-major spectrum [outer][rows][kxc] complex64 seen as float32 [outer][rows][2*kxc]; box = 256 rows of one kx tile
+static bool make_rows_tensor_map(const float2* base, int lanes, int kxc, int rows, int outer, unsigned long long out[16])
+{
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc || getenv("MVSIM_NO_TMA") || (kxc * 8) % 16 != 0) return false;
+    CUtensorMap m;
+    const cuuint64_t dims[3] = { (cuuint64_t)(2 * kxc), (cuuint64_t)rows, (cuuint64_t)outer };
+    const cuuint64_t strides[2] = { (cuuint64_t)kxc * 8, (cuuint64_t)rows * kxc * 8 };
+    const cuuint32_t box[3] = { (cuuint32_t)(2 * lanes), (cuuint32_t)kPrefetchBoxRows, 1 };
+    const cuuint32_t estr[3] = { 1, 1, 1 };
+    const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float2*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return false;
+    memcpy(out, &m, sizeof(m));
+    return true;
+}
+
+static int env_int(const char* name, int dflt)
+{
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+// L2 prefetch distance of the forward passes, in CTAs of launch order: a quarter of the CTAs resident on the device, i.e.
+// the target CTA starts ~2 us after the prefetch was issued.  Measured on B200, config 3 (profiles/r01_notes.md): y forward
+// 1.04 ms without, 0.83 at 74-100, 0.90 at 18 or 222, 1.13 at 592 (prefetched lines are evicted by the pass's own stores
+// before they are used); x forward 1.09 -> 0.95 for 28..222; fused z 2.61 -> 2.49 for 36..592.  The environment variable
+// overrides (0 switches the prefetch off).
+static int prefetch_dist(const char* env, int ctas_per_sm)
+{
+    static const int sms = [] {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 148;
+        return n;
+    }();
+    const int d = ctas_per_sm * sms / 4;
+    return env_int(env, d > 1 ? d : 1);
+}
+
 static bool otf_default()
 {
     static const bool on = getenv("MVSIM_H_MATERIALIZE") == nullptr;   // default: PSF spectrum computed inside the fused z pass
@@ -70,8 +109,14 @@ struct CudaLauncher {
         if (r != 0) return cuda_fail(ctx, (cudaError_t)r, what);
         return MVSIM_OK;
     }
-    int launch_x(bool inverse, const FftSize& s, const XParams& q)
+    int launch_x(bool inverse, const FftSize& s, const XParams& q0)
     {
+        XParams q = q0;
+        // rows of a later CTA prefetched into the L2 (16-byte granularity of the bulk prefetch: X % 4 == 0)
+        static const int xdist = prefetch_dist("MVSIM_X_PREFETCH", 3);
+        static const int xidist = prefetch_dist("MVSIM_XI_PREFETCH", 3);
+        if (inverse) q.prefetch_dist = ((s.n * 8) % 16 == 0 && (reinterpret_cast<uintptr_t>(q.cin) & 15) == 0) ? xidist : 0;
+        else q.prefetch_dist = (!psf_phase && q.X % 4 == 0 && (reinterpret_cast<uintptr_t>(q.rin) & 15) == 0) ? xdist : 0;
         StageTimer t(ctx, psf_phase ? MVSIM_T_PSF : (inverse ? MVSIM_T_FFT_XINV : MVSIM_T_FFT_XFWD));
         return finish(fft_launch(inverse ? FFT_XINV : FFT_XFWD, lanes, s.n, &q, (unsigned)x_blocks(s, q.n_rows), 1, ctx->stream), "x pass");
     }
@@ -79,6 +124,22 @@ struct CudaLauncher {
     {
         StridedParams q = q0;
         strided_fill_e32(q, s.n);
+        const int threads = lanes * (s.a > s.b ? s.a : s.b);
+        static const int ydist2 = prefetch_dist("MVSIM_Y_PREFETCH", 2), ydist4 = prefetch_dist("MVSIM_Y_PREFETCH", 4), ydist1 = prefetch_dist("MVSIM_Y_PREFETCH", 1);
+        const int ydist = threads <= 160 ? ydist4 : (threads <= 288 ? ydist2 : ydist1);      // resident CTAs per SM: min_blocks() in fft_group.cu
+        // forward image pass over row-major rows [outer][n_src][kx_count] (in_estride == kx_count, grid = tiles x outer)
+        if (!inverse && !psf_phase && ydist > 0 && q.n_peers <= 1 && !q.swap_grid && q.in_tile_global && q.in_estride == q.kx_count &&
+            q.in_ostride == (long long)q.n_src * q.kx_count && q.in_tstride == lanes &&
+            make_rows_tensor_map(q.in, lanes, q.kx_count, q.n_src, n_outer, q.in_tmap)) {
+            q.prefetch_dist = ydist; q.grid_x = n_tiles; q.grid_y = n_outer;
+        }
+        static const int yidist2 = prefetch_dist("MVSIM_YI_PREFETCH", 2), yidist4 = prefetch_dist("MVSIM_YI_PREFETCH", 4), yidist1 = prefetch_dist("MVSIM_YI_PREFETCH", 1);
+        const int yidist = threads <= 160 ? yidist4 : (threads <= 288 ? yidist2 : yidist1);
+        // inverse pass over tile-major input [tiles][outer][n][T] (one GPU): a CTA's input is one contiguous range
+        if (inverse && yidist > 0 && q.n_peers <= 1 && !q.swap_grid && q.in_estride == lanes && q.in_ostride == (long long)s.n * lanes &&
+            q.tile0 == 0 && (reinterpret_cast<uintptr_t>(q.in) & 15) == 0) {
+            q.prefetch_dist = yidist; q.grid_x = n_tiles; q.grid_y = n_outer;
+        }
         StageTimer t(ctx, psf_phase ? MVSIM_T_PSF : (inverse ? MVSIM_T_FFT_YINV : MVSIM_T_FFT_YFWD));
         const unsigned tiles = (unsigned)n_tiles;
         const unsigned gx = q.swap_grid ? (unsigned)n_outer : tiles, gy = q.swap_grid ? tiles : (unsigned)n_outer;
@@ -92,6 +153,12 @@ struct CudaLauncher {
         if (q.h_mode) {
             // PSF tile [KZ rows] through the TMA unit into its own shared-memory area
             q.use_tma = (zfused_otf_tma_fits(s.a, s.b, lanes, q.k_src) && make_h_tensor_map(q.p2, lanes, n_tiles, q.k_src, n_outer, q.h_tmap)) ? 1 : 0;
+            const int zthreads = lanes * (s.a > s.b ? s.a : s.b);
+            static const int zdist2 = prefetch_dist("MVSIM_Z_PREFETCH", 2), zdist4 = prefetch_dist("MVSIM_Z_PREFETCH", 4), zdist1 = prefetch_dist("MVSIM_Z_PREFETCH", 1);
+            const int zdist = zthreads <= 160 ? zdist4 : (zthreads <= 288 ? zdist2 : zdist1);
+            q.grid_x = n_outer; q.grid_y = n_tiles;
+            q.prefetch_dist = (q.use_tma && zdist > 0 && q.n_peers <= 1 && q.estride32 != 0 &&
+                               make_h_tensor_map(q.u, lanes, n_tiles, q.zg, n_outer, q.u_tmap)) ? zdist : 0;
             return finish(fft_launch(FFT_ZFUSED_OTF, lanes, s.n, &q, (unsigned)n_outer, tiles, ctx->stream), "fused z pass (PSF spectrum on the fly)");
         }
         q.use_tma = make_h_tensor_map(q.h, lanes, n_tiles, s.n, n_outer, q.h_tmap) ? 1 : 0;

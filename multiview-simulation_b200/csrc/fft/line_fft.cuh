@@ -196,7 +196,12 @@ struct StridedParams {
     int n_peers, my_rank, peer_tiles;
     unsigned peer_tiles_magic;
     float2* out_peers[kMaxRanks];
+    // L2 prefetch (forward image pass on row-major input, one GPU): thread 0 of CTA i asks the TMA unit for the source columns of
+    // CTA i + prefetch_dist (launch order: kx tile fastest).  0 = off.
+    int prefetch_dist, grid_x, grid_y;
+    alignas(64) unsigned long long in_tmap[16];   // CUtensorMap over `in` as float32 [outer][n_src][2*kx_count], box [1][256][2T]
 };
+constexpr int kPrefetchBoxRows = 256;
 
 struct NoState {};
 
@@ -226,6 +231,14 @@ template <int A_, int B_, int T_> struct StridedFwd : LineShape<A_, B_> {
         const int tin = q.in_tile_global ? tile + q.tile0 : tile, tout = q.out_tile_global ? tile + q.tile0 : tile;
         const bool active = (tile + q.tile0) * T + lane < q.kx_count;
         if (PH == 0) {
+#ifdef __CUDA_ARCH__
+            if (tid == 0 && q.prefetch_dist > 0) {
+                const int lin = by * q.grid_x + bx + q.prefetch_dist;
+                const int o2 = lin / q.grid_x, t2 = lin - o2 * q.grid_x;
+                if (o2 < q.grid_y)
+                    for (int r = 0; r < q.n_src; r += kPrefetchBoxRows) tma_prefetch_3d(q.in_tmap, 2 * T * t2, r, o2);
+            }
+#endif
             if (p < B && active) {
                 float2 x[A];
                 const float2* src = q.in + tin * q.in_tstride + outer * q.in_ostride + lane;
@@ -274,6 +287,14 @@ template <int A_, int B_, int T_> struct StridedInv : LineShape<A_, B_> {
         const int tin = q.in_tile_global ? tile + q.tile0 : tile, tout = q.out_tile_global ? tile + q.tile0 : tile;
         const bool active = (tile + q.tile0) * T + lane < q.kx_count;
         if (PH == 0) {
+#ifdef __CUDA_ARCH__
+            if (tid == 0 && q.prefetch_dist > 0) {
+                // tile-major input: the T columns x N rows of a CTA are one contiguous range
+                const int lin = by * q.grid_x + bx + q.prefetch_dist;
+                const int o2 = lin / q.grid_x, t2 = lin - o2 * q.grid_x;
+                if (o2 < q.grid_y) bulk_prefetch_l2(q.in + t2 * q.in_tstride + o2 * q.in_ostride, (unsigned)(S::N * T * sizeof(float2)));
+            }
+#endif
             if (p < A && active) {
                 float2 y[B];
                 const float2* src = q.in + tin * q.in_tstride + outer * q.in_ostride + lane;
@@ -348,6 +369,10 @@ struct ZFusedParams {
     int k_src;              // KZ: valid z samples of the PSF
     long long p2_tstride;   // kx-tile stride of p2 (= KZ*Ny*T)
     int use_tma;            // 1: the H tile is fetched by the TMA unit through h_tmap (device only), 0: cp.async per thread
+    // L2 prefetch (ZFusedOTF, one GPU): thread 0 of CTA i asks the TMA unit to bring the image tile of CTA i + prefetch_dist
+    // (launch order: ky fastest) into the L2, so that CTA's gather finds its lines there instead of in DRAM.  0 = off.
+    int prefetch_dist, grid_x, grid_y;
+    alignas(64) unsigned long long u_tmap[16];   // CUtensorMap over u as float32 [tiles][Z][Ny][2T], box [1][128][1][2T]
     alignas(64) unsigned long long h_tmap[16];   // CUtensorMap over h (or, h_mode 1, over p2) as float32 [tiles][rows][Ny][2T], box [1][128][1][2T]
 };
 
@@ -577,6 +602,12 @@ template <int A_, int B_, int T_> struct ZFusedOTF : ZFused<A_, B_, T_> {
                 mbar_init(bar, 1);
                 mbar_expect_tx(bar, (unsigned)(nbox * kTmaBoxRows * T * sizeof(float2)));
                 for (int b = 0; b < nbox; ++b) tma_load_4d(sm + PSF_ELEMS0 + b * kTmaBoxRows * T, q.h_tmap, 0, outer, b * kTmaBoxRows, tile, bar);
+                if (q.prefetch_dist > 0) {
+                    const int lin = by * q.grid_x + bx + q.prefetch_dist;
+                    const int t2 = lin / q.grid_x, o2 = lin - t2 * q.grid_x;
+                    if (t2 < q.grid_y)
+                        for (int z = 0; z < q.n_src; z += kTmaBoxRows) tma_prefetch_4d(q.u_tmap, 0, o2, z, t2);
+                }
             }
 #endif
             Z::template phase<0>(q, bx, by, tid, sm, st);       // image line: gather (mirror extension) + first half
@@ -661,6 +692,7 @@ struct XParams {
     const float2* twist;    // exp(-i pi m / 2N)
     double* partials;       // inverse: per-block sums of the stored voxels (may be null)
     int X, n_rows, left, ext, crop0;
+    int prefetch_dist;      // forward: thread 0 of CTA i prefetches the rows of CTA i + prefetch_dist into the L2 (0 = off)
 };
 
 template <int A_, int B_, int R_> struct XFwd : LineShape<A_, B_> {
@@ -680,6 +712,15 @@ template <int A_, int B_, int R_> struct XFwd : LineShape<A_, B_> {
         const long long row = (long long)bx * R + r;
         const bool active = row < q.n_rows;
         if (PH == 0) {
+#ifdef __CUDA_ARCH__
+            if (tid == 0 && q.prefetch_dist > 0) {
+                const long long r0 = ((long long)bx + q.prefetch_dist) * R;
+                if (r0 < q.n_rows) {
+                    const long long nr = q.n_rows - r0 < R ? q.n_rows - r0 : R;
+                    bulk_prefetch_l2(q.rin + r0 * q.X, (unsigned)(nr * q.X * sizeof(float)));
+                }
+            }
+#endif
             if (p < B && active) {
                 float2 x[A];
                 const float* __restrict__ src = q.rin + row * q.X;
@@ -755,6 +796,15 @@ template <int A_, int B_, int R_> struct XInv : LineShape<A_, B_> {
         const long long row = (long long)bx * R + r;
         const bool active = row < q.n_rows;
         if (PH == 0) {
+#ifdef __CUDA_ARCH__
+            if (tid == 0 && q.prefetch_dist > 0) {
+                const long long r0 = ((long long)bx + q.prefetch_dist) * R;
+                if (r0 < q.n_rows) {
+                    const long long nr = q.n_rows - r0 < R ? q.n_rows - r0 : R;
+                    bulk_prefetch_l2(q.cin + r0 * N, (unsigned)(nr * N * sizeof(float2)));
+                }
+            }
+#endif
             if (p < A && active) {
                 float2 y[B];
                 const float2* src = q.cin + row * N;

@@ -162,7 +162,7 @@ template <int VEC> __device__ __forceinline__ void vload(float (&d)[VEC], const 
 // arithmetic: offsets of taps that are masked off may wrap, the ones that are dereferenced are exact)
 template <int VEC, int U, bool IDX32> __global__ void __launch_bounds__(128) rotate_attenuate_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                                                         const RowTaps* __restrict__ tab, int X, int Y, int Z,
-                                                                                        double delta, int steps)
+                                                                                        double delta, int steps, int pf)
 {
     using V = typename VecT<VEC>::type;
     const int XV = X / VEC;
@@ -180,6 +180,27 @@ template <int VEC, int U, bool IDX32> __global__ void __launch_bounds__(128) rot
     for (; s + U <= steps; s += U, y -= U) {
         float t00[U][VEC], t10[U][VEC], t11[U][VEC], t01[U][VEC];
         RowTaps tp[U];
+#ifdef __CUDA_ARCH__
+        if (pf > 0 && threadIdx.x == 0) {
+            // one thread asks for the source-row segments this CTA will gather `pf` rows from now (L2 prefetch, whole segments:
+            // the CTA's columns are contiguous in x -- the host enables this only when a CTA never straddles two planes)
+#pragma unroll
+            for (int j = 0; j < U; ++j) {
+                const int yy = y - j - pf;
+                if (yy >= 0) {
+                    const RowTaps t = trow[yy];
+                    const bool y0 = (unsigned)t.iy < (unsigned)Y, y1 = (unsigned)(t.iy + 1) < (unsigned)Y;
+                    const bool z0 = (unsigned)t.iz < (unsigned)Z, z1 = (unsigned)(t.iz + 1) < (unsigned)Z;
+                    const long long r = (long long)x0 + (long long)X * t.iy + (long long)X * Y * t.iz;
+                    const unsigned bytes = (unsigned)(blockDim.x * VEC * sizeof(float));
+                    if (y0 && z0) bulk_prefetch_l2(in + r, bytes);
+                    if (y1 && z0) bulk_prefetch_l2(in + r + X, bytes);
+                    if (y1 && z1) bulk_prefetch_l2(in + r + X + (long long)X * Y, bytes);
+                    if (y0 && z1) bulk_prefetch_l2(in + r + (long long)X * Y, bytes);
+                }
+            }
+        }
+#endif
 #pragma unroll
         for (int j = 0; j < U; ++j) tp[j] = trow[y - j];
 #pragma unroll
@@ -252,16 +273,21 @@ int k_rotate_attenuate(mvsim_ctx* ctx, const float* in, float* out, const int64_
     // the march along y is sequential per column, so the grid is small (X*Z/VEC threads): pick the widest
     // vector whose single wave still fits the machine (config 3: 131072 threads x float4, 2 rows in flight)
     const bool idx32 = (double)X * Y * Z < 2147483648.0;
+    // L2 prefetch distance in rows of the march (MVSIM_ROT_PREFETCH); OFF by default: measured 0.905 ms without, 1.11 / 1.28 / 1.31 ms at
+    // 6 / 16 / 32 rows (the march already keeps 2 rows x 4 taps in flight per thread and re-reads every source row from the L2).
+    // Needs CTAs that stay inside one row of one plane.
+    static const int pf_env = [] { const char* v = getenv("MVSIM_ROT_PREFETCH"); return v ? atoi(v) : 0; }();
     if (X % 4 == 0 && aligned) {
         const size_t cols = (size_t)(X / 4) * Z;
-        if (idx32) rotate_attenuate_kernel<4, 2, true><<<blocks_for(cols, 128), 128, 0, ctx->stream>>>(in, out, tab, X, Y, Z, delta, steps);
-        else rotate_attenuate_kernel<4, 2, false><<<blocks_for(cols, 128), 128, 0, ctx->stream>>>(in, out, tab, X, Y, Z, delta, steps);
+        const int pf = (X / 4) % 128 == 0 ? pf_env : 0;
+        if (idx32) rotate_attenuate_kernel<4, 2, true><<<blocks_for(cols, 128), 128, 0, ctx->stream>>>(in, out, tab, X, Y, Z, delta, steps, pf);
+        else rotate_attenuate_kernel<4, 2, false><<<blocks_for(cols, 128), 128, 0, ctx->stream>>>(in, out, tab, X, Y, Z, delta, steps, pf);
     } else if (X % 2 == 0 && aligned) {
         const size_t cols = (size_t)(X / 2) * Z;
-        rotate_attenuate_kernel<2, 4, false><<<blocks_for(cols, 128), 128, 0, ctx->stream>>>(in, out, tab, X, Y, Z, delta, steps);
+        rotate_attenuate_kernel<2, 4, false><<<blocks_for(cols, 128), 128, 0, ctx->stream>>>(in, out, tab, X, Y, Z, delta, steps, 0);
     } else {
         const size_t cols = (size_t)X * Z;
-        rotate_attenuate_kernel<1, 4, false><<<blocks_for(cols, 128), 128, 0, ctx->stream>>>(in, out, tab, X, Y, Z, delta, steps);
+        rotate_attenuate_kernel<1, 4, false><<<blocks_for(cols, 128), 128, 0, ctx->stream>>>(in, out, tab, X, Y, Z, delta, steps, 0);
     }
     ctx->launches++;
     cudaError_t e = cudaGetLastError();
