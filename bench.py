@@ -385,6 +385,17 @@ def run_ours(args, rank, world, local_rank):
                                "frac_of_peak_fused_model": b_fused_model / (view_ms * 1e-3) / 1e9 / peak,
                                "frac_of_peak_stage_model": b_stage_model / (view_ms * 1e-3) / 1e9 / peak}}
     stages_ms = {k: {"ms_per_view": v[0] / (args.steps * nv), "launches": v[1]} for k, v in stage.items() if v[1]}
+    # every pass against the same peak: compulsory bytes of the pruned pass (what it must read + write once) / its CUDA-event time
+    try:
+        X, Y, Z = shape[2], shape[1], shape[0]
+        u1, u2 = 8 * kxc * Y * Z, 8 * kxc * ny * Z
+        per_pass_bytes = {"rotate": 8 * N, "fft_xfwd": 4 * N + u1, "fft_yfwd": u1 + u2, "fft_zfused": bytes_pruned,
+                          "fft_yinv": planes_out * 8 * kxc * (ny + Y), "fft_xinv": planes_out * Y * (8 * kxc + 4 * X), "sample": 8 * O}
+        roofline["passes"] = {k: {"GB": b / 1e9, "GBps": b / (stages_ms[k]["ms_per_view"] * 1e-3) / 1e9,
+                                  "frac": b / (stages_ms[k]["ms_per_view"] * 1e-3) / 1e9 / peak}
+                              for k, b in per_pass_bytes.items() if k in stages_ms and stages_ms[k]["ms_per_view"] > 0}
+    except Exception as e:      # reporting only
+        roofline["passes"] = {"error": str(e)}
 
     cpu, _ = cpu_reference_sample(args.workload, steps=2) if not args.no_cpu else ({"value": None, "unit": "voxels/s", "cores": 0, "kind": "port", "sample": "skipped"}, 0)
 
