@@ -85,7 +85,8 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.rows = []
+        self.rows = []          # (arrival time, csv line)
+        self.t_start = None
         self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
@@ -97,7 +98,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def mark_start(self):
+        """The timed region starts now: only samples that arrive from here on are reported (the sampler itself is started
+        before the warm-up, so that nvidia-smi's start-up does not eat a timed region of a few hundred ms)."""
+        self.t_start = time.perf_counter()
 
     def stop(self):
         if not self.proc:
@@ -107,9 +113,15 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
+        rows = list(self.rows)
+        inside = [r for t, r in rows if self.t_start is None or t >= self.t_start]
+        note = None
+        if not inside and rows:
+            inside = [rows[-1][1]]      # region shorter than the sampling period: the last sample before it (warm-up, same load)
+            note = "timed region shorter than the 100 ms sampling period: last warm-up sample"
         sm, mx, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in inside:
             f = [c.strip() for c in r.split(",")]
             if len(f) < 7:
                 continue
@@ -120,8 +132,11 @@ class ClockSampler:
             for nme, val in zip(names, f[3:7]):
                 if val.lower().startswith("active"):
                     reasons.add(nme)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+        out = {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+               "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+        if note:
+            out["note"] = note
+        return out
 
 
 def measured_peak_gbs():
@@ -230,13 +245,15 @@ def run_ours(args, rank, world, local_rank):
     max_over_ranks = grp.max
 
     # ---- device-resident arm -------------------------------------------------------------------------
+    clocks = ClockSampler(local_rank) if rank == 0 else None      # started early; samples are counted from mark_start() on
     for _ in range(args.warmup):
         step_device()
     barrier()
     ctx.profile(True)
     launches0 = ctx.kernel_launches
-    clocks = ClockSampler(local_rank) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if clocks:
+        clocks.mark_start()
     e0.record(stream)
     for _ in range(args.steps):
         step_device()

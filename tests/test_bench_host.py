@@ -1,0 +1,46 @@
+"""Host-side pieces of bench.py that can be checked without a GPU: the nvidia-smi clock sampler (fed by a stand-in
+`nvidia-smi` script) and the workload table."""
+import importlib.util
+import os
+import stat
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _bench():
+    spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(ROOT, "bench.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_clock_sampler_counts_only_samples_of_the_timed_region(tmp_path, monkeypatch):
+    fake = tmp_path / "nvidia-smi"
+    fake.write_text("#!/bin/bash\nsleep 0.1\nwhile true; do echo '1965, 1965, 450.1, Not Active, Not Active, Not Active, Active'; sleep 0.1; done\n")
+    fake.chmod(fake.stat().st_mode | stat.S_IEXEC)
+    monkeypatch.setenv("PATH", str(tmp_path) + os.pathsep + os.environ["PATH"])
+    b = _bench()
+    c = b.ClockSampler(0)
+    time.sleep(0.45)                 # "warm-up": samples arrive but must not be counted
+    before = len(c.rows)
+    c.mark_start()
+    time.sleep(0.35)
+    r = c.stop()
+    assert before >= 2
+    assert 1 <= r["samples"] <= 5 and r["samples"] < before + 5
+    assert r["sm_mhz"] == 1965.0 and r["reasons"] == ["sw_power_cap"] and "note" not in r
+    # a timed region shorter than the sampling period falls back to the last warm-up sample and says so
+    c = b.ClockSampler(0)
+    time.sleep(0.45)
+    c.mark_start()
+    r = c.stop()
+    assert r["samples"] == 1 and "note" in r
+
+
+def test_default_workload_is_baseline_config_3():
+    b = _bench()
+    shape, kshape, _, degrees, inc, snr = b.WORKLOADS["cfg3"]
+    assert shape == (512, 1024, 1024) and kshape == (128, 128, 128) and len(degrees) == 6 and inc == 5 and snr == 25.0
+    assert b.workload_config("cfg3")["workload"].startswith("BASELINE config 3")
