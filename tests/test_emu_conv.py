@@ -144,3 +144,12 @@ def test_zero_extended_psf_line_takes_the_pruned_path(emu, oracle):
     ref = oracle.convolve(vol, psf, "direct")
     out, _ = _run(emu, vol, psf)
     assert rel_err(out, ref) < 5e-6
+
+
+def test_generated_butterflies_are_in_sync_with_the_generator(tmp_path):
+    """fft/regfft_gen*.cuh are generated files: regenerating them must reproduce the committed text."""
+    import sys
+    a, b = tmp_path / "regfft_gen.cuh", tmp_path / "regfft_gen_packed.cuh"
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "gen_regfft.py"), str(a), str(b)])
+    assert a.read_text() == open(os.path.join(CSRC, "fft", "regfft_gen.cuh")).read()
+    assert b.read_text() == open(os.path.join(CSRC, "fft", "regfft_gen_packed.cuh")).read()
