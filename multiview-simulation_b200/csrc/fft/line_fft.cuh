@@ -236,7 +236,12 @@ template <int A_, int B_, int T_> struct StridedFwd : LineShape<A_, B_> {
                 const int lin = by * q.grid_x + bx + q.prefetch_dist;
                 const int o2 = lin / q.grid_x, t2 = lin - o2 * q.grid_x;
                 if (o2 < q.grid_y)
-                    for (int r = 0; r < q.n_src; r += kPrefetchBoxRows) tma_prefetch_3d(q.in_tmap, 2 * T * t2, r, o2);
+                {
+                    // source rows this launch touches: padded index i holds source i - left (overlap-save blocks use a window)
+                    const int r0 = q.left < 0 ? -q.left : 0;
+                    const int r1 = S::N - q.left < q.n_src ? S::N - q.left : q.n_src;
+                    for (int r = r0; r < r1; r += kPrefetchBoxRows) tma_prefetch_3d(q.in_tmap, 2 * T * t2, r, o2);
+                }
             }
 #endif
             if (p < B && active) {

@@ -19,7 +19,7 @@ SRC = os.path.join(HERE, "emu", "emu_sampler.cpp")
 def emu():
     deps = [SRC, os.path.join(CSRC, "sampler.cuh")]
     if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(d) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I", CSRC, SRC, "-o", SO])
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-fno-gnu-unique", "-Wl,-Bsymbolic", "-I", CSRC, SRC, "-o", SO])
     L = C.CDLL(SO)
     L.emu_poisson.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_float), C.c_uint64, C.c_uint64, C.c_uint64]
     return L
