@@ -197,7 +197,7 @@ static int dev_rotate(mvsim_ctx* ctx, const float* in, float* out, const int64_t
 
 static int dev_attenuate(mvsim_ctx* ctx, const float* in, float* out, const int64_t dims[3], double delta, int strict)
 {
-    int steps;
+    int steps = 0;
     MVSIM_TRY(attenuate_steps(ctx, dims, strict, &steps));
     StageTimer t(ctx, MVSIM_T_ATTENUATE);
     return k_attenuate(ctx, in, out, dims, delta, steps);
@@ -244,7 +244,7 @@ static int dev_simulate_view(mvsim_ctx* ctx, const mvsim_view_params* p, const f
     {
         // :570 + :573 in one pass (the rotated volume is not part of this entry point's output)
         double inv[12];
-        int steps;
+        int steps = 0;
         if (axis_rotation(p->dims, p->axis, p->degrees, nullptr, inv)) return set_error(ctx, MVSIM_EINVAL, "simulate_view: bad axis");
         MVSIM_TRY(attenuate_steps(ctx, p->dims, p->strict_reference, &steps));
         int st;
