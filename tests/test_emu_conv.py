@@ -31,6 +31,16 @@ def emu():
     return L
 
 
+@pytest.fixture(autouse=True, params=["materialised-H", "on-the-fly"])
+def psf_spectrum_mode(request, monkeypatch):
+    """Every test runs with both fused z kernels: ZFused (PSF spectrum H materialised by a z pass) and ZFusedOTF (the
+    library's default: the PSF line is transformed inside the fused z pass)."""
+    if request.param == "on-the-fly":
+        monkeypatch.setenv("MVSIM_EMU_OTF", "1")
+    else:
+        monkeypatch.delenv("MVSIM_EMU_OTF", raising=False)
+
+
 def _run(emu, vol, psfn, keep_inc=1, planes=None, world=1, max_line=0, p2p=0):
     z, y, x = vol.shape
     kz, ky, kx = psfn.shape

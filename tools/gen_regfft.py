@@ -258,6 +258,35 @@ def gen_size_packed_pruned(n):
             f"  static MVSIM_HD void run(float2 (&x)[{n}]) {{\n" + "\n".join(body) + "\n  }\n};\n")
 
 
+# ---- inverse transforms of which only the outputs o = r (mod inc) are wanted (the kept planes of extractSlices fall on one
+# residue class of the second-level index when inc divides B): full dataflow generated, dead code removed ----------------
+DECIM = [(n, inc) for inc in (3, 5) for n in SIZES if n % inc == 0 and n // inc >= 2]
+
+
+def gen_size_packed_decimated(n, inc, r):
+    import re
+    g = GenPacked(1)
+    x = [f"x[{i}]" for i in range(n)]
+    out = g.fft(n, x)
+    wanted = [out[r + inc * j] for j in range(n // inc)]
+    defs = {}
+    for idx, line in enumerate(g.lines):
+        m = re.match(r"const float2 (t\d+) = (.*);$", line)
+        defs[m.group(1)] = (idx, set(re.findall(r"\bt\d+\b", m.group(2))))
+    live, stack = set(), [w for w in wanted if w in defs]
+    while stack:
+        v = stack.pop()
+        if v in live:
+            continue
+        live.add(v)
+        stack.extend(d for d in defs[v][1] if d not in live)
+    body = ["    " + line for line in g.lines if re.match(r"const float2 (t\d+) =", line).group(1) in live]
+    for j, v in enumerate(wanted):
+        body.append(f"    o[{j}] = {v};")
+    return (f"template <> struct RegFFTPD<{n}, {inc}, {r}> {{\n"
+            f"  static MVSIM_HD void run(const float2 (&x)[{n}], float2 (&o)[{n // inc}]) {{\n" + "\n".join(body) + "\n  }\n};\n"), len(body)
+
+
 def gen_size_packed(n, sign):
     g = GenPacked(sign)
     x = [f"x[{i}]" for i in range(n)]
@@ -298,6 +327,12 @@ def main_packed(path):
     for n in SIZES:
         parts.append(gen_size_packed_pruned(n))
         parts.append("\n")
+    parts.append("// Inverse transforms restricted to the outputs o = R (mod INC): o[j] = X[R + INC*j]; dead code removed at generation time.\n"
+                 "template <int N, int INC, int R> struct RegFFTPD;\n\n")
+    for n, inc in DECIM:
+        for r in range(inc):
+            parts.append(gen_size_packed_decimated(n, inc, r)[0])
+            parts.append("\n")
     parts.append("}  // namespace mvsim\n")
     with open(path, "w") as f:
         f.write("".join(parts))
