@@ -5,6 +5,8 @@
 
 #include <string.h>
 
+#include <vector>
+
 #include "ctx.h"
 #include "fft/conv_driver.h"
 #include "fft/fft_launch.h"
@@ -144,6 +146,40 @@ struct CudaLauncher {
         const unsigned tiles = (unsigned)n_tiles;
         const unsigned gx = q.swap_grid ? (unsigned)n_outer : tiles, gy = q.swap_grid ? tiles : (unsigned)n_outer;
         return finish(fft_launch(inverse ? FFT_SINV : FFT_SFWD, lanes, s.n, &q, gx, gy, ctx->stream), "strided pass");
+    }
+    // EXPERIMENT (MVSIM_Z_DECIMATE=1): decimated inverse of the whole-view fused z pass, see ZFusedDec in fft/line_fft.cuh
+    bool z_decimate(const FftSize& s) const
+    {
+        static const bool on = env_int("MVSIM_Z_DECIMATE", 0) != 0 && MVSIM_PACKED_FFT != 0;
+        return on && s.n >= kDecMinLine && s.n <= kDecMaxLine;
+    }
+    int launch_zfused_dec(const FftSize& s, const ZFusedParams& q0, int n_tiles, int n_outer, int inc)
+    {
+        ZFusedParams q = q0;
+        // D table: host closed form, staged copy (pageable source: the call returns once the bytes are staged), stream-ordered free
+        float2* d_tab = nullptr;
+        MVSIM_TRY(dev_alloc(ctx, (void**)&d_tab, sizeof(float2) * (size_t)s.n));
+        {
+            std::vector<float2> h((size_t)s.n);
+            zfused_dec_table(s.n, q.crop0, q.n_src, h.data());
+            const cudaError_t e = cudaMemcpyAsync(d_tab, h.data(), sizeof(float2) * (size_t)s.n, cudaMemcpyHostToDevice, ctx->stream);
+            if (e != cudaSuccess) { dev_free(ctx, d_tab); return cuda_fail(ctx, e, "decimation table upload"); }
+        }
+        q.dtab = d_tab;
+        int r;
+        {
+            StageTimer t(ctx, MVSIM_T_FFT_ZFUSED);
+            q.use_tma = (zfused_otf_tma_fits(s.b, s.a, lanes, q.k_src) && make_h_tensor_map(q.p2, lanes, n_tiles, q.k_src, n_outer, q.h_tmap)) ? 1 : 0;
+            const int zthreads = lanes * (s.a > s.b ? s.a : s.b);
+            static const int zdist2 = prefetch_dist("MVSIM_Z_PREFETCH", 2), zdist4 = prefetch_dist("MVSIM_Z_PREFETCH", 4), zdist1 = prefetch_dist("MVSIM_Z_PREFETCH", 1);
+            const int zdist = zthreads <= 160 ? zdist4 : (zthreads <= 288 ? zdist2 : zdist1);
+            q.grid_x = n_outer; q.grid_y = n_tiles;
+            q.prefetch_dist = (q.use_tma && zdist > 0 && make_h_tensor_map(q.u, lanes, n_tiles, q.zg, n_outer, q.u_tmap)) ? zdist : 0;
+            r = finish(fft_launch(inc == 3 ? FFT_ZFUSED_DEC3 : FFT_ZFUSED_DEC5, lanes, s.n, &q, (unsigned)n_outer, (unsigned)n_tiles, ctx->stream),
+                       "fused z pass (decimated inverse)");
+        }
+        dev_free(ctx, d_tab);
+        return r;
     }
     int launch_zfused(const FftSize& s, const ZFusedParams& q0, int n_tiles, int n_outer)
     {

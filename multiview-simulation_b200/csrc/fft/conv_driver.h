@@ -143,7 +143,27 @@ template <class L> int conv_middle_z(L& l, const ConvPlan& pl, const SlabGeom& g
         zp.n_peers = ws.n_peers;
         for (int r = 0; r < ws.n_peers; ++r) zp.out_peers[r] = ws.peers_y[r];
     }
+    // experiment (launcher decides, off by default): decimated inverse when the kept planes are whole columns of the exchange
+    if (pruned && l.h_on_the_fly && zp.estride32 != 0 && zfused_dec_ok(pl.sz.a, pl.sz.b, keep_inc) && l.z_decimate(pl.sz))
+        return l.launch_zfused_dec(pl.sz, zp, g.tiles_own, pl.sy.n, keep_inc);
     return l.launch_zfused(pl.sz, zp, g.tiles_own, pl.sy.n);
+}
+
+// D[k] = sum_{n = crop0}^{crop0 + n_src - 1} exp(+2 pi i n k / N), k < N (ZFusedDec: the sum of the cropped outputs of the unscaled
+// inverse transform is sum_k Yhat[k] D[k]); double arithmetic, stored as float2
+inline void zfused_dec_table(int n, int crop0, int n_src, float2* out)
+{
+    // closed form of the geometric sum: exp(i t (crop0 + (n_src - 1)/2)) sin(n_src t / 2) / sin(t / 2), t = 2 pi k / n
+    const double pi = 3.14159265358979323846;
+    out[0].x = (float)n_src; out[0].y = 0.f;
+    for (int k = 1; k < n; ++k) {
+        const double half = pi * (double)k / (double)n;                                  // t / 2
+        const long long m2 = ((long long)(2 * crop0 + n_src - 1) * k) % (2LL * n);       // phase t (crop0 + (n_src-1)/2) = pi m2 / n, reduced exactly
+        const double ph = pi * (double)m2 / (double)n;
+        const long long ms = ((long long)n_src * k) % (2LL * n);                         // n_src t / 2 = pi ms / n
+        const double amp = sin(pi * (double)ms / (double)n) / sin(half);
+        out[k].x = (float)(amp * cos(ph)); out[k].y = (float)(amp * sin(ph));
+    }
 }
 
 // y inverse of block b: ws.u2 (tile-major [KT][Zl][Ny][T], `planes` of the Zl planes in use) -> rows of ws.u1o

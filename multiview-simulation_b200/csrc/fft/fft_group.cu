@@ -67,6 +67,12 @@ template <int A, int B> static int launch_size(int kind, const void* params, uns
     case FFT_SINV: return launch<StridedInv<A, B, T>>(params, gx, gy, s);
     case FFT_ZFUSED: return launch<ZFused<A, B, T>>(params, gx, gy, s);
     case FFT_ZFUSED_OTF: return launch<ZFusedOTF<A, B, T>>(params, gx, gy, s);
+    case FFT_ZFUSED_DEC3:
+        if constexpr (zfused_dec_ok(A, B, 3) && A * B >= kDecMinLine && A * B <= kDecMaxLine) return launch<ZFusedDec<B, A, T, 3>>(params, gx, gy, s);
+        break;
+    case FFT_ZFUSED_DEC5:
+        if constexpr (zfused_dec_ok(A, B, 5) && A * B >= kDecMinLine && A * B <= kDecMaxLine) return launch<ZFusedDec<B, A, T, 5>>(params, gx, gy, s);
+        break;
     }
     return (int)cudaErrorInvalidValue;
 }

@@ -7,8 +7,12 @@
 
 namespace mvsim {
 
-enum FftKind { FFT_XFWD = 0, FFT_XINV = 1, FFT_SFWD = 2, FFT_SINV = 3, FFT_ZFUSED = 4, FFT_ZFUSED_OTF = 5 };
+enum FftKind { FFT_XFWD = 0, FFT_XINV = 1, FFT_SFWD = 2, FFT_SINV = 3, FFT_ZFUSED = 4, FFT_ZFUSED_OTF = 5,
+               FFT_ZFUSED_DEC3 = 6, FFT_ZFUSED_DEC5 = 7 };   // decimated inverse (experiment): the planner's (a, b) with 3 | a resp. 5 | a
 
+// the experimental decimated fused z kernels are built only for z lines of these lengths (build time): covers the BASELINE
+// configs (339 -> 360 with inc 3, 639 -> 640 with inc 5)
+constexpr int kDecMinLine = 300, kDecMaxLine = 660;
 constexpr int kXThreadsTarget = 256; // x passes: rows per CTA = kXThreadsTarget / threads-per-line
 
 constexpr int x_rows_per_block(int a, int b) { return (kXThreadsTarget / (a > b ? a : b)) > 0 ? kXThreadsTarget / (a > b ? a : b) : 1; }

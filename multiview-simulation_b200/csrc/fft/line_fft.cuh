@@ -377,6 +377,8 @@ struct ZFusedParams {
     // L2 prefetch (ZFusedOTF, one GPU): thread 0 of CTA i asks the TMA unit to bring the image tile of CTA i + prefetch_dist
     // (launch order: ky fastest) into the L2, so that CTA's gather finds its lines there instead of in DRAM.  0 = off.
     int prefetch_dist, grid_x, grid_y;
+    // ZFusedDec: D[k] = sum over the cropped range of exp(+2 pi i n k / N): sum of the cropped outputs = sum_k Yhat[k] D[k]
+    const float2* dtab;
     alignas(64) unsigned long long u_tmap[16];   // CUtensorMap over u as float32 [tiles][Z][Ny][2T], box [1][128][1][2T]
     alignas(64) unsigned long long h_tmap[16];   // CUtensorMap over h (or, h_mode 1, over p2) as float32 [tiles][rows][Ny][2T], box [1][128][1][2T]
 };
@@ -674,6 +676,212 @@ template <int A_, int B_, int T_> struct ZFusedOTF : ZFused<A_, B_, T_> {
                     }
                     fwd_first<A, B, kPackedStrided>(p, x, sm, lane, T, q.tw);
                 }
+            }
+        }
+    }
+};
+
+// ==============================================================================================
+// EXPERIMENT for the next round (MVSIM_Z_DECIMATE=1, off by default, emulated on the CPU but not yet measured on a GPU):
+// fused z pass of the whole-view call with a DECIMATED inverse.  extractSlices keeps z = 0, INC, 2 INC, ... (:206), i.e. the
+// padded outputs n = crop0 + INC kz.  With the split n = n1 B + n2 and INC | B these are exactly the columns
+// n2 = r (mod INC), r = crop0 mod INC, of the exchange, so
+//   - the first inverse half needs B/INC of its B outputs per thread (RegFFTPD: dead code removed by the generator),
+//   - the second inverse half runs for B/INC of the B threads of a line,
+//   - the plane that carries the sum of the dropped slices (adjustImage's mean) comes from ONE dot product: the sum of all
+//     cropped outputs is sum_k Yhat[k] D[k] with D[k] = sum_{n in crop} exp(+2 pi i n k / N), minus the kept outputs.
+// A_, B_ are the planner's (b, a): the first level has the larger transform here (config 3: A = 32, B = 20, INC = 5).
+// Phases: image first half | image second half, park | PSF first half | PSF second half, multiply, dot with D |
+//         pruned inverse first half | inverse second half of the kept columns, stores | sum plane.
+// ==============================================================================================
+// may the planner's split (a, b) of a z line run the decimated kernel ZFusedDec<b, a, T, inc>?
+constexpr bool zfused_dec_ok(int a, int b, int inc) { return (inc == 3 || inc == 5) && a % inc == 0 && a / inc >= 2 && a + b <= a * b; }
+
+template <int A_, int B_, int T_, int INC_> struct ZFusedDec : LineShape<A_, B_> {
+    using S = LineShape<A_, B_>;
+    static constexpr int A = A_, B = B_, T = T_, INC = INC_;
+    static_assert(B_ % INC_ == 0 && B_ / INC_ >= 2, "the kept outputs must be whole columns of the exchange");
+    static constexpr int KEEP = B / INC;          // kept columns per line
+    static constexpr int THREADS = T * S::P;
+    static constexpr int NPH = 7;
+    static constexpr int EXCH_ELEMS = (S::ELEMS * T + 15) / 16 * 16;
+    static constexpr int H_ROWS = (S::N + kTmaBoxRows - 1) / kTmaBoxRows * kTmaBoxRows;
+    static constexpr int BAR_ELEMS = EXCH_ELEMS + H_ROWS * T;
+    static constexpr int PSF_ELEMS0 = BAR_ELEMS + 16;
+    static constexpr int SMEM_BYTES = PSF_ELEMS0 * (int)sizeof(float2);
+    static_assert(SMEM_BYTES == zfused_otf_smem_base(A_, B_, T_), "host-side shared memory formula out of sync");
+    static_assert(A_ + B_ <= S::N, "partial sums live in the parked-spectrum area");
+    using Params = ZFusedParams;
+    using State = RegState<B>;
+    static int smem_bytes(const Params& q) { return SMEM_BYTES + (q.use_tma ? zfused_otf_psf_tile_bytes(q.k_src, T) : 0); }
+    static int smem_bytes_max() { const int m = SMEM_BYTES + H_ROWS * T * (int)sizeof(float2); return m < kSmemLimit ? m : kSmemLimit; }
+
+    // first inverse half restricted to the columns n2 = R + INC j: twiddle and store
+    template <int R> static MVSIM_HD void inv_first_kept(int p, const float2 (&y)[B], float2* sm, int lane, const float2* __restrict__ tw)
+    {
+        constexpr int BP = B | 1;
+        float2 o[KEEP];
+        RegFFTPD<B, INC, R>::run(y, o);
+        MVSIM_UNROLL
+        for (int j = 0; j < KEEP; ++j) {
+            const int n2 = R + INC * j;
+            const float2 v = n2 == 0 ? o[j] : cmulc(o[j], tw[n2 * p]);
+            sm[lane + (p * BP + n2) * T] = v;
+        }
+    }
+
+    template <int PH> static MVSIM_HD void phase(const Params& q, int bx, int by, int tid, float2* sm, State& st)
+    {
+        const int lane = tid % T, p = tid / T;
+        const int tile = by, outer = bx;
+        const bool active = (tile + q.tile0) * T + lane < q.kx_count;
+        float2* smh = sm + EXCH_ELEMS;
+        const int r = q.crop0 % INC;
+        if (PH == 0) {
+#ifdef __CUDA_ARCH__
+            if (q.use_tma && tid == 0) {
+                uint64_t* bar = reinterpret_cast<uint64_t*>(sm + BAR_ELEMS);
+                const int nbox = (q.k_src + kTmaBoxRows - 1) / kTmaBoxRows;
+                mbar_init(bar, 1);
+                mbar_expect_tx(bar, (unsigned)(nbox * kTmaBoxRows * T * sizeof(float2)));
+                for (int b = 0; b < nbox; ++b) tma_load_4d(sm + PSF_ELEMS0 + b * kTmaBoxRows * T, q.h_tmap, 0, outer, b * kTmaBoxRows, tile, bar);
+                if (q.prefetch_dist > 0) {
+                    const int lin = by * q.grid_x + bx + q.prefetch_dist;
+                    const int t2 = lin / q.grid_x, o2 = lin - t2 * q.grid_x;
+                    if (t2 < q.grid_y)
+                        for (int z = 0; z < q.n_src; z += kTmaBoxRows) tma_prefetch_4d(q.u_tmap, 0, o2, z, t2);
+                }
+            }
+#endif
+            if (p < B && active) {
+                float2 x[A];
+                const float2* __restrict__ src = q.u + tile * q.u_tstride + outer * q.ostride + lane;
+                int idx[A];
+                if (q.ext == EXT_MIRROR1) {
+                    MVSIM_UNROLL
+                    for (int n1 = 0; n1 < A; ++n1) idx[n1] = mirror_once(p + n1 * B - q.left, q.n_src);
+                } else {
+                    MVSIM_UNROLL
+                    for (int n1 = 0; n1 < A; ++n1) idx[n1] = mirror_single(p + n1 * B - q.left, q.n_src);
+                }
+                const unsigned e = (unsigned)q.estride32;
+                MVSIM_UNROLL
+                for (int n1 = 0; n1 < A; ++n1) x[n1] = *at32(src, (unsigned)idx[n1], e);
+                fwd_first<A, B, kPackedStrided>(p, x, sm, lane, T, q.tw);
+            }
+        } else if (PH == 1) {
+            if (p < A && active) {
+                float2 y[B];
+                fwd_second<A, B, kPackedStrided>(p, y, sm, lane, T);
+                MVSIM_UNROLL
+                for (int k2 = 0; k2 < B; ++k2) smh[(p + A * k2) * T + lane] = y[k2];     // read back by the same thread only
+            }
+        } else if (PH == 2) {
+            constexpr int K = RegSelZ<A, kPackedStrided>::K;
+            const bool pruned = q.k_src <= K * B;
+#ifdef __CUDA_ARCH__
+            if (q.use_tma) {
+                mbar_wait(reinterpret_cast<uint64_t*>(sm + BAR_ELEMS), 0);
+                if (p < B && active) {
+                    const float2* tilep = sm + PSF_ELEMS0;
+                    const int rows = (q.k_src + kTmaBoxRows - 1) / kTmaBoxRows * kTmaBoxRows;
+                    float2 x[A];
+                    if (pruned) {
+                        MVSIM_UNROLL
+                        for (int n1 = 0; n1 < K; ++n1) {
+                            const int n = p + n1 * B;
+                            x[n1] = n < rows ? tilep[n * T + lane] : make_float2(0.f, 0.f);
+                        }
+                        fwd_first_zext<A, B, kPackedStrided>(p, x, sm, lane, T, q.tw);
+                    } else {
+                        MVSIM_UNROLL
+                        for (int n1 = 0; n1 < A; ++n1) {
+                            const int n = p + n1 * B;
+                            x[n1] = n < rows ? tilep[n * T + lane] : make_float2(0.f, 0.f);
+                        }
+                        fwd_first<A, B, kPackedStrided>(p, x, sm, lane, T, q.tw);
+                    }
+                }
+            } else
+#endif
+            if (p < B && active) {
+                float2 x[A];
+                const float2* __restrict__ src = q.p2 + tile * q.p2_tstride + outer * q.ostride + lane;
+                if (pruned) {
+                    MVSIM_UNROLL
+                    for (int n1 = 0; n1 < K; ++n1) {
+                        const int n = p + n1 * B;
+                        const bool ok = n < q.k_src;
+                        const float2 v = src[(ok ? n : 0) * q.estride];
+                        x[n1] = ok ? v : make_float2(0.f, 0.f);
+                    }
+                    fwd_first_zext<A, B, kPackedStrided>(p, x, sm, lane, T, q.tw);
+                } else {
+                    MVSIM_UNROLL
+                    for (int n1 = 0; n1 < A; ++n1) {
+                        const int n = p + n1 * B;
+                        const bool ok = n < q.k_src;
+                        const float2 v = src[(ok ? n : 0) * q.estride];
+                        x[n1] = ok ? v : make_float2(0.f, 0.f);
+                    }
+                    fwd_first<A, B, kPackedStrided>(p, x, sm, lane, T, q.tw);
+                }
+            }
+        } else if (PH == 3) {
+            if (p < A && active) {
+                fwd_second<A, B, kPackedStrided>(p, st.y, sm, lane, T);
+                float2 acc = make_float2(0.f, 0.f);
+                MVSIM_UNROLL
+                for (int k2 = 0; k2 < B; ++k2) {
+                    st.y[k2] = cmul(st.y[k2], smh[(p + A * k2) * T + lane]);
+                    const float2 d = q.dtab[p + A * k2];
+                    acc.x += st.y[k2].x * d.x - st.y[k2].y * d.y;
+                    acc.y += st.y[k2].x * d.y + st.y[k2].y * d.x;
+                }
+                smh[p * T + lane] = acc;        // own slot (k2 = 0), read in the last phase
+            }
+        } else if (PH == 4) {
+            if (p < A && active) {
+                // uniform switch on the residue class of the kept outputs
+                if (INC == 3) {
+                    if (r == 0) inv_first_kept<0>(p, st.y, sm, lane, q.tw);
+                    else if (r == 1) inv_first_kept<1>(p, st.y, sm, lane, q.tw);
+                    else inv_first_kept<2>(p, st.y, sm, lane, q.tw);
+                } else {
+                    if (r == 0) inv_first_kept<0>(p, st.y, sm, lane, q.tw);
+                    else if (r == 1) inv_first_kept<1>(p, st.y, sm, lane, q.tw);
+                    else if (r == 2) inv_first_kept<2>(p, st.y, sm, lane, q.tw);
+                    else if (r == 3) inv_first_kept<(INC > 3 ? 3 : 0)>(p, st.y, sm, lane, q.tw);
+                    else inv_first_kept<(INC > 4 ? 4 : 0)>(p, st.y, sm, lane, q.tw);
+                }
+            }
+        } else if (PH == 5) {
+            // the KEEP kept columns of every line, packed into the first warps: thread (j, lane) owns column n2 = r + INC j
+            const int j = tid / T;
+            if (j < KEEP && active) {
+                const int n2 = r + INC * j;
+                float2 x[A];
+                inv_second<A, B, kPackedStrided>(n2, x, sm, lane, T);
+                float2* dst = q.u + tile * q.u_tstride + outer * q.ostride + lane;
+                const unsigned e = (unsigned)q.estride32;
+                float2 ksum = make_float2(0.f, 0.f);
+                MVSIM_UNROLL
+                for (int n1 = 0; n1 < A; ++n1) {
+                    const int o = n2 + n1 * B - q.crop0;                   // = INC * kz exactly
+                    if ((unsigned)o < (unsigned)q.n_src) {
+                        const unsigned kz = umulhi32((uint32_t)o, q.keep_magic);
+                        *at32(dst, kz, e) = x[n1];
+                        ksum.x += x[n1].x; ksum.y += x[n1].y;
+                    }
+                }
+                smh[(A + j) * T + lane] = ksum;
+            }
+        } else {
+            if (p == 0 && active) {
+                float2 s = make_float2(0.f, 0.f);
+                for (int k = 0; k < A; ++k) { s.x += smh[k * T + lane].x; s.y += smh[k * T + lane].y; }
+                for (int j = 0; j < KEEP; ++j) { s.x -= smh[(A + j) * T + lane].x; s.y -= smh[(A + j) * T + lane].y; }
+                q.u[tile * q.u_tstride + outer * q.ostride + lane + q.n_keep * q.estride] = s;
             }
         }
     }

@@ -67,6 +67,31 @@ struct EmuLauncher {
         }
         return 5;
     }
+    bool z_decimate(const FftSize&) const { return getenv("MVSIM_EMU_DECIMATE") != nullptr; }
+    int launch_zfused_dec(const FftSize& s, const ZFusedParams& q0, int tiles, int n_outer, int inc)
+    {
+        ZFusedParams q = q0;
+        std::vector<float2> d((size_t)s.n);
+        zfused_dec_table(s.n, q.crop0, q.n_src, d.data());
+        q.dtab = d.data();
+        ++decimated_launches;
+        switch (s.n) {
+#define MVSIM_X(n_, a_, b_) case n_: return inc == 3 ? dec<a_, b_, 3>(q, n_outer, tiles) : dec<a_, b_, 5>(q, n_outer, tiles);
+            MVSIM_FFT_SIZES(MVSIM_X)
+#undef MVSIM_X
+        }
+        return 5;
+    }
+    template <int A, int B, int INC> static int dec(const ZFusedParams& q, int n_outer, int tiles)
+    {
+        if constexpr (zfused_dec_ok(A, B, INC)) {
+            emulate<ZFusedDec<B, A, T, INC>>(q, n_outer, tiles);
+            return 0;
+        } else {
+            return 5;
+        }
+    }
+    static int decimated_launches;
     int launch_zfused(const FftSize& s, const ZFusedParams& q, int tiles, int n_outer)
     {
         if (q.h_mode)
@@ -83,6 +108,9 @@ struct EmuLauncher {
         return 5;
     }
 };
+
+int EmuLauncher::decimated_launches = 0;
+extern "C" int emu_decimated_launches() { return EmuLauncher::decimated_launches; }
 
 extern "C" int emu_plan(const int64_t dims[3], const int64_t kdims[3], int out[11], int max_line)
 {

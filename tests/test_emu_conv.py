@@ -165,3 +165,32 @@ def test_generated_butterflies_are_in_sync_with_the_generator(tmp_path):
     subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "gen_regfft.py"), str(a), str(b)])
     assert a.read_text() == open(os.path.join(CSRC, "fft", "regfft_gen.cuh")).read()
     assert b.read_text() == open(os.path.join(CSRC, "fft", "regfft_gen_packed.cuh")).read()
+
+
+@pytest.mark.parametrize("shape,kshape,inc", [
+    ((30, 6, 9), (7, 3, 4), 3),        # z line 36 = 6 x 6 -> ZFusedDec<6, 6, T, 3>, r = crop0 mod 3 = 0
+    ((45, 5, 8), (10, 2, 3), 3),       # 54 = 6 x 9 -> ZFusedDec<9, 6, T, 3>, even kernel: r = 0 (crop0 = 9)
+    ((46, 5, 8), (8, 2, 3), 3),        # 54 again with crop0 = 7: r = 1
+    ((80, 4, 9), (21, 3, 2), 5),       # 100 = 10 x 10 -> ZFusedDec<10, 10, T, 5>, crop0 = 20: r = 0
+    ((100, 3, 10), (19, 2, 3), 5),     # 120 = 10 x 12 -> ZFusedDec<12, 10, T, 5>, crop0 = 18: r = 3
+    ((101, 3, 20), (17, 1, 2), 5),     # 120, crop0 = 16: r = 1; partial last kx tile
+])
+def test_decimated_inverse_of_the_fused_z_pass(emu, oracle, monkeypatch, psf_spectrum_mode, request, shape, kshape, inc):
+    """EXPERIMENT for the next round (MVSIM_Z_DECIMATE): kept planes = whole columns of the exchange, pruned first inverse
+    half, second inverse half for the kept columns only, sum plane from a dot product with the crop's Dirichlet table."""
+    monkeypatch.setenv("MVSIM_EMU_DECIMATE", "1")
+    emu.emu_decimated_launches.restype = C.c_int
+    before = emu.emu_decimated_launches()
+    rng = np.random.default_rng(21)
+    vol = rng.random(shape, dtype=np.float32)
+    psf = rng.random(kshape, dtype=np.float32)
+    ref = oracle.convolve(vol, psf, "direct")
+    kept = ref[::inc]
+    nk = kept.shape[0]
+    out, s = _run(emu, vol, psf, keep_inc=inc, planes=nk + 1)
+    if "on-the-fly" in request.node.name:
+        assert emu.emu_decimated_launches() == before + 1       # the decimated kernel really ran
+    assert rel_err(out[:nk], kept) < 5e-6
+    dropped = ref.astype(np.float64).sum(axis=0) - kept.astype(np.float64).sum(axis=0)
+    assert rel_err(out[nk], dropped.astype(np.float32)) < 3e-5
+    assert s == pytest.approx(float(ref.astype(np.float64).sum()), rel=3e-6)
