@@ -148,10 +148,15 @@ struct CudaLauncher {
         return finish(fft_launch(inverse ? FFT_SINV : FFT_SFWD, lanes, s.n, &q, gx, gy, ctx->stream), "strided pass");
     }
     // EXPERIMENT (MVSIM_Z_DECIMATE=1): decimated inverse of the whole-view fused z pass, see ZFusedDec in fft/line_fft.cuh
+    // 0 = off (default), 1 = ZFusedDec (both sides in the (b, a) split), 2 = ZFusedDecW (forward side in the planner's split)
+    static int z_decimate_mode()
+    {
+        static const int mode = MVSIM_PACKED_FFT != 0 ? env_int("MVSIM_Z_DECIMATE", 0) : 0;
+        return mode;
+    }
     bool z_decimate(const FftSize& s) const
     {
-        static const bool on = env_int("MVSIM_Z_DECIMATE", 0) != 0 && MVSIM_PACKED_FFT != 0;
-        return on && s.n >= kDecMinLine && s.n <= kDecMaxLine;
+        return z_decimate_mode() != 0 && s.n >= kDecMinLine && s.n <= kDecMaxLine;
     }
     int launch_zfused_dec(const FftSize& s, const ZFusedParams& q0, int n_tiles, int n_outer, int inc)
     {
@@ -169,13 +174,16 @@ struct CudaLauncher {
         int r;
         {
             StageTimer t(ctx, MVSIM_T_FFT_ZFUSED);
-            q.use_tma = (zfused_otf_tma_fits(s.b, s.a, lanes, q.k_src) && make_h_tensor_map(q.p2, lanes, n_tiles, q.k_src, n_outer, q.h_tmap)) ? 1 : 0;
+            const bool wide = z_decimate_mode() == 2;
+            const bool fits = wide ? zfused_decw_tma_fits(s.a, s.b, lanes, q.k_src) : zfused_otf_tma_fits(s.b, s.a, lanes, q.k_src);
+            q.use_tma = (fits && make_h_tensor_map(q.p2, lanes, n_tiles, q.k_src, n_outer, q.h_tmap)) ? 1 : 0;
             const int zthreads = lanes * (s.a > s.b ? s.a : s.b);
             static const int zdist2 = prefetch_dist("MVSIM_Z_PREFETCH", 2), zdist4 = prefetch_dist("MVSIM_Z_PREFETCH", 4), zdist1 = prefetch_dist("MVSIM_Z_PREFETCH", 1);
             const int zdist = zthreads <= 160 ? zdist4 : (zthreads <= 288 ? zdist2 : zdist1);
             q.grid_x = n_outer; q.grid_y = n_tiles;
             q.prefetch_dist = (q.use_tma && zdist > 0 && make_h_tensor_map(q.u, lanes, n_tiles, q.zg, n_outer, q.u_tmap)) ? zdist : 0;
-            r = finish(fft_launch(inc == 3 ? FFT_ZFUSED_DEC3 : FFT_ZFUSED_DEC5, lanes, s.n, &q, (unsigned)n_outer, (unsigned)n_tiles, ctx->stream),
+            const int kind = wide ? (inc == 3 ? FFT_ZFUSED_DECW3 : FFT_ZFUSED_DECW5) : (inc == 3 ? FFT_ZFUSED_DEC3 : FFT_ZFUSED_DEC5);
+            r = finish(fft_launch(kind, lanes, s.n, &q, (unsigned)n_outer, (unsigned)n_tiles, ctx->stream),
                        "fused z pass (decimated inverse)");
         }
         dev_free(ctx, d_tab);

@@ -54,10 +54,33 @@ template <class K> static int launch(const void* params, unsigned gx, unsigned g
     return (int)cudaGetLastError();
 }
 
+#ifndef MVSIM_DEC_UNIT
+#define MVSIM_DEC_UNIT 0
+#endif
+
 template <int A, int B> static int launch_size(int kind, const void* params, unsigned gx, unsigned gy, cudaStream_t s)
 {
     constexpr int R = x_rows_per_block(A, B);
     constexpr int T = MVSIM_LANES;
+    (void)R;
+#if MVSIM_DEC_UNIT
+    // the experimental decimated fused z kernels live in their own translation units (build time of the main ones)
+    constexpr bool built = A * B >= kDecMinLine && A * B <= kDecMaxLine;
+    switch (kind) {
+    case FFT_ZFUSED_DEC3:
+        if constexpr (built && zfused_dec_ok(A, B, 3)) return launch<ZFusedDec<B, A, T, 3>>(params, gx, gy, s);
+        break;
+    case FFT_ZFUSED_DEC5:
+        if constexpr (built && zfused_dec_ok(A, B, 5)) return launch<ZFusedDec<B, A, T, 5>>(params, gx, gy, s);
+        break;
+    case FFT_ZFUSED_DECW3:
+        if constexpr (built && zfused_dec_ok(A, B, 3)) return launch<ZFusedDecW<A, B, T, 3>>(params, gx, gy, s);
+        break;
+    case FFT_ZFUSED_DECW5:
+        if constexpr (built && zfused_dec_ok(A, B, 5)) return launch<ZFusedDecW<A, B, T, 5>>(params, gx, gy, s);
+        break;
+    }
+#else
     switch (kind) {
 #if MVSIM_LANES == 8
     case FFT_XFWD: return launch<XFwd<A, B, R>>(params, gx, gy, s);
@@ -67,13 +90,8 @@ template <int A, int B> static int launch_size(int kind, const void* params, uns
     case FFT_SINV: return launch<StridedInv<A, B, T>>(params, gx, gy, s);
     case FFT_ZFUSED: return launch<ZFused<A, B, T>>(params, gx, gy, s);
     case FFT_ZFUSED_OTF: return launch<ZFusedOTF<A, B, T>>(params, gx, gy, s);
-    case FFT_ZFUSED_DEC3:
-        if constexpr (zfused_dec_ok(A, B, 3) && A * B >= kDecMinLine && A * B <= kDecMaxLine) return launch<ZFusedDec<B, A, T, 3>>(params, gx, gy, s);
-        break;
-    case FFT_ZFUSED_DEC5:
-        if constexpr (zfused_dec_ok(A, B, 5) && A * B >= kDecMinLine && A * B <= kDecMaxLine) return launch<ZFusedDec<B, A, T, 5>>(params, gx, gy, s);
-        break;
     }
+#endif
     return (int)cudaErrorInvalidValue;
 }
 
@@ -92,7 +110,11 @@ template <int A, int B> static int launch_size(int kind, const void* params, uns
 #define MVSIM_GROUP_SIZES(X) MVSIM_FFT_SIZES_G4(X)
 #endif
 
+#if MVSIM_DEC_UNIT
+#define MVSIM_FN MVSIM_CAT(MVSIM_CAT(MVSIM_CAT(fft_launch_dec_g, MVSIM_GROUP), _t), MVSIM_LANES)
+#else
 #define MVSIM_FN MVSIM_CAT(MVSIM_CAT(MVSIM_CAT(fft_launch_g, MVSIM_GROUP), _t), MVSIM_LANES)
+#endif
 int MVSIM_FN(int kind, int n, const void* params, unsigned gx, unsigned gy, cudaStream_t s)
 {
     switch (n) {

@@ -77,6 +77,7 @@ struct EmuLauncher {
         ++decimated_launches;
         switch (s.n) {
 #define MVSIM_X(n_, a_, b_) case n_: return inc == 3 ? dec<a_, b_, 3>(q, n_outer, tiles) : dec<a_, b_, 5>(q, n_outer, tiles);
+
             MVSIM_FFT_SIZES(MVSIM_X)
 #undef MVSIM_X
         }
@@ -85,7 +86,9 @@ struct EmuLauncher {
     template <int A, int B, int INC> static int dec(const ZFusedParams& q, int n_outer, int tiles)
     {
         if constexpr (zfused_dec_ok(A, B, INC)) {
-            emulate<ZFusedDec<B, A, T, INC>>(q, n_outer, tiles);
+            const char* mode = getenv("MVSIM_EMU_DECIMATE");
+            if (mode && mode[0] == '2') emulate<ZFusedDecW<A, B, T, INC>>(q, n_outer, tiles);
+            else emulate<ZFusedDec<B, A, T, INC>>(q, n_outer, tiles);
             return 0;
         } else {
             return 5;

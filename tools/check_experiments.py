@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Next-round A/B of the two experiments that were written at the end of round 1 without GPU time left:
-MVSIM_Z_DECIMATE=1 (ZFusedDec: decimated inverse in the fused z pass) and MVSIM_ROT_PFWARP=<rows> (prefetch warp in
+MVSIM_Z_DECIMATE=1 / 2 (ZFusedDec / ZFusedDecW: decimated inverse in the fused z pass) and MVSIM_ROT_PFWARP=<rows> (prefetch warp in
 rotate_attenuate).  Runs tools/time_view.py in sub-processes (the knobs are read once per process), prints the stage
 times and checks that the noise-free checksums agree.  NOT a test: run it on the GPU box,
     python tools/check_experiments.py [reps]
@@ -12,7 +12,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 reps = sys.argv[1] if len(sys.argv) > 1 else "12"
-variants = [("default", {}), ("z decimate", {"MVSIM_Z_DECIMATE": "1"}), ("rotate pfwarp 8", {"MVSIM_ROT_PFWARP": "8"}),
+variants = [("default", {}), ("z decimate (b,a)", {"MVSIM_Z_DECIMATE": "1"}), ("z decimate wide", {"MVSIM_Z_DECIMATE": "2"}), ("rotate pfwarp 8", {"MVSIM_ROT_PFWARP": "8"}),
             ("rotate pfwarp 16", {"MVSIM_ROT_PFWARP": "16"}), ("rotate pfwarp 32", {"MVSIM_ROT_PFWARP": "32"})]
 sums = {}
 for name, env in variants:
