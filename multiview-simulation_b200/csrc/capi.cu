@@ -354,6 +354,7 @@ int mvsim_ctx_destroy(mvsim_ctx* ctx)
     Activate act(ctx);
     cudaStreamSynchronize(ctx->stream);
     for (auto& kv : ctx->tables) cudaFree(kv.second.tw);
+    for (auto& kv : ctx->dec_tables) cudaFree(kv.second);
     for (auto& ev : ctx->events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
     for (auto& ev : ctx->pool) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
     cudaFree(ctx->d_scalars);

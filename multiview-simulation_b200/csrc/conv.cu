@@ -5,6 +5,7 @@
 
 #include <string.h>
 
+#include <array>
 #include <vector>
 
 #include "ctx.h"
@@ -71,26 +72,45 @@ static int env_int(const char* name, int dflt)
     return v ? atoi(v) : dflt;
 }
 
-// L2 prefetch distance of the forward passes, in CTAs of launch order: a quarter of the CTAs resident on the device, i.e.
+// L2 prefetch distance of the passes, in CTAs of launch order: a quarter of the CTAs resident on the device, i.e.
 // the target CTA starts ~2 us after the prefetch was issued.  Measured on B200, config 3 (profiles/r01_notes.md): y forward
 // 1.04 ms without, 0.83 at 74-100, 0.90 at 18 or 222, 1.13 at 592 (prefetched lines are evicted by the pass's own stores
-// before they are used); x forward 1.09 -> 0.95 for 28..222; fused z 2.61 -> 2.49 for 36..592.  The environment variable
-// overrides (0 switches the prefetch off).
-static int prefetch_dist(const char* env, int ctas_per_sm)
+// before they are used); x forward 1.09 -> 0.95 for 28..222; fused z 2.61 -> 2.49 for 36..592.  MVSIM_L2_PREFETCH=0
+// switches all of them off (A/B runs).
+static int prefetch_dist(int ctas_per_sm)
 {
     static const int sms = [] {
         int dev = 0, n = 0;
         if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 148;
         return n;
     }();
+    static const bool on = env_int("MVSIM_L2_PREFETCH", 1) != 0;
     const int d = ctas_per_sm * sms / 4;
-    return env_int(env, d > 1 ? d : 1);
+    return on ? (d > 1 ? d : 1) : 0;
 }
 
 static bool otf_default()
 {
     static const bool on = getenv("MVSIM_H_MATERIALIZE") == nullptr;   // default: PSF spectrum computed inside the fused z pass
     return on;
+}
+
+// D table of the decimated fused z pass (zfused_dec_table, fft/conv_driver.h), built once per (n, crop0, n_src) and kept in the
+// context like the twiddle tables (synchronous upload from pageable memory: the host vector may die right after)
+static int get_dec_table(mvsim_ctx* ctx, int n, int crop0, int n_src, const float2** out)
+{
+    const std::array<int, 3> key = { n, crop0, n_src };
+    auto it = ctx->dec_tables.find(key);
+    if (it != ctx->dec_tables.end()) { *out = it->second; return MVSIM_OK; }
+    std::vector<float2> h((size_t)n);
+    zfused_dec_table(n, crop0, n_src, h.data());
+    float2* d = nullptr;
+    MVSIM_CUDA(ctx, cudaMalloc((void**)&d, sizeof(float2) * (size_t)n));
+    const cudaError_t e = cudaMemcpy(d, h.data(), sizeof(float2) * (size_t)n, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(d); return cuda_fail(ctx, e, "decimation table upload"); }
+    ctx->dec_tables[key] = d;
+    *out = d;
+    return MVSIM_OK;
 }
 
 struct CudaLauncher {
@@ -115,8 +135,8 @@ struct CudaLauncher {
     {
         XParams q = q0;
         // rows of a later CTA prefetched into the L2 (16-byte granularity of the bulk prefetch: X % 4 == 0)
-        static const int xdist = prefetch_dist("MVSIM_X_PREFETCH", 3);
-        static const int xidist = prefetch_dist("MVSIM_XI_PREFETCH", 3);
+        static const int xdist = prefetch_dist(3);
+        static const int xidist = prefetch_dist(3);
         if (inverse) q.prefetch_dist = ((s.n * 8) % 16 == 0 && (reinterpret_cast<uintptr_t>(q.cin) & 15) == 0) ? xidist : 0;
         else q.prefetch_dist = (!psf_phase && q.X % 4 == 0 && (reinterpret_cast<uintptr_t>(q.rin) & 15) == 0) ? xdist : 0;
         StageTimer t(ctx, psf_phase ? MVSIM_T_PSF : (inverse ? MVSIM_T_FFT_XINV : MVSIM_T_FFT_XFWD));
@@ -127,7 +147,7 @@ struct CudaLauncher {
         StridedParams q = q0;
         strided_fill_e32(q, s.n);
         const int threads = lanes * (s.a > s.b ? s.a : s.b);
-        static const int ydist2 = prefetch_dist("MVSIM_Y_PREFETCH", 2), ydist4 = prefetch_dist("MVSIM_Y_PREFETCH", 4), ydist1 = prefetch_dist("MVSIM_Y_PREFETCH", 1);
+        static const int ydist2 = prefetch_dist(2), ydist4 = prefetch_dist(4), ydist1 = prefetch_dist(1);
         const int ydist = threads <= 160 ? ydist4 : (threads <= 288 ? ydist2 : ydist1);      // resident CTAs per SM: min_blocks() in fft_group.cu
         // forward image pass over row-major rows [outer][n_src][kx_count] (in_estride == kx_count, grid = tiles x outer)
         if (!inverse && !psf_phase && ydist > 0 && q.n_peers <= 1 && !q.swap_grid && q.in_tile_global && q.in_estride == q.kx_count &&
@@ -135,7 +155,7 @@ struct CudaLauncher {
             make_rows_tensor_map(q.in, lanes, q.kx_count, q.n_src, n_outer, q.in_tmap)) {
             q.prefetch_dist = ydist; q.grid_x = n_tiles; q.grid_y = n_outer;
         }
-        static const int yidist2 = prefetch_dist("MVSIM_YI_PREFETCH", 2), yidist4 = prefetch_dist("MVSIM_YI_PREFETCH", 4), yidist1 = prefetch_dist("MVSIM_YI_PREFETCH", 1);
+        static const int yidist2 = prefetch_dist(2), yidist4 = prefetch_dist(4), yidist1 = prefetch_dist(1);
         const int yidist = threads <= 160 ? yidist4 : (threads <= 288 ? yidist2 : yidist1);
         // inverse pass over tile-major input [tiles][outer][n][T] (one GPU): a CTA's input is one contiguous range
         if (inverse && yidist > 0 && q.n_peers <= 1 && !q.swap_grid && q.in_estride == lanes && q.in_ostride == (long long)s.n * lanes &&
@@ -147,47 +167,26 @@ struct CudaLauncher {
         const unsigned gx = q.swap_grid ? (unsigned)n_outer : tiles, gy = q.swap_grid ? tiles : (unsigned)n_outer;
         return finish(fft_launch(inverse ? FFT_SINV : FFT_SFWD, lanes, s.n, &q, gx, gy, ctx->stream), "strided pass");
     }
-    // EXPERIMENT (MVSIM_Z_DECIMATE=1): decimated inverse of the whole-view fused z pass, see ZFusedDec in fft/line_fft.cuh
-    // 0 = off (default), 1 = ZFusedDec (both sides in the (b, a) split), 2 = ZFusedDecW (forward side in the planner's split)
-    static int z_decimate_mode()
-    {
-        static const int mode = MVSIM_PACKED_FFT != 0 ? env_int("MVSIM_Z_DECIMATE", 0) : 0;
-        return mode;
-    }
+    // Decimated inverse of the whole-view fused z pass (ZFusedDec in fft/line_fft.cuh): the default wherever the planner's split
+    // allows it (measured 2.49 -> 2.13 ms at config 3).  MVSIM_Z_DECIMATE=0 selects the full inverse (ZFusedOTF) for A/B runs.
     bool z_decimate(const FftSize& s) const
     {
-        return z_decimate_mode() != 0 && s.n >= kDecMinLine && s.n <= kDecMaxLine;
+        static const bool on = MVSIM_PACKED_FFT != 0 && env_int("MVSIM_Z_DECIMATE", 1) != 0;
+        return on && s.n >= kDecMinLine && s.n <= kDecMaxLine;
     }
     int launch_zfused_dec(const FftSize& s, const ZFusedParams& q0, int n_tiles, int n_outer, int inc)
     {
         ZFusedParams q = q0;
-        // D table: host closed form, staged copy (pageable source: the call returns once the bytes are staged), stream-ordered free
-        float2* d_tab = nullptr;
-        MVSIM_TRY(dev_alloc(ctx, (void**)&d_tab, sizeof(float2) * (size_t)s.n));
-        {
-            std::vector<float2> h((size_t)s.n);
-            zfused_dec_table(s.n, q.crop0, q.n_src, h.data());
-            const cudaError_t e = cudaMemcpyAsync(d_tab, h.data(), sizeof(float2) * (size_t)s.n, cudaMemcpyHostToDevice, ctx->stream);
-            if (e != cudaSuccess) { dev_free(ctx, d_tab); return cuda_fail(ctx, e, "decimation table upload"); }
-        }
-        q.dtab = d_tab;
-        int r;
-        {
-            StageTimer t(ctx, MVSIM_T_FFT_ZFUSED);
-            const bool wide = z_decimate_mode() == 2;
-            const bool fits = wide ? zfused_decw_tma_fits(s.a, s.b, lanes, q.k_src) : zfused_otf_tma_fits(s.b, s.a, lanes, q.k_src);
-            q.use_tma = (fits && make_h_tensor_map(q.p2, lanes, n_tiles, q.k_src, n_outer, q.h_tmap)) ? 1 : 0;
-            const int zthreads = lanes * (s.a > s.b ? s.a : s.b);
-            static const int zdist2 = prefetch_dist("MVSIM_Z_PREFETCH", 2), zdist4 = prefetch_dist("MVSIM_Z_PREFETCH", 4), zdist1 = prefetch_dist("MVSIM_Z_PREFETCH", 1);
-            const int zdist = zthreads <= 160 ? zdist4 : (zthreads <= 288 ? zdist2 : zdist1);
-            q.grid_x = n_outer; q.grid_y = n_tiles;
-            q.prefetch_dist = (q.use_tma && zdist > 0 && make_h_tensor_map(q.u, lanes, n_tiles, q.zg, n_outer, q.u_tmap)) ? zdist : 0;
-            const int kind = wide ? (inc == 3 ? FFT_ZFUSED_DECW3 : FFT_ZFUSED_DECW5) : (inc == 3 ? FFT_ZFUSED_DEC3 : FFT_ZFUSED_DEC5);
-            r = finish(fft_launch(kind, lanes, s.n, &q, (unsigned)n_outer, (unsigned)n_tiles, ctx->stream),
-                       "fused z pass (decimated inverse)");
-        }
-        dev_free(ctx, d_tab);
-        return r;
+        MVSIM_TRY(get_dec_table(ctx, s.n, q.crop0, q.n_src, &q.dtab));       // cached per (n, crop0, n_src) in the context
+        StageTimer t(ctx, MVSIM_T_FFT_ZFUSED);
+        q.use_tma = (zfused_otf_tma_fits(s.b, s.a, lanes, q.k_src) && make_h_tensor_map(q.p2, lanes, n_tiles, q.k_src, n_outer, q.h_tmap)) ? 1 : 0;
+        const int zthreads = lanes * (s.a > s.b ? s.a : s.b);
+        static const int zdist2 = prefetch_dist(2), zdist4 = prefetch_dist(4), zdist1 = prefetch_dist(1);
+        const int zdist = zthreads <= 160 ? zdist4 : (zthreads <= 288 ? zdist2 : zdist1);
+        q.grid_x = n_outer; q.grid_y = n_tiles;
+        q.prefetch_dist = (q.use_tma && zdist > 0 && make_h_tensor_map(q.u, lanes, n_tiles, q.zg, n_outer, q.u_tmap)) ? zdist : 0;
+        return finish(fft_launch(inc == 3 ? FFT_ZFUSED_DEC3 : FFT_ZFUSED_DEC5, lanes, s.n, &q, (unsigned)n_outer, (unsigned)n_tiles, ctx->stream),
+                      "fused z pass (decimated inverse)");
     }
     int launch_zfused(const FftSize& s, const ZFusedParams& q0, int n_tiles, int n_outer)
     {
@@ -198,7 +197,7 @@ struct CudaLauncher {
             // PSF tile [KZ rows] through the TMA unit into its own shared-memory area
             q.use_tma = (zfused_otf_tma_fits(s.a, s.b, lanes, q.k_src) && make_h_tensor_map(q.p2, lanes, n_tiles, q.k_src, n_outer, q.h_tmap)) ? 1 : 0;
             const int zthreads = lanes * (s.a > s.b ? s.a : s.b);
-            static const int zdist2 = prefetch_dist("MVSIM_Z_PREFETCH", 2), zdist4 = prefetch_dist("MVSIM_Z_PREFETCH", 4), zdist1 = prefetch_dist("MVSIM_Z_PREFETCH", 1);
+            static const int zdist2 = prefetch_dist(2), zdist4 = prefetch_dist(4), zdist1 = prefetch_dist(1);
             const int zdist = zthreads <= 160 ? zdist4 : (zthreads <= 288 ? zdist2 : zdist1);
             q.grid_x = n_outer; q.grid_y = n_tiles;
             q.prefetch_dist = (q.use_tma && zdist > 0 && q.n_peers <= 1 && q.estride32 != 0 &&
@@ -364,6 +363,7 @@ int mvsim_slabconv_create(mvsim_ctx* ctx, const int64_t dims[3], const int64_t k
 int mvsim_slabconv_destroy(mvsim_ctx* ctx, mvsim_slabconv* p)
 {
     if (!p) return MVSIM_OK;
+    DeviceGuard guard(ctx ? ctx->device : 0);
     if (ctx) cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < p->n_opened; ++i) cudaIpcCloseMemHandle(p->opened[i]);
     for (int i = 0; i < p->n_owned; ++i) cudaFree(p->owned[i]);
@@ -446,9 +446,11 @@ int mvsim_slabconv_bind(mvsim_slabconv* p, void* send_buffer, void* recv_buffer)
     return MVSIM_OK;
 }
 
+// every entry point that launches kernels runs with the context's device current (the caller's current device may differ)
 #define MVSIM_SLAB_ENTER(ctx, p)                                                                   \
     if (!(ctx) || !(p)) return mvsim::set_error((ctx), MVSIM_EINVAL, "slabconv: null argument");   \
-    if (!(p)->send) return mvsim::set_error((ctx), MVSIM_EINVAL, "slabconv: bind the exchange buffers first")
+    if (!(p)->send) return mvsim::set_error((ctx), MVSIM_EINVAL, "slabconv: bind the exchange buffers first"); \
+    DeviceGuard guard__((ctx)->device)
 
 int mvsim_slabconv_prepare(mvsim_ctx* ctx, mvsim_slabconv* p, const float* d_psf, const float* d_img_slab)
 {

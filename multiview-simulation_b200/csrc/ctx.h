@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <array>
 #include <map>
 #include <string>
 #include <vector>
@@ -29,6 +30,7 @@ struct mvsim_ctx {
     std::string err;
     double* d_scalars;                       // [8] device doubles: sums, corrections
     std::map<int, mvsim_tables> tables;      // by complex line length
+    std::map<std::array<int, 3>, float2*> dec_tables;   // decimated fused z pass: D table by (n, crop0, n_src)
     int64_t launches;
     // profiling
     bool profiling;

@@ -143,7 +143,7 @@ template <class L> int conv_middle_z(L& l, const ConvPlan& pl, const SlabGeom& g
         zp.n_peers = ws.n_peers;
         for (int r = 0; r < ws.n_peers; ++r) zp.out_peers[r] = ws.peers_y[r];
     }
-    // experiment (launcher decides, off by default): decimated inverse when the kept planes are whole columns of the exchange
+    // decimated inverse when the kept planes are whole columns of the exchange (the launcher may veto: line length, A/B knob)
     if (pruned && l.h_on_the_fly && zp.estride32 != 0 && zfused_dec_ok(pl.sz.a, pl.sz.b, keep_inc) && l.z_decimate(pl.sz))
         return l.launch_zfused_dec(pl.sz, zp, g.tiles_own, pl.sy.n, keep_inc);
     return l.launch_zfused(pl.sz, zp, g.tiles_own, pl.sy.n);

@@ -64,7 +64,7 @@ template <int A, int B> static int launch_size(int kind, const void* params, uns
     constexpr int T = MVSIM_LANES;
     (void)R;
 #if MVSIM_DEC_UNIT
-    // the experimental decimated fused z kernels live in their own translation units (build time of the main ones)
+    // the decimated fused z kernels live in their own translation units (build time)
     constexpr bool built = A * B >= kDecMinLine && A * B <= kDecMaxLine;
     switch (kind) {
     case FFT_ZFUSED_DEC3:
@@ -72,12 +72,6 @@ template <int A, int B> static int launch_size(int kind, const void* params, uns
         break;
     case FFT_ZFUSED_DEC5:
         if constexpr (built && zfused_dec_ok(A, B, 5)) return launch<ZFusedDec<B, A, T, 5>>(params, gx, gy, s);
-        break;
-    case FFT_ZFUSED_DECW3:
-        if constexpr (built && zfused_dec_ok(A, B, 3)) return launch<ZFusedDecW<A, B, T, 3>>(params, gx, gy, s);
-        break;
-    case FFT_ZFUSED_DECW5:
-        if constexpr (built && zfused_dec_ok(A, B, 5)) return launch<ZFusedDecW<A, B, T, 5>>(params, gx, gy, s);
         break;
     }
 #else

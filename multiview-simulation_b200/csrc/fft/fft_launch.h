@@ -8,9 +8,9 @@
 namespace mvsim {
 
 enum FftKind { FFT_XFWD = 0, FFT_XINV = 1, FFT_SFWD = 2, FFT_SINV = 3, FFT_ZFUSED = 4, FFT_ZFUSED_OTF = 5,
-               FFT_ZFUSED_DEC3 = 6, FFT_ZFUSED_DEC5 = 7, FFT_ZFUSED_DECW3 = 8, FFT_ZFUSED_DECW5 = 9 };   // decimated inverse (experiment): the planner's (a, b) with 3 | a resp. 5 | a
+               FFT_ZFUSED_DEC3 = 6, FFT_ZFUSED_DEC5 = 7 };   // decimated inverse (ZFusedDec): the planner's (a, b) with 3 | a resp. 5 | a
 
-// the experimental decimated fused z kernels are built only for z lines of these lengths (build time): covers the BASELINE
+// the decimated fused z kernels are built only for z lines of these lengths (build time): covers the BASELINE
 // configs (339 -> 360 with inc 3, 639 -> 640 with inc 5)
 constexpr int kDecMinLine = 300, kDecMaxLine = 660;
 constexpr int kXThreadsTarget = 256; // x passes: rows per CTA = kXThreadsTarget / threads-per-line
@@ -25,7 +25,7 @@ int strided_lanes();
 #define MVSIM_DECL(g, t) int fft_launch_g##g##_t##t(int kind, int n, const void* params, unsigned gx, unsigned gy, cudaStream_t s);
 MVSIM_DECL(0, 8) MVSIM_DECL(1, 8) MVSIM_DECL(2, 8) MVSIM_DECL(3, 8) MVSIM_DECL(4, 8)
 #undef MVSIM_DECL
-// experimental decimated fused z kernels (kinds FFT_ZFUSED_DEC*): line lengths kDecMinLine..kDecMaxLine live in groups 1 and 2
+// decimated fused z kernels (kinds FFT_ZFUSED_DEC*): line lengths kDecMinLine..kDecMaxLine live in groups 1 and 2
 int fft_launch_dec_g1_t8(int kind, int n, const void* params, unsigned gx, unsigned gy, cudaStream_t s);
 int fft_launch_dec_g2_t8(int kind, int n, const void* params, unsigned gx, unsigned gy, cudaStream_t s);
 

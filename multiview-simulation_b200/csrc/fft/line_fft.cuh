@@ -682,8 +682,9 @@ template <int A_, int B_, int T_> struct ZFusedOTF : ZFused<A_, B_, T_> {
 };
 
 // ==============================================================================================
-// EXPERIMENT for the next round (MVSIM_Z_DECIMATE=1, off by default, emulated on the CPU but not yet measured on a GPU):
-// fused z pass of the whole-view call with a DECIMATED inverse.  extractSlices keeps z = 0, INC, 2 INC, ... (:206), i.e. the
+// Fused z pass of the whole-view call with a DECIMATED inverse (default wherever zfused_dec_ok() holds; measured on B200,
+// config 3: 2.49 -> 2.13 ms against ZFusedOTF, profiles/r02_experiments.txt; MVSIM_Z_DECIMATE=0 switches back for A/B runs).
+// extractSlices keeps z = 0, INC, 2 INC, ... (:206), i.e. the
 // padded outputs n = crop0 + INC kz.  With the split n = n1 B + n2 and INC | B these are exactly the columns
 // n2 = r (mod INC), r = crop0 mod INC, of the exchange, so
 //   - the first inverse half needs B/INC of its B outputs per thread (RegFFTPD: dead code removed by the generator),
@@ -881,226 +882,6 @@ template <int A_, int B_, int T_, int INC_> struct ZFusedDec : LineShape<A_, B_>
                 float2 s = make_float2(0.f, 0.f);
                 for (int k = 0; k < A; ++k) { s.x += smh[k * T + lane].x; s.y += smh[k * T + lane].y; }
                 for (int j = 0; j < KEEP; ++j) { s.x -= smh[(A + j) * T + lane].x; s.y -= smh[(A + j) * T + lane].y; }
-                q.u[tile * q.u_tstride + outer * q.ostride + lane + q.n_keep * q.estride] = s;
-            }
-        }
-    }
-};
-
-// Second form of the same experiment (MVSIM_Z_DECIMATE=2): the FORWARD side keeps the planner's split (a, b) (config 3:
-// 20 x 32 -- the gather and the first half of the image line, the longest phase, stay on 32 threads per line), the product
-// spectrum is parked in shared memory in natural order, and only the INVERSE side uses the split (b, a) in which the kept planes
-// are whole columns.  One more 640-element exchange per line than ZFusedDec, no 20-thread gather.
-//   A_, B_ = the planner's (a, b), INC | A_.
-constexpr int zfused_decw_exch(int a, int b, int t)
-{
-    const int f = a * (b | 1), i = b * (a | 1);
-    return ((f > i ? f : i) * t + 15) / 16 * 16;
-}
-constexpr int zfused_decw_smem_base(int a, int b, int t)
-{
-    return (zfused_decw_exch(a, b, t) + (a * b + kTmaBoxRows - 1) / kTmaBoxRows * kTmaBoxRows * t + 16) * (int)sizeof(float2);
-}
-inline bool zfused_decw_tma_fits(int a, int b, int t, int k_src)
-{
-    const int base = zfused_decw_smem_base(a, b, t), with = base + zfused_otf_psf_tile_bytes(k_src, t);
-    if (with > kSmemLimit) return false;
-    const int c0 = 233472 / (base + 1024), c1 = 233472 / (with + 1024);
-    return c1 >= (c0 < 4 ? c0 : 4);
-}
-
-template <int A_, int B_, int T_, int INC_> struct ZFusedDecW : LineShape<A_, B_> {
-    using S = LineShape<A_, B_>;
-    static constexpr int A = A_, B = B_, T = T_, INC = INC_;
-    static constexpr int AI = B_, BI = A_;        // inverse-side split: n = n1 BI + n2, k = k1 + AI k2
-    static_assert(BI % INC_ == 0 && BI / INC_ >= 2, "the kept outputs must be whole columns of the inverse-side exchange");
-    static constexpr int KEEP = BI / INC;
-    static constexpr int THREADS = T * S::P;
-    static constexpr int NPH = 7;
-    static constexpr int EXCH_ELEMS = zfused_decw_exch(A_, B_, T_);
-    static constexpr int H_ROWS = (S::N + kTmaBoxRows - 1) / kTmaBoxRows * kTmaBoxRows;
-    static constexpr int BAR_ELEMS = EXCH_ELEMS + H_ROWS * T;
-    static constexpr int PSF_ELEMS0 = BAR_ELEMS + 16;
-    static constexpr int SMEM_BYTES = PSF_ELEMS0 * (int)sizeof(float2);
-    static_assert(SMEM_BYTES == zfused_decw_smem_base(A_, B_, T_), "host-side shared memory formula out of sync");
-    static_assert(AI + KEEP <= S::N, "partial sums live in the parked-spectrum area");
-    using Params = ZFusedParams;
-    using State = NoState;
-    static int smem_bytes(const Params& q) { return SMEM_BYTES + (q.use_tma ? zfused_otf_psf_tile_bytes(q.k_src, T) : 0); }
-    static int smem_bytes_max() { const int m = SMEM_BYTES + H_ROWS * T * (int)sizeof(float2); return m < kSmemLimit ? m : kSmemLimit; }
-
-    // dot product with D, pruned first inverse half of the columns n2 = R + INC j, twiddle, store (inverse-side layout)
-    template <int R> static MVSIM_HD void inv_first_kept(int p, const float2 (&y)[BI], float2* sm, int lane, const float2* __restrict__ tw)
-    {
-        constexpr int BP = BI | 1;
-        float2 o[KEEP];
-        RegFFTPD<BI, INC, R>::run(y, o);
-        MVSIM_UNROLL
-        for (int j = 0; j < KEEP; ++j) {
-            const int n2 = R + INC * j;
-            const float2 v = n2 == 0 ? o[j] : cmulc(o[j], tw[n2 * p]);
-            sm[lane + (p * BP + n2) * T] = v;
-        }
-    }
-
-    template <int PH> static MVSIM_HD void phase(const Params& q, int bx, int by, int tid, float2* sm, State&)
-    {
-        const int lane = tid % T, p = tid / T;
-        const int tile = by, outer = bx;
-        const bool active = (tile + q.tile0) * T + lane < q.kx_count;
-        float2* smh = sm + EXCH_ELEMS;
-        const int r = q.crop0 % INC;
-        if (PH == 0) {
-#ifdef __CUDA_ARCH__
-            if (q.use_tma && tid == 0) {
-                uint64_t* bar = reinterpret_cast<uint64_t*>(sm + BAR_ELEMS);
-                const int nbox = (q.k_src + kTmaBoxRows - 1) / kTmaBoxRows;
-                mbar_init(bar, 1);
-                mbar_expect_tx(bar, (unsigned)(nbox * kTmaBoxRows * T * sizeof(float2)));
-                for (int b = 0; b < nbox; ++b) tma_load_4d(sm + PSF_ELEMS0 + b * kTmaBoxRows * T, q.h_tmap, 0, outer, b * kTmaBoxRows, tile, bar);
-                if (q.prefetch_dist > 0) {
-                    const int lin = by * q.grid_x + bx + q.prefetch_dist;
-                    const int t2 = lin / q.grid_x, o2 = lin - t2 * q.grid_x;
-                    if (t2 < q.grid_y)
-                        for (int z = 0; z < q.n_src; z += kTmaBoxRows) tma_prefetch_4d(q.u_tmap, 0, o2, z, t2);
-                }
-            }
-#endif
-            if (p < B && active) {
-                float2 x[A];
-                const float2* __restrict__ src = q.u + tile * q.u_tstride + outer * q.ostride + lane;
-                int idx[A];
-                if (q.ext == EXT_MIRROR1) {
-                    MVSIM_UNROLL
-                    for (int n1 = 0; n1 < A; ++n1) idx[n1] = mirror_once(p + n1 * B - q.left, q.n_src);
-                } else {
-                    MVSIM_UNROLL
-                    for (int n1 = 0; n1 < A; ++n1) idx[n1] = mirror_single(p + n1 * B - q.left, q.n_src);
-                }
-                const unsigned e = (unsigned)q.estride32;
-                MVSIM_UNROLL
-                for (int n1 = 0; n1 < A; ++n1) x[n1] = *at32(src, (unsigned)idx[n1], e);
-                fwd_first<A, B, kPackedStrided>(p, x, sm, lane, T, q.tw);
-            }
-        } else if (PH == 1) {
-            if (p < A && active) {
-                float2 y[B];
-                fwd_second<A, B, kPackedStrided>(p, y, sm, lane, T);
-                MVSIM_UNROLL
-                for (int k2 = 0; k2 < B; ++k2) smh[(p + A * k2) * T + lane] = y[k2];     // natural order; own slots
-            }
-        } else if (PH == 2) {
-            constexpr int K = RegSelZ<A, kPackedStrided>::K;
-            const bool pruned = q.k_src <= K * B;
-#ifdef __CUDA_ARCH__
-            if (q.use_tma) {
-                mbar_wait(reinterpret_cast<uint64_t*>(sm + BAR_ELEMS), 0);
-                if (p < B && active) {
-                    const float2* tilep = sm + PSF_ELEMS0;
-                    const int rows = (q.k_src + kTmaBoxRows - 1) / kTmaBoxRows * kTmaBoxRows;
-                    float2 x[A];
-                    if (pruned) {
-                        MVSIM_UNROLL
-                        for (int n1 = 0; n1 < K; ++n1) {
-                            const int n = p + n1 * B;
-                            x[n1] = n < rows ? tilep[n * T + lane] : make_float2(0.f, 0.f);
-                        }
-                        fwd_first_zext<A, B, kPackedStrided>(p, x, sm, lane, T, q.tw);
-                    } else {
-                        MVSIM_UNROLL
-                        for (int n1 = 0; n1 < A; ++n1) {
-                            const int n = p + n1 * B;
-                            x[n1] = n < rows ? tilep[n * T + lane] : make_float2(0.f, 0.f);
-                        }
-                        fwd_first<A, B, kPackedStrided>(p, x, sm, lane, T, q.tw);
-                    }
-                }
-            } else
-#endif
-            if (p < B && active) {
-                float2 x[A];
-                const float2* __restrict__ src = q.p2 + tile * q.p2_tstride + outer * q.ostride + lane;
-                if (pruned) {
-                    MVSIM_UNROLL
-                    for (int n1 = 0; n1 < K; ++n1) {
-                        const int n = p + n1 * B;
-                        const bool ok = n < q.k_src;
-                        const float2 v = src[(ok ? n : 0) * q.estride];
-                        x[n1] = ok ? v : make_float2(0.f, 0.f);
-                    }
-                    fwd_first_zext<A, B, kPackedStrided>(p, x, sm, lane, T, q.tw);
-                } else {
-                    MVSIM_UNROLL
-                    for (int n1 = 0; n1 < A; ++n1) {
-                        const int n = p + n1 * B;
-                        const bool ok = n < q.k_src;
-                        const float2 v = src[(ok ? n : 0) * q.estride];
-                        x[n1] = ok ? v : make_float2(0.f, 0.f);
-                    }
-                    fwd_first<A, B, kPackedStrided>(p, x, sm, lane, T, q.tw);
-                }
-            }
-        } else if (PH == 3) {
-            // PSF second half; the PRODUCT spectrum replaces the parked image spectrum (natural order, own slots)
-            if (p < A && active) {
-                float2 h[B];
-                fwd_second<A, B, kPackedStrided>(p, h, sm, lane, T);
-                MVSIM_UNROLL
-                for (int k2 = 0; k2 < B; ++k2) {
-                    float2* slot = smh + (p + A * k2) * T + lane;
-                    *slot = cmul(h[k2], *slot);
-                }
-            }
-        } else if (PH == 4) {
-            // inverse-side layout: thread k1 < AI holds Yhat[k1 + AI k2], k2 < BI
-            if (p < AI && active) {
-                float2 y[BI];
-                float2 acc = make_float2(0.f, 0.f);
-                MVSIM_UNROLL
-                for (int k2 = 0; k2 < BI; ++k2) {
-                    y[k2] = smh[(p + AI * k2) * T + lane];
-                    const float2 d = q.dtab[p + AI * k2];
-                    acc.x += y[k2].x * d.x - y[k2].y * d.y;
-                    acc.y += y[k2].x * d.y + y[k2].y * d.x;
-                }
-                smh[p * T + lane] = acc;        // own slot (k2 = 0)
-                if (INC == 3) {
-                    if (r == 0) inv_first_kept<0>(p, y, sm, lane, q.tw);
-                    else if (r == 1) inv_first_kept<1>(p, y, sm, lane, q.tw);
-                    else inv_first_kept<2>(p, y, sm, lane, q.tw);
-                } else {
-                    if (r == 0) inv_first_kept<0>(p, y, sm, lane, q.tw);
-                    else if (r == 1) inv_first_kept<1>(p, y, sm, lane, q.tw);
-                    else if (r == 2) inv_first_kept<2>(p, y, sm, lane, q.tw);
-                    else if (r == 3) inv_first_kept<(INC > 3 ? 3 : 0)>(p, y, sm, lane, q.tw);
-                    else inv_first_kept<(INC > 4 ? 4 : 0)>(p, y, sm, lane, q.tw);
-                }
-            }
-        } else if (PH == 5) {
-            const int j = tid / T;
-            if (j < KEEP && active) {
-                const int n2 = r + INC * j;
-                float2 x[AI];
-                inv_second<AI, BI, kPackedStrided>(n2, x, sm, lane, T);
-                float2* dst = q.u + tile * q.u_tstride + outer * q.ostride + lane;
-                const unsigned e = (unsigned)q.estride32;
-                float2 ksum = make_float2(0.f, 0.f);
-                MVSIM_UNROLL
-                for (int n1 = 0; n1 < AI; ++n1) {
-                    const int o = n2 + n1 * BI - q.crop0;                  // = INC * kz exactly
-                    if ((unsigned)o < (unsigned)q.n_src) {
-                        const unsigned kz = umulhi32((uint32_t)o, q.keep_magic);
-                        *at32(dst, kz, e) = x[n1];
-                        ksum.x += x[n1].x; ksum.y += x[n1].y;
-                    }
-                }
-                smh[(AI + j) * T + lane] = ksum;
-            }
-        } else {
-            if (p == 0 && active) {
-                float2 s = make_float2(0.f, 0.f);
-                for (int k = 0; k < AI; ++k) { s.x += smh[k * T + lane].x; s.y += smh[k * T + lane].y; }
-                for (int j = 0; j < KEEP; ++j) { s.x -= smh[(AI + j) * T + lane].x; s.y -= smh[(AI + j) * T + lane].y; }
                 q.u[tile * q.u_tstride + outer * q.ostride + lane + q.n_keep * q.estride] = s;
             }
         }

@@ -96,8 +96,10 @@ MVSIM_HD float fast_log(float a)
 #endif
 }
 
-// (0,1) float uniform from 32 random bits (24 significant)
-MVSIM_HD float u01f(uint32_t x) { return ((float)(x >> 8) + 0.5f) * 0x1.0p-24f; }
+// float uniform strictly inside (0,1) from the top 23 of 32 random bits: (m + 1/2) 2^-23, m < 2^23.  Every value
+// (2m + 1) 2^-24 <= 1 - 2^-24 is exactly representable; with 24 bits the "+ 0.5f" of m = 2^24 - 1 rounded to 2^24, i.e. u = 1.0f
+// with probability 2^-24 per draw.
+MVSIM_HD float u01f(uint32_t x) { return ((float)(x >> 9) + 0.5f) * 0x1.0p-23f; }
 
 // PTRS hat-function constants for one lambda (float32 everywhere on the fast path)
 struct PtrsParams { float lam, b, a, vr; };
@@ -188,9 +190,18 @@ MVSIM_HD bool poisson_fast(double lam_d, uint32_t ru, uint32_t rv, float& out)
         // inversion by sequential search: k = min { k : u <= sum_{j<=k} e^-lam lam^j / j! }
         const float lam = (float)lam_d;
         const float u = u01f(ru);
+        // The float32 CDF saturates just below 1 (0.9999998 .. 0.99999994 depending on lam) once p < ulp(s)/2: a u above that
+        // plateau ends the search at the first k whose term no longer changes the sum (the exact quantile lies within a
+        // couple of counts of it; such u have probability < 2e-7) instead of running on to the iteration cap.
         float p = fast_exp(-lam), s = p;
         int k = 0;
-        while (u > s && k < 64) { ++k; p *= fast_div(lam, (float)k); s += p; }
+        while (u > s && k < 64) {
+            ++k;
+            p *= fast_div(lam, (float)k);
+            const float s2 = s + p;
+            if (s2 == s) break;
+            s = s2;
+        }
         out = (float)k;
         return true;
     }

@@ -162,7 +162,7 @@ template <int VEC> __device__ __forceinline__ void vload(float (&d)[VEC], const 
 // arithmetic: offsets of taps that are masked off may wrap, the ones that are dereferenced are exact)
 template <int VEC, int U, bool IDX32> __global__ void __launch_bounds__(128) rotate_attenuate_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                                                         const RowTaps* __restrict__ tab, int X, int Y, int Z,
-                                                                                        double delta, int steps, int pf)
+                                                                                        double delta, int steps)
 {
     using V = typename VecT<VEC>::type;
     const int XV = X / VEC;
@@ -180,27 +180,6 @@ template <int VEC, int U, bool IDX32> __global__ void __launch_bounds__(128) rot
     for (; s + U <= steps; s += U, y -= U) {
         float t00[U][VEC], t10[U][VEC], t11[U][VEC], t01[U][VEC];
         RowTaps tp[U];
-#ifdef __CUDA_ARCH__
-        if (pf > 0 && threadIdx.x == 0) {
-            // one thread asks for the source-row segments this CTA will gather `pf` rows from now (L2 prefetch, whole segments:
-            // the CTA's columns are contiguous in x -- the host enables this only when a CTA never straddles two planes)
-#pragma unroll
-            for (int j = 0; j < U; ++j) {
-                const int yy = y - j - pf;
-                if (yy >= 0) {
-                    const RowTaps t = trow[yy];
-                    const bool y0 = (unsigned)t.iy < (unsigned)Y, y1 = (unsigned)(t.iy + 1) < (unsigned)Y;
-                    const bool z0 = (unsigned)t.iz < (unsigned)Z, z1 = (unsigned)(t.iz + 1) < (unsigned)Z;
-                    const long long r = (long long)x0 + (long long)X * t.iy + (long long)X * Y * t.iz;
-                    const unsigned bytes = (unsigned)(blockDim.x * VEC * sizeof(float));
-                    if (y0 && z0) bulk_prefetch_l2(in + r, bytes);
-                    if (y1 && z0) bulk_prefetch_l2(in + r + X, bytes);
-                    if (y1 && z1) bulk_prefetch_l2(in + r + X + (long long)X * Y, bytes);
-                    if (y0 && z1) bulk_prefetch_l2(in + r + (long long)X * Y, bytes);
-                }
-            }
-        }
-#endif
 #pragma unroll
         for (int j = 0; j < U; ++j) tp[j] = trow[y - j];
 #pragma unroll
@@ -256,110 +235,6 @@ template <int VEC, int U, bool IDX32> __global__ void __launch_bounds__(128) rot
     for (; y >= 0; --y) *reinterpret_cast<V*>(out + (Off)(obase + sy * (Off)y)) = *reinterpret_cast<V*>(zero);
 }
 
-// EXPERIMENT for the next round (MVSIM_ROT_PFWARP=<rows>, off by default, not yet measured): the same march with a FIFTH warp
-// per CTA whose lane 0 only issues L2 prefetches (cp.async.bulk.prefetch.L2) for the source-row segments the four marching
-// warps will gather `pf` rows later, paced by a progress counter in shared memory.  The in-thread variant above lost time
-// because the prefetching thread's warp fell behind in a single-wave grid; here the marching warps do no extra work.
-// float4 columns, 2 rows per iteration, 32-bit offsets; the host launches it only when a CTA stays inside one row of one plane.
-__global__ void __launch_bounds__(160) rotate_attenuate_pfwarp_kernel(const float* __restrict__ in, float* __restrict__ out,
-                                                                      const RowTaps* __restrict__ tab, int X, int Y, int Z,
-                                                                      double delta, int steps, int pf)
-{
-    constexpr int VEC = 4, U = 2, CT = 128;
-    __shared__ int progress;                 // rows consumed by warp 0
-    if (threadIdx.x == 0) progress = 0;
-    __syncthreads();
-    const int XV = X / VEC;
-    const long long col0 = (long long)blockIdx.x * CT;
-    if (threadIdx.x >= CT) {
-#ifdef __CUDA_ARCH__
-        if (threadIdx.x == CT && col0 < (long long)XV * Z) {
-            const int x0 = (int)(col0 % XV) * VEC, z = (int)(col0 / XV);
-            const RowTaps* trow = tab + (long long)Y * z;
-            const unsigned bytes = (unsigned)(CT * VEC * sizeof(float));
-            for (int k = 0; k < steps; ++k) {            // k-th row of the march is y = Y - 1 - k
-                while (k - pf > *(volatile int*)&progress) __nanosleep(200);
-                const RowTaps t = trow[Y - 1 - k];
-                const bool y0 = (unsigned)t.iy < (unsigned)Y, y1 = (unsigned)(t.iy + 1) < (unsigned)Y;
-                const bool z0 = (unsigned)t.iz < (unsigned)Z, z1 = (unsigned)(t.iz + 1) < (unsigned)Z;
-                const long long r = (long long)x0 + (long long)X * t.iy + (long long)X * Y * t.iz;
-                if (y0 && z0) bulk_prefetch_l2(in + r, bytes);
-                if (y1 && z0) bulk_prefetch_l2(in + r + X, bytes);
-                if (y1 && z1) bulk_prefetch_l2(in + r + X + (long long)X * Y, bytes);
-                if (y0 && z1) bulk_prefetch_l2(in + r + (long long)X * Y, bytes);
-            }
-        }
-#endif
-        return;
-    }
-    const long long col = col0 + threadIdx.x;
-    if (col >= (long long)XV * Z) return;
-    const int x0 = (int)(col % XV) * VEC, z = (int)(col / XV);
-    const unsigned sy = (unsigned)X, sz = (unsigned)X * (unsigned)Y;
-    const RowTaps* trow = tab + (long long)Y * z;
-    const unsigned obase = (unsigned)x0 + sz * (unsigned)z;
-    double n[VEC];
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) n[i] = 1.0;
-    int y = Y - 1, s = 0;
-    for (; s + U <= steps; s += U, y -= U) {
-        float t00[U][VEC], t10[U][VEC], t11[U][VEC], t01[U][VEC];
-        RowTaps tp[U];
-#pragma unroll
-        for (int j = 0; j < U; ++j) tp[j] = trow[y - j];
-#pragma unroll
-        for (int j = 0; j < U; ++j) {
-            const int iy = tp[j].iy, iz = tp[j].iz;
-            const bool y0 = (unsigned)iy < (unsigned)Y, y1 = (unsigned)(iy + 1) < (unsigned)Y;
-            const bool z0 = (unsigned)iz < (unsigned)Z, z1 = (unsigned)(iz + 1) < (unsigned)Z;
-            const unsigned r = (unsigned)x0 + sy * (unsigned)iy + sz * (unsigned)iz;
-            vload<VEC>(t00[j], in + r, y0 && z0);
-            vload<VEC>(t10[j], in + (unsigned)(r + sy), y1 && z0);
-            vload<VEC>(t11[j], in + (unsigned)(r + sy + sz), y1 && z1);
-            vload<VEC>(t01[j], in + (unsigned)(r + sz), y0 && z1);
-        }
-#pragma unroll
-        for (int j = 0; j < U; ++j) {
-            float res[VEC];
-#pragma unroll
-            for (int i = 0; i < VEC; ++i) {
-                const float v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(t00[j][i], tp[j].w00), __fmul_rn(t10[j][i], tp[j].w10)),
-                                                    __fmul_rn(t11[j][i], tp[j].w11)), __fmul_rn(t01[j][i], tp[j].w01));
-                const double dv = (double)v;
-                const double phi = __dmul_rn(__dmul_rn(dv, delta), n[i]);
-                n[i] = fmax(__dsub_rn(n[i], phi), 0.0);
-                res[i] = (float)__dmul_rn(dv, n[i]);
-            }
-            *reinterpret_cast<float4*>(out + (unsigned)(obase + sy * (unsigned)(y - j))) = *reinterpret_cast<float4*>(res);
-        }
-        if (threadIdx.x == 0) *(volatile int*)&progress = s + U;
-    }
-    if (threadIdx.x == 0) *(volatile int*)&progress = 0x7fffffff;      // the tail needs no pacing
-    for (; s < steps; ++s, --y) {
-        const RowTaps t = trow[y];
-        const bool y0 = (unsigned)t.iy < (unsigned)Y, y1 = (unsigned)(t.iy + 1) < (unsigned)Y;
-        const bool z0 = (unsigned)t.iz < (unsigned)Z, z1 = (unsigned)(t.iz + 1) < (unsigned)Z;
-        const unsigned r = (unsigned)x0 + sy * (unsigned)t.iy + sz * (unsigned)t.iz;
-        float a00[VEC], a10[VEC], a11[VEC], a01[VEC], res[VEC];
-        vload<VEC>(a00, in + r, y0 && z0);
-        vload<VEC>(a10, in + (unsigned)(r + sy), y1 && z0);
-        vload<VEC>(a11, in + (unsigned)(r + sy + sz), y1 && z1);
-        vload<VEC>(a01, in + (unsigned)(r + sz), y0 && z1);
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-            const float v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a00[i], t.w00), __fmul_rn(a10[i], t.w10)), __fmul_rn(a11[i], t.w11)),
-                                      __fmul_rn(a01[i], t.w01));
-            const double dv = (double)v;
-            const double phi = __dmul_rn(__dmul_rn(dv, delta), n[i]);
-            n[i] = fmax(__dsub_rn(n[i], phi), 0.0);
-            res[i] = (float)__dmul_rn(dv, n[i]);
-        }
-        *reinterpret_cast<float4*>(out + (unsigned)(obase + sy * (unsigned)y)) = *reinterpret_cast<float4*>(res);
-    }
-    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (; y >= 0; --y) *reinterpret_cast<float4*>(out + (unsigned)(obase + sy * (unsigned)y)) = zero;
-}
-
 // returns MVSIM_EUNSUPPORTED when the fused path does not apply (caller falls back to the two kernels)
 int k_rotate_attenuate(mvsim_ctx* ctx, const float* in, float* out, const int64_t dims[3], int axis, const double inv[12], double delta, int steps)
 {
@@ -377,24 +252,19 @@ int k_rotate_attenuate(mvsim_ctx* ctx, const float* in, float* out, const int64_
     // the march along y is sequential per column, so the grid is small (X*Z/VEC threads): pick the widest
     // vector whose single wave still fits the machine (config 3: 131072 threads x float4, 2 rows in flight)
     const bool idx32 = (double)X * Y * Z < 2147483648.0;
-    // L2 prefetch distance in rows of the march (MVSIM_ROT_PREFETCH); OFF by default: measured 0.905 ms without, 1.11 / 1.28 / 1.31 ms at
-    // 6 / 16 / 32 rows (the march already keeps 2 rows x 4 taps in flight per thread and re-reads every source row from the L2).
-    // Needs CTAs that stay inside one row of one plane.
-    static const int pf_env = [] { const char* v = getenv("MVSIM_ROT_PREFETCH"); return v ? atoi(v) : 0; }();
+    // (L2 prefetch of the source rows was measured and lost in both forms -- issued by thread 0: 0.905 -> 1.11 .. 1.31 ms; by a
+    // fifth, paced warp per CTA: 1.04 .. 1.06 ms, profiles/r02_experiments.txt -- the march already keeps 2 rows x 4 taps in
+    // flight per thread and re-reads every source row from the L2.)
     if (X % 4 == 0 && aligned) {
         const size_t cols = (size_t)(X / 4) * Z;
-        const int pf = (X / 4) % 128 == 0 ? pf_env : 0;
-        static const int pfwarp_env = [] { const char* v = getenv("MVSIM_ROT_PFWARP"); return v ? atoi(v) : 0; }();
-        if (idx32 && pfwarp_env > 0 && (X / 4) % 128 == 0)
-            rotate_attenuate_pfwarp_kernel<<<blocks_for(cols, 128), 160, 0, ctx->stream>>>(in, out, tab, X, Y, Z, delta, steps, pfwarp_env);
-        else if (idx32) rotate_attenuate_kernel<4, 2, true><<<blocks_for(cols, 128), 128, 0, ctx->stream>>>(in, out, tab, X, Y, Z, delta, steps, pf);
-        else rotate_attenuate_kernel<4, 2, false><<<blocks_for(cols, 128), 128, 0, ctx->stream>>>(in, out, tab, X, Y, Z, delta, steps, pf);
+        if (idx32) rotate_attenuate_kernel<4, 2, true><<<blocks_for(cols, 128), 128, 0, ctx->stream>>>(in, out, tab, X, Y, Z, delta, steps);
+        else rotate_attenuate_kernel<4, 2, false><<<blocks_for(cols, 128), 128, 0, ctx->stream>>>(in, out, tab, X, Y, Z, delta, steps);
     } else if (X % 2 == 0 && aligned) {
         const size_t cols = (size_t)(X / 2) * Z;
-        rotate_attenuate_kernel<2, 4, false><<<blocks_for(cols, 128), 128, 0, ctx->stream>>>(in, out, tab, X, Y, Z, delta, steps, 0);
+        rotate_attenuate_kernel<2, 4, false><<<blocks_for(cols, 128), 128, 0, ctx->stream>>>(in, out, tab, X, Y, Z, delta, steps);
     } else {
         const size_t cols = (size_t)X * Z;
-        rotate_attenuate_kernel<1, 4, false><<<blocks_for(cols, 128), 128, 0, ctx->stream>>>(in, out, tab, X, Y, Z, delta, steps, 0);
+        rotate_attenuate_kernel<1, 4, false><<<blocks_for(cols, 128), 128, 0, ctx->stream>>>(in, out, tab, X, Y, Z, delta, steps);
     }
     ctx->launches++;
     cudaError_t e = cudaGetLastError();

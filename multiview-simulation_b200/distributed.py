@@ -68,6 +68,10 @@ class Group:
             tensor.copy_(h, non_blocking=True)
         if self.dist is not None:
             self.dist.broadcast(tensor, src=src)
+        if tensor.is_cuda:
+            # the copy and the broadcast are ordered on torch's current stream; the context may own another (non-blocking)
+            # stream, so the ground truth must have ARRIVED before the volume is handed to it
+            torch.cuda.current_stream(tensor.device).synchronize()
         return DeviceVolume.wrap(ctx, shape_zyx, tensor.data_ptr(), keepalive=tensor), tensor
 
     def my_views(self, n_views):

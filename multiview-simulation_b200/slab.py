@@ -27,18 +27,22 @@ class SlabConvolution:
         dev = torch.device("cuda", ctx.device)
         self.shape = tuple(shape_zyx)
         self.p2p = bool(p2p) and world > 1
+        # host_plane: the process group cannot move CUDA tensors (gloo; ranks that SHARE one GPU, where NCCL refuses to run).
+        # Handles travel as CPU tensors, the cross-rank barrier is stream-synchronise + host barrier, and the all-to-all of the
+        # non-p2p mode is staged through host memory.  Same kernels, same buffers, same layouts -- used by the 1-GPU tests.
+        self.host_plane = world > 1 and dist.get_backend() != "nccl"
         if self.p2p:
             import numpy as np
             self.nbuf = min(2, self.y_blocks)
             mine = np.zeros(self.nbuf * 2 * 64, dtype=np.uint8)
             check(ctx._lib.mvsim_slabconv_p2p_alloc(ctx.h, self.h, self.nbuf, C.c_void_p(mine.ctypes.data)), ctx.h)
-            t = torch.from_numpy(mine).to(dev)
+            t = torch.from_numpy(mine) if self.host_plane else torch.from_numpy(mine).to(dev)
             parts = [torch.empty_like(t) for _ in range(world)]
             dist.all_gather(parts, t)
             allh = torch.cat(parts).cpu().numpy()
             check(ctx._lib.mvsim_slabconv_p2p_open(ctx.h, self.h, C.c_void_p(allh.ctypes.data)), ctx.h)
             check(ctx._lib.mvsim_slabconv_p2p_select(self.h, 0), ctx.h)
-            self._flag = torch.zeros(1, dtype=torch.float32, device=dev)
+            self._flag = torch.zeros(1, dtype=torch.float32, device="cpu" if self.host_plane else dev)
             dist.barrier()
             return
         # up to three exchange buffer sets: the all-to-all of one y block overlaps the kernels of its neighbours
@@ -52,6 +56,30 @@ class SlabConvolution:
         r = self.recv[i]
         check(self.ctx._lib.mvsim_slabconv_bind(self.h, C.c_void_p(self.send[i].data_ptr()),
                                                 C.c_void_p(r.data_ptr()) if r is not None else None), self.ctx.h)
+
+    def _barrier(self):
+        """All ranks' kernels enqueued so far have finished before any rank's later kernels start."""
+        if self.host_plane:
+            import torch
+            torch.cuda.current_stream().synchronize()
+            self.dist.barrier()
+        else:
+            self.dist.all_reduce(self._flag)        # stream-ordered (NCCL runs on the current stream's dependency chain)
+
+    def _all_to_all(self, dst, src, async_op):
+        if not self.host_plane:
+            return self.dist.all_to_all_single(dst, src, async_op=async_op)
+        import torch
+        torch.cuda.current_stream().synchronize()
+        s = torch.view_as_real(src).cpu()
+        d = torch.empty_like(s)
+        self.dist.all_to_all_single(d, s)
+        torch.view_as_real(dst).copy_(d)
+
+        class _Done:
+            def wait(self):
+                return True
+        return _Done()
 
     def exchange_bytes_per_rank(self):
         """bytes this rank sends to OTHER ranks per convolution (two transposes per y block; in p2p mode the same bytes
@@ -70,9 +98,9 @@ class SlabConvolution:
             for b in range(nb):
                 check(lib.mvsim_slabconv_p2p_select(self.h, b % self.nbuf), ctx.h)
                 check(lib.mvsim_slabconv_forward_y(ctx.h, self.h, b), ctx.h)       # stores into the owners' z-pass buffers
-                self.dist.all_reduce(self._flag)                                    # stream-ordered cross-rank barrier
+                self._barrier()                                                     # stream-ordered cross-rank barrier
                 check(lib.mvsim_slabconv_middle_z(ctx.h, self.h), ctx.h)            # stores into the owners' inverse buffers
-                self.dist.all_reduce(self._flag)
+                self._barrier()
                 check(lib.mvsim_slabconv_inverse_y(ctx.h, self.h, b), ctx.h)
         elif self.world == 1:
             for b in range(nb):
@@ -88,13 +116,13 @@ class SlabConvolution:
                     i = t % self.nbuf
                     self._bind(i)
                     check(lib.mvsim_slabconv_forward_y(ctx.h, self.h, t), ctx.h)
-                    works[t] = self.dist.all_to_all_single(self.recv[i], self.send[i], async_op=True)
+                    works[t] = self._all_to_all(self.recv[i], self.send[i], True)
                 if 0 <= t - 1 < nb:
                     b, i = t - 1, (t - 1) % self.nbuf
                     works.pop(b).wait()
                     self._bind(i)
                     check(lib.mvsim_slabconv_middle_z(ctx.h, self.h), ctx.h)
-                    works[b] = self.dist.all_to_all_single(self.send[i], self.recv[i], async_op=True)
+                    works[b] = self._all_to_all(self.send[i], self.recv[i], True)
                 if 0 <= t - 2 < nb:
                     b, i = t - 2, (t - 2) % self.nbuf
                     works.pop(b).wait()

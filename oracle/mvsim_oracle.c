@@ -47,6 +47,21 @@ int orc_max_threads(void)
     return 1;
 #endif
 }
+/* processors available to this process, independent of OMP_NUM_THREADS (torchrun exports OMP_NUM_THREADS=1) */
+int orc_hw_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_num_procs();
+#else
+    return 1;
+#endif
+}
+/* Timing-only knob of bench.py's "best effort" baseline: with n > 1 extractSlices gives every kept slice its own
+ * java.util.Random (seed + slice index) so that the O(lambda) loops of different slices run on n threads.  The
+ * reference draws all slices from ONE sequential generator (S/SimulateMultiViewDataset.java:76,183): 0 / 1 (the
+ * default, and what every test uses) reproduces that order. */
+static int g_poisson_threads = 0;
+void orc_set_poisson_threads(int n) { g_poisson_threads = n; }
 
 #define ORC_OK 0
 #define ORC_EINVAL 1
@@ -537,6 +552,18 @@ int orc_extract_slices(const float* in, const int64_t dims[3], int inc, float sn
 {
     if (inc < 1) return ORC_EINVAL;
     const int64_t X = dims[0], Y = dims[1], Z = dims[2];
+    if (g_poisson_threads > 1 && snr >= 0.0f) {
+        const int64_t nk = (Z - 1) / inc + 1;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(g_poisson_threads)
+        for (int64_t k = 0; k < nk; ++k) {
+            orc_jrandom r;
+            orc_jrandom_init(&r, seed + k);
+            float* o = out + X * Y * k;
+            memcpy(o, in + X * Y * (k * inc), sizeof(float) * (size_t)(X * Y));
+            orc_poisson(o, (size_t)(X * Y), (double)snr, &r);
+        }
+        return ORC_OK;
+    }
     orc_jrandom rnd;
     orc_jrandom_init(&rnd, seed);
     int64_t cz = 0;

@@ -59,6 +59,8 @@ def lib():
         L.orc_fft_size.restype = C.c_int64
         L.orc_set_stage_threads.argtypes = [C.c_int]
         L.orc_max_threads.restype = C.c_int
+        L.orc_hw_threads.restype = C.c_int
+        L.orc_set_poisson_threads.argtypes = [C.c_int]
         L.orc_make_isotropic.argtypes = [fp, i64p, C.c_int, fp]
         L.orc_weight_image.argtypes = [i64p, fp]
         L.orc_normalize_weights.argtypes = [C.POINTER(fp), C.c_int, C.c_size_t, C.c_float, fp]
@@ -171,7 +173,7 @@ def convolve(vol, psf, method="direct", nthreads=0):
     if method == "direct":
         err = lib().orc_convolve_direct(_f(vol), _dims(vol), _f(psf), _dims(psf), _f(out))
     else:
-        nt = nthreads or lib().orc_max_threads()
+        nt = nthreads or host_threads()
         err = lib().orc_convolve_fft(_f(vol), _dims(vol), _f(psf), _dims(psf), _f(out), nt)
     _check(err, "convolve")
     return out
@@ -197,23 +199,36 @@ def poisson(a, snr, rnd):
     lib().orc_poisson(_f(a), a.size, float(snr), rnd.ptr)
 
 
+def host_threads():
+    """Processors this process may use -- NOT omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1, which made the
+    round-1 reference arm run on one core whenever it was launched under torch.distributed.run."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def simulate_view(gt, psf, axis=0, degrees=15, delta=0.01, min_value=0.0001, target_avg=1.0, inc=3,
-                  snr=25.0, seed=464232194, use_fft=True, fft_threads=0, stage_threads=0):
-    """Loop body S/SimulateMultiViewDataset.java:570-585.  Returns (acquired, convolved+adjusted, times)."""
+                  snr=25.0, seed=464232194, use_fft=True, fft_threads=0, stage_threads=0, poisson_threads=0, want_conv=True):
+    """Loop body S/SimulateMultiViewDataset.java:570-585.  Returns (acquired, convolved+adjusted, times).
+    fft_threads / stage_threads: 0 = every processor of this process (host_threads()); poisson_threads > 1 is the
+    timing-only split of the Poisson loop over slices (see orc_set_poisson_threads)."""
     gt = _vol(gt)
     psf = np.ascontiguousarray(psf, dtype=np.float32).copy()
     z, y, x = gt.shape
     out = np.empty(((z - 1) // inc + 1, y, x), dtype=np.float32)
-    conv = np.empty_like(gt)
+    conv = np.empty_like(gt) if want_conv else None
     times = (C.c_double * 5)()
     L = lib()
-    L.orc_set_stage_threads(stage_threads)
+    L.orc_set_stage_threads(stage_threads or host_threads())
+    L.orc_set_poisson_threads(poisson_threads)
     try:
         err = L.orc_simulate_view(_f(gt), _dims(gt), _f(psf), _dims(psf), axis, degrees, delta, min_value,
-                                  target_avg, inc, snr, seed, int(use_fft), fft_threads or L.orc_max_threads(),
-                                  _f(out), _f(conv), times)
+                                  target_avg, inc, snr, seed, int(use_fft), fft_threads or host_threads(),
+                                  _f(out), _f(conv) if want_conv else None, times)
     finally:
         L.orc_set_stage_threads(0)
+        L.orc_set_poisson_threads(0)
     _check(err, "simulate_view")
     return out, conv, list(times)
 

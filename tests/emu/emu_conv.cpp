@@ -86,9 +86,7 @@ struct EmuLauncher {
     template <int A, int B, int INC> static int dec(const ZFusedParams& q, int n_outer, int tiles)
     {
         if constexpr (zfused_dec_ok(A, B, INC)) {
-            const char* mode = getenv("MVSIM_EMU_DECIMATE");
-            if (mode && mode[0] == '2') emulate<ZFusedDecW<A, B, T, INC>>(q, n_outer, tiles);
-            else emulate<ZFusedDec<B, A, T, INC>>(q, n_outer, tiles);
+            emulate<ZFusedDec<B, A, T, INC>>(q, n_outer, tiles);
             return 0;
         } else {
             return 5;

@@ -22,3 +22,8 @@ extern "C" void emu_poisson(const double* lam, float* out, uint64_t n, uint64_t 
         for (int i = 0; i < 4 && 4 * g + i < n; ++i) out[4 * g + i] = o[i];
     }
 }
+
+// one variate from given random words (top-of-range words probe the float32 CDF plateau of the inversion search);
+// returns 1 when the fast path finished it
+extern "C" int emu_poisson_fast(double lam, uint32_t ru, uint32_t rv, float* out) { return poisson_fast(lam, ru, rv, *out) ? 1 : 0; }
+extern "C" float emu_u01f(uint32_t x) { return u01f(x); }

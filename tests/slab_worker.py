@@ -21,10 +21,13 @@ def main():
     kshape = tuple(int(v) for v in sys.argv[2].split("x"))
     out_path = sys.argv[3]
     p2p = len(sys.argv) < 5 or sys.argv[4] != "nccl"
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    # "shared": every rank runs on GPU 0 (the driver's 1-GPU box): CUDA IPC maps the peers' buffers between the processes,
+    # gloo carries the handles, the barriers and (non-p2p mode) the all-to-all -- NCCL refuses two ranks on one device
+    shared = len(sys.argv) > 5 and sys.argv[5] == "shared"
+    local = 0 if shared else int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    grp = mv.Group("nccl", device=dev)
+    grp = mv.Group("gloo" if shared else "nccl", device=dev)
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     ctx = mv.Context(local, cuda_stream=stream.cuda_stream)
@@ -39,6 +42,8 @@ def main():
     out = torch.empty_like(img)
     sc.convolve(img, d_psf, out)
     torch.cuda.synchronize()
+    if shared:
+        out = out.cpu()
     parts = [torch.empty_like(out) for _ in range(grp.world)] if grp.rank == 0 else None
     if grp.world > 1:
         grp.dist.gather(out, parts, dst=0)
@@ -49,7 +54,7 @@ def main():
         ref = mv.SimulateMultiViewDataset.convolve(vol, psf.copy(), ctx=ctx)      # undecomposed, same GPU kernels
         err = float(np.abs(got.astype(np.float64) - ref).max() / np.abs(ref).max())
         with open(out_path, "w") as f:
-            json.dump({"world": grp.world, "p2p": sc.p2p, "y_blocks": sc.y_blocks, "nfft": sc.nfft, "max_rel_err": err,
+            json.dump({"world": grp.world, "p2p": sc.p2p, "shared_gpu": shared, "y_blocks": sc.y_blocks, "nfft": sc.nfft, "max_rel_err": err,
                        "identical": bool(np.array_equal(got, ref))}, f)
     sc.close()
     grp.close()

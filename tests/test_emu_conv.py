@@ -175,11 +175,10 @@ def test_generated_butterflies_are_in_sync_with_the_generator(tmp_path):
     ((100, 3, 10), (19, 2, 3), 5),     # 120 = 10 x 12 -> ZFusedDec<12, 10, T, 5>, crop0 = 18: r = 3
     ((101, 3, 20), (17, 1, 2), 5),     # 120, crop0 = 16: r = 1; partial last kx tile
 ])
-@pytest.mark.parametrize("variant", ["1", "2"])      # ZFusedDec / ZFusedDecW
-def test_decimated_inverse_of_the_fused_z_pass(emu, oracle, monkeypatch, psf_spectrum_mode, request, shape, kshape, inc, variant):
-    """EXPERIMENT for the next round (MVSIM_Z_DECIMATE): kept planes = whole columns of the exchange, pruned first inverse
-    half, second inverse half for the kept columns only, sum plane from a dot product with the crop's Dirichlet table."""
-    monkeypatch.setenv("MVSIM_EMU_DECIMATE", variant)
+def test_decimated_inverse_of_the_fused_z_pass(emu, oracle, monkeypatch, psf_spectrum_mode, request, shape, kshape, inc):
+    """ZFusedDec (the whole-view default where the split allows it): kept planes = whole columns of the exchange, pruned first
+    inverse half, second inverse half for the kept columns only, sum plane from a dot product with the crop's Dirichlet table."""
+    monkeypatch.setenv("MVSIM_EMU_DECIMATE", "1")
     emu.emu_decimated_launches.restype = C.c_int
     before = emu.emu_decimated_launches()
     rng = np.random.default_rng(21)

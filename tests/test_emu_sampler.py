@@ -86,3 +86,31 @@ def test_edge_cases_and_streams(emu):
     assert not np.array_equal(a, b) and not np.array_equal(a, c)
     big = sample(emu, 3.0e8, 20000)
     assert abs(big.mean() / 3.0e8 - 1) < 1e-5 and abs(big.std() / math.sqrt(3.0e8) - 1) < 0.05
+
+
+def test_uniform_is_strictly_inside_the_unit_interval(emu):
+    """with 24 bits, (float)(2^24 - 1) + 0.5f rounded to 2^24 and u01f returned exactly 1.0f."""
+    emu.emu_u01f.restype = C.c_float
+    emu.emu_u01f.argtypes = [C.c_uint32]
+    words = [0, 1, 0x1ff, 0x200, 0x7fffffff, 0x80000000, 0xfffffdff, 0xfffffe00, 0xffffff00, 0xfffffffe, 0xffffffff]
+    us = [emu.emu_u01f(w) for w in words]
+    assert all(0.0 < u < 1.0 for u in us)
+    assert us[0] == 2.0 ** -24 and us[-1] == 1.0 - 2.0 ** -24
+    assert us == sorted(us)
+
+
+@pytest.mark.parametrize("lam", [0.0125, 0.5, 1.0, 5.0, 9.99])
+def test_inversion_search_terminates_on_the_cdf_plateau(emu, lam):
+    """The float32 CDF saturates below 1; the top random words must not run the search to its iteration cap (they returned
+    64 at lam = 0.0125, the background rate at the default SNR 25 / minValue 1e-4)."""
+    from scipy import stats
+    emu.emu_poisson_fast.restype = C.c_int
+    emu.emu_poisson_fast.argtypes = [C.c_double, C.c_uint32, C.c_uint32, C.POINTER(C.c_float)]
+    out = C.c_float()
+    hi = stats.poisson.ppf(1 - 1e-9, lam) + 3          # a generous bound on any plausible draw
+    for w in [0xffffffff, 0xfffffffe, 0xfffffe00, 0xfffffdff, 0xfffffc00, 0xfffff000]:
+        assert emu.emu_poisson_fast(lam, w, 0, C.byref(out)) == 1
+        assert 0 <= out.value <= hi, (lam, hex(w), out.value)
+    # the median word gives the median count
+    assert emu.emu_poisson_fast(lam, 0x80000000, 0, C.byref(out)) == 1
+    assert out.value == stats.poisson.ppf(0.5, lam)
