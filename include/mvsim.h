@@ -92,6 +92,16 @@ int mvsim_stage_times(mvsim_ctx* ctx, double ms[MVSIM_NSTAGES], int64_t launches
 /* number of kernels this context has launched since creation */
 int64_t mvsim_kernel_launches(mvsim_ctx* ctx);
 
+/* PSF-spectrum cache of a context (OFF by default = the reference's behaviour, which rebuilds the kernel FFT on every
+ * call, S/SimulateMultiViewDataset.java:257).  With max_bytes > 0 the convolution keeps the partial spectrum of every distinct
+ * (normalised) PSF it has seen, keyed by a 128-bit content hash computed on the device, up to max_bytes of HBM (least recently used
+ * out first); repeated PSFs -- SNR sweeps, tile pairs (S/SimulateTileStitching.java:71,95,110), the 8 distinct volumes among the 18
+ * fixtures -- then skip the PSF transforms.  Results are bit-identical with and without; the in-place normalisation of the
+ * caller's PSF (:255) still happens on every call.  Shrinking the budget drops all entries.
+ * stats = { hits, misses, entries, bytes held }. */
+int mvsim_psf_cache_configure(mvsim_ctx* ctx, size_t max_bytes);
+int mvsim_psf_cache_stats(mvsim_ctx* ctx, int64_t stats[4]);
+
 int mvsim_alloc_pinned(size_t bytes, void** ptr);
 int mvsim_free_pinned(void* ptr);
 

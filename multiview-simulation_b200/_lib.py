@@ -45,6 +45,8 @@ SYMBOLS = [
     ("mvsim_profile_reset", C.c_int, [_vp]),
     ("mvsim_stage_times", C.c_int, [_vp, _dp, _i64p]),
     ("mvsim_kernel_launches", C.c_int64, [_vp]),
+    ("mvsim_psf_cache_configure", C.c_int, [_vp, C.c_size_t]),
+    ("mvsim_psf_cache_stats", C.c_int, [_vp, _i64p]),
     ("mvsim_alloc_pinned", C.c_int, [C.c_size_t, C.POINTER(_vp)]),
     ("mvsim_free_pinned", C.c_int, [_vp]),
     ("mvsim_conv_padded_dims", C.c_int, [_i64p, _i64p, _i64p]),

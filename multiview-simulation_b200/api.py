@@ -93,6 +93,17 @@ class Context:
     def kernel_launches(self):
         return int(self._lib.mvsim_kernel_launches(self.h))
 
+    def psf_cache(self, max_bytes):
+        """PSF-spectrum cache of this context (mvsim_psf_cache_configure): keep the spectra of repeated PSFs in up to
+        `max_bytes` of HBM (0 = off, the library default: the reference rebuilds the kernel FFT per call, :257)."""
+        check(self._lib.mvsim_psf_cache_configure(self.h, int(max_bytes)), self.h)
+        return self
+
+    def psf_cache_stats(self):
+        st = (C.c_int64 * 4)()
+        check(self._lib.mvsim_psf_cache_stats(self.h, st), self.h)
+        return {"hits": int(st[0]), "misses": int(st[1]), "entries": int(st[2]), "bytes": int(st[3])}
+
 
 _tls = threading.local()
 

@@ -307,6 +307,10 @@ static int ctx_create(int device, bool own, void* cuda_stream, mvsim_ctx** out)
     ctx->mempool = nullptr;
     ctx->d_scalars = nullptr;
     ctx->launches = 0;
+    ctx->psf_cache_max_bytes = 0;
+    ctx->psf_cache_tick = ctx->psf_cache_hits = ctx->psf_cache_misses = 0;
+    ctx->d_hash = nullptr;
+    ctx->h_hash = nullptr;
     ctx->profiling = false;
     memset(ctx->acc_ms, 0, sizeof(ctx->acc_ms));
     memset(ctx->acc_n, 0, sizeof(ctx->acc_n));
@@ -355,6 +359,9 @@ int mvsim_ctx_destroy(mvsim_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     for (auto& kv : ctx->tables) cudaFree(kv.second.tw);
     for (auto& kv : ctx->dec_tables) cudaFree(kv.second);
+    for (auto& e : ctx->psf_cache) cudaFree(e.p2);
+    if (ctx->d_hash) cudaFree(ctx->d_hash);
+    if (ctx->h_hash) cudaFreeHost(ctx->h_hash);
     for (auto& ev : ctx->events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
     for (auto& ev : ctx->pool) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
     cudaFree(ctx->d_scalars);
@@ -416,6 +423,28 @@ int mvsim_stage_times(mvsim_ctx* ctx, double ms[MVSIM_NSTAGES], int64_t launches
 }
 
 int64_t mvsim_kernel_launches(mvsim_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int mvsim_psf_cache_configure(mvsim_ctx* ctx, size_t max_bytes)
+{
+    MVSIM_ENTER(ctx);
+    MVSIM_TRY(sync(ctx));                       // nothing in flight reads an entry that is about to go
+    if (max_bytes < ctx->psf_cache_max_bytes) {
+        for (auto& e : ctx->psf_cache) cudaFree(e.p2);
+        ctx->psf_cache.clear();
+    }
+    ctx->psf_cache_max_bytes = max_bytes;
+    return MVSIM_OK;
+}
+
+int mvsim_psf_cache_stats(mvsim_ctx* ctx, int64_t stats[4])
+{
+    if (!ctx || !stats) return MVSIM_EINVAL;
+    size_t held = 0;
+    for (auto& e : ctx->psf_cache) held += e.bytes;
+    stats[0] = (int64_t)ctx->psf_cache_hits; stats[1] = (int64_t)ctx->psf_cache_misses;
+    stats[2] = (int64_t)ctx->psf_cache.size(); stats[3] = (int64_t)held;
+    return MVSIM_OK;
+}
 
 int mvsim_alloc_pinned(size_t bytes, void** ptr)
 {

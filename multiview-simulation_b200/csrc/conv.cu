@@ -230,6 +230,46 @@ struct Buffers {
 
 int strided_lanes() { return 8; }
 
+// PSF-spectrum cache.  Hashes the (normalised) PSF on the device, reads the 16 bytes back (one stream synchronisation per
+// convolution: ~20 us against a >= 0.28 ms PSF stage at config 3) and looks the key up.  Hit: *p2 is the cached partial spectrum.
+// Miss: *p2 is a fresh cache-owned buffer the caller must fill (entries beyond the byte budget are evicted least recently used;
+// the stream is idle at that point, so no kernel still reads them).  *p2 == nullptr: not cacheable (budget too small / no memory).
+static int psf_cache_lookup(mvsim_ctx* ctx, const float* d_psf, const ConvPlan& pl, int lanes, size_t p2_elems, float2** p2, bool* hit)
+{
+    *p2 = nullptr; *hit = false;
+    const size_t bytes = p2_elems * sizeof(float2);
+    if (ctx->psf_cache_max_bytes == 0 || bytes > ctx->psf_cache_max_bytes) return MVSIM_OK;
+    if (!ctx->d_hash) {
+        MVSIM_CUDA(ctx, cudaMalloc((void**)&ctx->d_hash, 2 * sizeof(unsigned long long)));
+        MVSIM_CUDA(ctx, cudaHostAlloc((void**)&ctx->h_hash, 2 * sizeof(unsigned long long), cudaHostAllocDefault));
+    }
+    const size_t n = (size_t)pl.kdims[0] * pl.kdims[1] * pl.kdims[2];
+    MVSIM_TRY(k_hash128(ctx, d_psf, n, ctx->d_hash));
+    MVSIM_CUDA(ctx, cudaMemcpyAsync(ctx->h_hash, ctx->d_hash, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    MVSIM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const std::array<uint64_t, 9> key = { ctx->h_hash[0], ctx->h_hash[1], (uint64_t)pl.kdims[0], (uint64_t)pl.kdims[1], (uint64_t)pl.kdims[2],
+                                          (uint64_t)pl.sx.n, (uint64_t)pl.sy.n, (uint64_t)pl.sz.n, (uint64_t)lanes };
+    const uint64_t now = ++ctx->psf_cache_tick;
+    for (auto& e : ctx->psf_cache)
+        if (e.key == key) { e.last_use = now; *p2 = e.p2; *hit = true; ctx->psf_cache_hits++; return MVSIM_OK; }
+    ctx->psf_cache_misses++;
+    size_t held = 0;
+    for (auto& e : ctx->psf_cache) held += e.bytes;
+    while (!ctx->psf_cache.empty() && held + bytes > ctx->psf_cache_max_bytes) {
+        size_t lru = 0;
+        for (size_t i = 1; i < ctx->psf_cache.size(); ++i)
+            if (ctx->psf_cache[i].last_use < ctx->psf_cache[lru].last_use) lru = i;
+        held -= ctx->psf_cache[lru].bytes;
+        cudaFree(ctx->psf_cache[lru].p2);
+        ctx->psf_cache.erase(ctx->psf_cache.begin() + (long)lru);
+    }
+    float2* buf = nullptr;
+    if (cudaMalloc((void**)&buf, bytes) != cudaSuccess) { cudaGetLastError(); return MVSIM_OK; }      // no room: plain path
+    ctx->psf_cache.push_back({ key, buf, bytes, now });
+    *p2 = buf;
+    return MVSIM_OK;
+}
+
 static int plan_error(mvsim_ctx* ctx, int perr)
 {
     if (perr == 1) return set_error(ctx, MVSIM_EINVAL, "convolve: bad dims");
@@ -260,12 +300,21 @@ int conv_device(mvsim_ctx* ctx, const float* img, const int64_t dims[3], const f
     MVSIM_TRY(buf.get(&ws.u2, (size_t)pl.u2_elems(lanes, g.z_local)));
     ws.ex = ws.u2;
     if (!otf_default()) MVSIM_TRY(buf.get(&ws.h, (size_t)pl.h_elems(lanes, g.tiles_own)));
-    MVSIM_TRY(buf.get(&ws.p1, (size_t)pl.p1_elems()));
-    MVSIM_TRY(buf.get(&ws.p2, (size_t)pl.p2_elems(lanes, g.tiles_own)));
+    // PSF partial spectrum: from the cache when this (normalised) PSF has been seen with this plan, else computed -- into a
+    // cache-owned buffer when the cache is on, into a pool buffer otherwise
+    bool psf_hit = false;
+    float2* cached = nullptr;
+    if (otf_default()) {
+        StageTimer t(ctx, MVSIM_T_PSF);
+        MVSIM_TRY(psf_cache_lookup(ctx, psf, pl, lanes, (size_t)pl.p2_elems(lanes, g.tiles_own), &cached, &psf_hit));
+    }
+    if (cached) ws.p2 = cached;
+    else MVSIM_TRY(buf.get(&ws.p2, (size_t)pl.p2_elems(lanes, g.tiles_own)));
+    if (!psf_hit) MVSIM_TRY(buf.get(&ws.p1, (size_t)pl.p1_elems()));
     ws.tw_x = tx.tw; ws.twist_x = tx.twist; ws.tw_y = ty.tw; ws.tw_z = tz.tw;
 
     CudaLauncher l = { ctx, true, lanes };
-    MVSIM_TRY(conv_psf_spectrum(l, pl, g, ws, psf));
+    if (!psf_hit) MVSIM_TRY(conv_psf_spectrum(l, pl, g, ws, psf));
     l.psf_phase = false;
     double* partials = nullptr;
     const int planes = conv_out_planes(pl, g, keep_inc);

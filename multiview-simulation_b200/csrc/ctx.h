@@ -31,6 +31,15 @@ struct mvsim_ctx {
     double* d_scalars;                       // [8] device doubles: sums, corrections
     std::map<int, mvsim_tables> tables;      // by complex line length
     std::map<std::array<int, 3>, float2*> dec_tables;   // decimated fused z pass: D table by (n, crop0, n_src)
+    // PSF-spectrum cache: partial spectra P2 keyed by a device-computed content hash of the NORMALISED PSF + the plan.
+    // The reference rebuilds the kernel FFT on every call (S/SimulateMultiViewDataset.java:257) although its callers reuse one
+    // PSF across SNR sweeps and tile pairs (S/SimulateTileStitching.java:71,95,110); results are bit-identical either way.
+    struct PsfEntry { std::array<uint64_t, 9> key; float2* p2; size_t bytes; uint64_t last_use; };
+    std::vector<PsfEntry> psf_cache;
+    size_t psf_cache_max_bytes;              // 0 = off
+    uint64_t psf_cache_tick, psf_cache_hits, psf_cache_misses;
+    unsigned long long* d_hash;              // [2] device words
+    unsigned long long* h_hash;              // [2] pinned host words
     int64_t launches;
     // profiling
     bool profiling;
@@ -85,6 +94,8 @@ int k_make_isotropic(mvsim_ctx* ctx, const float* in, const int64_t dims[3], int
 int k_weight_image(mvsim_ctx* ctx, const int64_t dims[3], float* out);
 int k_normalize_weights(mvsim_ctx* ctx, float* const* d_weights, int n_views, size_t n, float osem, float* d_sum_out);
 int k_poisson(mvsim_ctx* ctx, float* inout, size_t n, double snr, uint64_t seed, uint64_t stream);
+// 128-bit content hash of n floats (order-independent sum of two 64-bit mixes of (bits, index)): d_out[2], enqueued on the stream
+int k_hash128(mvsim_ctx* ctx, const float* in, size_t n, unsigned long long* d_out);
 
 // input generators (phantom.cu).  points / host_rec / host_val are HOST arrays (consumed before return), the rest device pointers
 int k_render_beads(mvsim_ctx* ctx, const double* points, int n, const double sigma[3], const int64_t imin[3], const int64_t imax[3], float* d_out);

@@ -402,6 +402,54 @@ int k_sum(mvsim_ctx* ctx, const float* in, size_t n, double* d_sum)
     return st;
 }
 
+// ---------------------------------------------------------------------------------------------
+// 128-bit content hash for the PSF-spectrum cache: h_j = sum_i mix_j(bits_i, i) mod 2^64 for two independent finalisers
+// (splitmix64 / murmur3 constants).  A sum is order independent, so the grid shape does not matter and integer atomics
+// keep it deterministic.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long mix_a(unsigned long long z)
+{
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ unsigned long long mix_b(unsigned long long z)
+{
+    z ^= z >> 33; z *= 0xFF51AFD7ED558CCDull;
+    z ^= z >> 33; z *= 0xC4CEB9FE1A85EC53ull;
+    return z ^ (z >> 33);
+}
+
+__global__ void __launch_bounds__(256) hash128_kernel(const float* __restrict__ in, size_t n, unsigned long long* __restrict__ out)
+{
+    unsigned long long a = 0, b = 0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const unsigned long long w = ((unsigned long long)i << 32) ^ (unsigned long long)__float_as_uint(__ldg(in + i)) ^ ((unsigned long long)(i >> 32) * 0xD6E8FEB86659FD93ull);
+        a += mix_a(w);
+        b += mix_b(w ^ 0xA5A5A5A55A5A5A5Aull);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        a += __shfl_down_sync(0xffffffffu, a, d);
+        b += __shfl_down_sync(0xffffffffu, b, d);
+    }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(out, a); atomicAdd(out + 1, b); }
+}
+
+int k_hash128(mvsim_ctx* ctx, const float* in, size_t n, unsigned long long* d_out)
+{
+    cudaError_t e = cudaMemsetAsync(d_out, 0, 2 * sizeof(unsigned long long), ctx->stream);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "hash memset");
+    unsigned blocks = blocks_for(n, 256 * 8);
+    if (blocks > 1184) blocks = 1184;
+    if (blocks < 1) blocks = 1;
+    hash128_kernel<<<blocks, 256, 0, ctx->stream>>>(in, n, d_out);
+    MVSIM_LAUNCH_CHECK(ctx);
+    return MVSIM_OK;
+}
+
 // normImage: t = (float)((double)t / sum)   S/Tools.java:116-117
 __global__ void __launch_bounds__(256) divide_by_sum_kernel(float* __restrict__ a, size_t n, const double* __restrict__ d_sum)
 {

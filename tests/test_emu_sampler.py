@@ -75,7 +75,7 @@ def test_ks_against_reference_sampler(emu, oracle, lam):
     ref = np.full(n, v, dtype=np.float32)
     oracle.poisson(ref, snr, oracle.JavaRandom(3))
     got = sample(emu, float(v) * mul, 3 * n)
-    assert stats.ks_2samp(got, ref).pvalue > 1e-3
+    assert stats.ks_2samp(got, ref).pvalue > 0.01
 
 
 def test_edge_cases_and_streams(emu):

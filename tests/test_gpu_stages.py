@@ -172,8 +172,9 @@ def test_poisson_matches_reference_sampler_statistically(mv, oracle, lam):
     m = 20000 if lam <= 300 else 4000
     b = np.full(m, v, dtype=np.float32)
     oracle.poisson(b, snr, oracle.JavaRandom(5))
-    # discrete data: KS p-values are conservative; 0.001 keeps the false alarm rate negligible
-    assert _ks_two_sample(a[:m * 3], b) > 1e-3
+    # two-sample KS against the oracle's replay of the reference sampler, p > 0.01 as SURVEY 8c asks (the CPU emulation of
+    # the same sampler code gives p = 0.70 .. 1.0 for these seeds)
+    assert _ks_two_sample(a[:m * 3], b) > 0.01
 
 
 def test_poisson_zero_negative_and_snr0(mv):
