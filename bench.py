@@ -139,6 +139,39 @@ class ClockSampler:
         return out
 
 
+def host_link_probe(torch, n=1 << 28):
+    """Pinned-memory copy rates of this GPU's host link right now: each direction alone and both at once (GB/s)."""
+    h_in = torch.empty(n, dtype=torch.float32).pin_memory()
+    h_out = torch.empty(n, dtype=torch.float32).pin_memory()
+    d_a = torch.empty(n, dtype=torch.float32, device="cuda")
+    d_b = torch.ones(n, dtype=torch.float32, device="cuda")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    gb = n * 4 / 1e9
+
+    def up():
+        with torch.cuda.stream(s1):
+            d_a.copy_(h_in, non_blocking=True)
+
+    def down():
+        with torch.cuda.stream(s2):
+            h_out.copy_(d_b, non_blocking=True)
+
+    def timed(fns):
+        best = float("inf")
+        for _ in range(3):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for f in fns:
+                f()
+            torch.cuda.synchronize()
+            best = min(best, time.perf_counter() - t0)
+        return gb / best
+    r = {"h2d_alone_GBps": timed([up]), "d2h_alone_GBps": timed([down])}
+    both = timed([up, down])
+    r["h2d_concurrent_GBps"] = r["d2h_concurrent_GBps"] = both
+    return r
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -303,31 +336,24 @@ def run_ours(args, rank, world, local_rank):
     # callers up so that the H2D of one step runs under the kernels of another and the D2H tail of a third (PCIe is full duplex).  Every step still moves all of its bytes inside the timed region.
     S = mv.SimulateMultiViewDataset
     e2e_steps = max(1, min(args.steps, 3))
+    kvox, ovox = int(np.prod(kshape)), int(np.prod(oshape))
 
     def step_e2e(c=ctx, psfs=psf_pin, outs=out_pin):
         for v in range(nv):
             psfs[v].array[...] = psf_raw[v]          # the call normalises the PSF in place
         S.simulateViews(gt_pin.array, [p.array for p in psfs], degrees, inc=inc, poissonSNR=snr, rnd=464232194, ctx=c,
                         outs=[o.array for o in outs], first_stream=rank * nv)
-    step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    e0.record(stream)
-    for _ in range(e2e_steps):
-        step_e2e()
-    e1.record(stream)
-    barrier()
-    wall = (time.perf_counter() - t0) / e2e_steps
-    serial_ms = max_over_ranks(max(e0.elapsed_time(e1) / e2e_steps, wall * 1e3))
-    h2d = 4 * vox_per_view + nv * 4 * int(np.prod(kshape))
-    d2h = nv * 4 * (int(np.prod(oshape)) + int(np.prod(kshape)))
-    result_checksum = float(out_pin[0].array[::7, ::31, ::29].astype(np.float64).mean())
 
-    # three callers fill the pipeline on one GPU; with several ranks the shared host link is the limit and concurrent
-    # callers only add contention (measured at 2 and 8 GPUs: 141 vs 111 and 504 vs 327 ms per step), so N > 1 uses one
-    n_callers = 3 if world == 1 else 1
+    # the same protocol at every N: up to three caller threads per rank (pinned host memory permitting), the same step counts
     callers = [(ctx, psf_pin, out_pin)]
-    for _ in range(n_callers - 1):
+    per_caller = nv * (4 * ovox + 4 * kvox + 2 * ovox)          # pinned outputs + PSFs + uint16 staging
+    for _ in range(2):
+        try:
+            import psutil
+            if psutil.virtual_memory().available < 3 * world * per_caller:      # never drive the box towards its memory limit
+                break
+        except ImportError:
+            pass
         try:
             callers.append((mv.Context(local_rank), [mv.PinnedBuffer(kshape) for _ in range(nv)], [mv.PinnedBuffer(oshape) for _ in range(nv)]))
         except (MemoryError, mv.MvsimError):
@@ -335,57 +361,76 @@ def run_ours(args, rank, world, local_rank):
     n_callers = int(grp.min(len(callers)))      # the same number on every rank
     callers = callers[:n_callers]
     pipe_steps = 4 * n_callers
+    gt_tensor = torch.empty(shape, dtype=torch.float32, device=torch.device("cuda", local_rank)) if world > 1 else None
 
     def caller_loop(i, n):
         for _ in range(n):
             step_e2e(*callers[i])
-    pipe_ms = float("inf")
-    if n_callers > 1:
-        for i in range(1, n_callers):       # warm the other contexts' workspaces
+
+    def step_bcast():
+        for v in range(nv):
+            psf_pin[v].array[...] = psf_raw[v]
+        vol, _ = grp.broadcast_ground_truth(ctx, shape, host=gt_pin.array if rank == 0 else None, tensor=gt_tensor)
+        S.simulateViews(vol, [p.array for p in psf_pin], degrees, inc=inc, poissonSNR=snr, rnd=464232194, ctx=ctx,
+                        outs=[o.array for o in out_pin], first_stream=rank * nv)
+        vol.free()
+
+    def checksum(outs):
+        return float(outs[0].array[::7, ::31, ::29].astype(np.float64).mean())
+
+    def run_modes(uint16):
+        """All e2e modes with one count transport; returns {mode: ms per step (max over ranks)} and the result checksum."""
+        for c, _, _ in callers:
+            c.count_transport(uint16)
+        res = {}
+        for i in range(n_callers):           # warm every context (workspaces, staging buffers)
             caller_loop(i, 1)
-        barrier()
-        threads = [threading.Thread(target=caller_loop, args=(i, pipe_steps // n_callers)) for i in range(n_callers)]
-        t0 = time.perf_counter()
-        for t in threads:
-            t.start()
-        for t in threads:
-            t.join()                        # every call returns only after its results are in the host buffers
-        torch.cuda.synchronize()
-        pipe_ms = (time.perf_counter() - t0) * 1e3 / pipe_steps
-    pipe_ms = max_over_ranks(pipe_ms)
-    barrier()
-    pipe_checksum = float(callers[-1][2][0].array[::7, ::31, ::29].astype(np.float64).mean())
-
-    # Shared ground truth (N > 1): the views of ONE dataset are sharded over the ranks, so rank 0 uploads the ground truth
-    # once and NCCL broadcasts it over NVLink; every rank then uploads only its PSFs and downloads its own results.
-    bcast_ms = float("inf")
-    if world > 1:
-        gt_tensor = torch.empty(shape, dtype=torch.float32, device=torch.device("cuda", local_rank))
-
-        def step_bcast():
-            for v in range(nv):
-                psf_pin[v].array[...] = psf_raw[v]
-            vol, _ = grp.broadcast_ground_truth(ctx, shape, host=gt_pin.array if rank == 0 else None, tensor=gt_tensor)
-            S.simulateViews(vol, [p.array for p in psf_pin], degrees, inc=inc, poissonSNR=snr, rnd=464232194, ctx=ctx,
-                            outs=[o.array for o in out_pin], first_stream=rank * nv)
-            vol.free()
-        step_bcast()
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            step_bcast()
+            step_e2e()
         barrier()
-        bcast_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / e2e_steps)
-        bcast_checksum = float(out_pin[0].array[::7, ::31, ::29].astype(np.float64).mean())
-        if bcast_checksum != result_checksum:
-            raise SystemExit(f"bench.py: broadcast ground truth changed the result ({bcast_checksum} vs {result_checksum})")
-    modes = {"1 caller thread per rank, ground truth uploaded by every rank": serial_ms,
-             f"{n_callers} caller threads x 1 context each per rank, steps dealt round-robin (H2D of one step runs under the kernels and D2H of the others)": pipe_ms,
-             "views of one dataset sharded over the ranks: ground truth uploaded once by rank 0 and NCCL-broadcast over NVLink": bcast_ms}
-    e2e_mode = min(modes, key=modes.get)
-    e2e_ms = modes[e2e_mode]
-    if e2e_ms == bcast_ms and world > 1:
-        h2d = 4 * vox_per_view // world + nv * 4 * int(np.prod(kshape))      # per rank, averaged: one upload for all ranks
+        res["serial"] = max_over_ranks((time.perf_counter() - t0) * 1e3 / e2e_steps)
+        chk = checksum(out_pin)
+        if n_callers > 1:
+            barrier()
+            threads = [threading.Thread(target=caller_loop, args=(i, pipe_steps // n_callers)) for i in range(n_callers)]
+            t0 = time.perf_counter()
+            for t in threads:
+                t.start()
+            for t in threads:
+                t.join()                        # every call returns only after its results are in the host buffers
+            torch.cuda.synchronize()
+            res["pipelined"] = max_over_ranks((time.perf_counter() - t0) * 1e3 / pipe_steps)
+            barrier()
+            if checksum(callers[-1][2]) != chk:
+                raise SystemExit("bench.py: concurrent callers changed the result")
+        if world > 1:
+            step_bcast()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                step_bcast()
+            barrier()
+            res["broadcast"] = max_over_ranks((time.perf_counter() - t0) * 1e3 / e2e_steps)
+            if checksum(out_pin) != chk:
+                raise SystemExit("bench.py: broadcast ground truth changed the result")
+        return res, chk
+
+    MODE_TEXT = {"serial": "1 caller thread per rank, ground truth uploaded by every rank",
+                 "pipelined": f"{n_callers} caller threads x 1 context each per rank, steps dealt round-robin (H2D of one step runs under the kernels and D2H of the others)",
+                 "broadcast": "views of one dataset sharded over the ranks: ground truth uploaded once by rank 0 and NCCL-broadcast over NVLink, 1 caller per rank"}
+    modes_f32, chk_f32 = run_modes(False)
+    modes_u16, result_checksum = run_modes(True)
+    if chk_f32 != result_checksum:
+        raise SystemExit(f"bench.py: the uint16 count transport changed the result ({result_checksum} vs {chk_f32})")
+    e2e_key = min(modes_u16, key=modes_u16.get)
+    e2e_ms = modes_u16[e2e_key]
+    e2e_mode = MODE_TEXT[e2e_key]
+    h2d = (4 * vox_per_view // world if e2e_key == "broadcast" else 4 * vox_per_view) + nv * 4 * kvox      # per rank (broadcast: one upload for all)
+    d2h = nv * (2 * ovox + 4 * kvox + 4)            # uint16 counts + the normalised PSFs + the overflow flags
+    d2h_f32 = nv * 4 * (ovox + kvox)
+    link = host_link_probe(torch) if rank == 0 else None
 
     if rank != 0:
         grp.close()
@@ -462,11 +507,17 @@ def run_ours(args, rank, world, local_rank):
             "views_per_s": world * nv / (ms_step * 1e-3), "ms_per_view": view_ms,
             "e2e": {"value": world * nv * vox_per_view / (e2e_ms * 1e-3), "unit": "voxels/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "views_per_s": world * nv / (e2e_ms * 1e-3),
-                    "api": "mvsim_simulate_views / mvsim_dev_simulate_views (pinned host buffers)",
-                    "steps": pipe_steps if e2e_ms == pipe_ms else e2e_steps, "mode": e2e_mode,
-                    "serial_ms_per_step": serial_ms, "pipelined_ms_per_step": pipe_ms if math.isfinite(pipe_ms) else None,
-                    "broadcast_ms_per_step": bcast_ms if math.isfinite(bcast_ms) else None, "callers": n_callers,
-                    "result_checksum": result_checksum, "result_checksum_second_caller": pipe_checksum},
+                    "api": "mvsim_simulate_views / mvsim_dev_simulate_views (pinned host buffers in, float32 volumes out)",
+                    "steps": pipe_steps if e2e_key == "pipelined" else e2e_steps, "mode": e2e_mode, "callers": n_callers,
+                    "count_transport": ("uint16 (opt-in MVSIM_OPT_COUNT_TRANSPORT): Poisson counts cross the host link as uint16 and host threads widen "
+                                        "them to the caller's float32 buffers inside the timed call; results bit-identical to the float32 transport"),
+                    "ms_per_step_by_mode": modes_u16, "ms_per_step_by_mode_float32_transport": modes_f32,
+                    "float32_transport": {"value": world * nv * vox_per_view / (min(modes_f32.values()) * 1e-3), "ms_per_step": min(modes_f32.values()),
+                                          "d2h_bytes_per_step": d2h_f32},
+                    "host_link": link,
+                    "frac_of_host_link": (max(h2d / link["h2d_concurrent_GBps"], d2h / link["d2h_concurrent_GBps"]) / 1e9 / (e2e_ms * 1e-3)) if link else None,
+                    "frac_of_host_link_basis": "time the busier direction needs at the rate measured with both directions active / e2e time per step (1 GPU active)",
+                    "result_checksum": result_checksum},
             "gpu_launches": launches, "roofline": roofline, "stages": stages_ms, "fft_ms_per_launch": fft_passes,
             "fft_padded_xyz": [int(nfft[0]), int(ny), int(nz)], "cpu_baseline": cpu, "clocks": clk}
     print(json.dumps(line), flush=True)

@@ -72,8 +72,21 @@ typedef struct mvsim_view_params {
 enum {
     MVSIM_T_H2D = 0, MVSIM_T_ROTATE, MVSIM_T_ATTENUATE, MVSIM_T_PSF, MVSIM_T_FFT_XFWD, MVSIM_T_FFT_YFWD,
     MVSIM_T_FFT_ZFUSED, MVSIM_T_FFT_YINV, MVSIM_T_FFT_XINV, MVSIM_T_ADJUST, MVSIM_T_SAMPLE, MVSIM_T_D2H,
+    MVSIM_T_WIDEN,          /* host: uint16 counts -> float32 (count transport), wall-clock milliseconds of the widening threads */
     MVSIM_NSTAGES
 };
+
+/* context options (mvsim_ctx_set_option) */
+enum {
+    /* 1: in the batch calls (mvsim_simulate_views / mvsim_dev_simulate_views) the Poisson counts of a view (snr >= 0) cross the host
+     * link as uint16 -- half the device->host bytes, which bound the end-to-end rate -- and are widened to the float32 of the
+     * reference's API (Img<FloatType>) by host threads inside the call, overlapped with the later views.  Results are bit-identical to
+     * the float32 transport; a view with a count above 65535 is fetched as float32 instead.  0 (default): float32. */
+    MVSIM_OPT_COUNT_TRANSPORT = 1,
+    /* host threads that widen (0 = default: half the processors, at most 8) */
+    MVSIM_OPT_HOST_THREADS = 2
+};
+int mvsim_ctx_set_option(mvsim_ctx* ctx, int option, int64_t value);
 
 /* ---- library / context ------------------------------------------------------------------- */
 int mvsim_version(void);
@@ -225,6 +238,25 @@ int mvsim_slabconv_finish(mvsim_ctx* ctx, mvsim_slabconv* plan, float* d_out_sla
 int mvsim_slabconv_p2p_alloc(mvsim_ctx* ctx, mvsim_slabconv* plan, int nbuf, unsigned char* handles_out /* 2*nbuf*64 bytes */);
 int mvsim_slabconv_p2p_open(mvsim_ctx* ctx, mvsim_slabconv* plan, const unsigned char* all_handles /* world*2*nbuf*64 bytes, rank major */);
 int mvsim_slabconv_p2p_select(mvsim_slabconv* plan, int buffer_set);
+
+
+/* ---- the stages around the decomposed convolution: ONE view of a volume distributed by z slabs (DEVICE pointers) ----------
+ * rank r owns the output planes [z0, z0 + z_local) of every stage.  Order, mirroring the loop body S/SimulateMultiViewDataset.java:570-585:
+ *   mvsim_slab_rotate_attenuate (:570,573)  -> mvsim_slabconv_* (:580) -> mvsim_slab_sum, [all-gather of `world` doubles, rank order],
+ *   mvsim_slab_adjust (:582, Tools.adjustImage S/Tools.java:143-159) -> mvsim_slab_extract (:585).
+ * The ground truth stays WHOLE on every rank (generated there or broadcast over NVLink): a rotation about x reads source planes far
+ * outside the output slab.  Only rotations about axis 0 (the reference's) are decomposed. */
+int mvsim_slab_rotate_attenuate(mvsim_ctx* ctx, const float* d_gt, const int64_t dims[3], int axis, int degrees, double delta, int strict_reference,
+                                int64_t z0, int64_t z_local, float* d_out_slab);
+/* deterministic double sum of this rank's slab -> *d_sum (device memory) */
+int mvsim_slab_sum(mvsim_ctx* ctx, const float* d_slab, size_t n_local, double* d_sum);
+/* d_sums = the `world` per-rank sums in rank order (added in that order, so the correction is the same on every rank and does not depend on
+ * the collective's reduction order); n_global = voxels of the whole volume.  In place: t = f32(f32(t * corr) + min_value). */
+int mvsim_slab_adjust(mvsim_ctx* ctx, float* d_slab, size_t n_local, const double* d_sums, int world, double n_global, float min_value, float target_avg);
+/* keeps the global planes z % inc == 0 that fall into the slab, compacted in order (*planes_out of them; d_out must hold
+ * X*Y*((z_local-1)/inc+1) floats).  Philox counters are GLOBAL output voxel indices: the noise does not depend on the decomposition. */
+int mvsim_slab_extract(mvsim_ctx* ctx, const float* d_slab, const int64_t dims[3], int64_t z0, int64_t z_local, int inc, float snr, uint64_t seed,
+                       uint64_t stream, float* d_out, int64_t* planes_out);
 
 #ifdef __cplusplus
 }

@@ -10,4 +10,4 @@ from .api import (Context, DeviceVolume, JavaRandom, PinnedBuffer, SimulateBeads
 from .drivers import SimulateTileStitching, default_psf, open_psf, run_main   # noqa: F401
 from .distributed import Group                         # noqa: F401
 from .sharding import views_for_rank                   # noqa: F401
-from .slab import SlabConvolution                      # noqa: F401
+from .slab import SlabConvolution, SlabView            # noqa: F401

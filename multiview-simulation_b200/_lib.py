@@ -11,7 +11,8 @@ LIB_PATH = os.environ.get("MVSIM_LIB") or os.path.join(_PKG, "libmvsim.so")
 
 MVSIM_OK, MVSIM_EINVAL, MVSIM_ENOMEM, MVSIM_ECUDA, MVSIM_ENCCL, MVSIM_EUNSUPPORTED = range(6)
 STAGE_NAMES = ["h2d", "rotate", "attenuate", "psf", "fft_xfwd", "fft_yfwd", "fft_zfused", "fft_yinv", "fft_xinv",
-               "adjust", "sample", "d2h"]
+               "adjust", "sample", "d2h", "widen"]
+OPT_COUNT_TRANSPORT, OPT_HOST_THREADS = 1, 2
 NSTAGES = len(STAGE_NAMES)
 
 
@@ -45,6 +46,7 @@ SYMBOLS = [
     ("mvsim_profile_reset", C.c_int, [_vp]),
     ("mvsim_stage_times", C.c_int, [_vp, _dp, _i64p]),
     ("mvsim_kernel_launches", C.c_int64, [_vp]),
+    ("mvsim_ctx_set_option", C.c_int, [_vp, C.c_int, C.c_int64]),
     ("mvsim_psf_cache_configure", C.c_int, [_vp, C.c_size_t]),
     ("mvsim_psf_cache_stats", C.c_int, [_vp, _i64p]),
     ("mvsim_alloc_pinned", C.c_int, [C.c_size_t, C.POINTER(_vp)]),
@@ -99,6 +101,10 @@ SYMBOLS = [
     ("mvsim_slabconv_p2p_alloc", C.c_int, [_vp, _vp, C.c_int, _vp]),
     ("mvsim_slabconv_p2p_open", C.c_int, [_vp, _vp, _vp]),
     ("mvsim_slabconv_p2p_select", C.c_int, [_vp, C.c_int]),
+    ("mvsim_slab_rotate_attenuate", C.c_int, [_vp, _vp, _i64p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int64, C.c_int64, _vp]),
+    ("mvsim_slab_sum", C.c_int, [_vp, _vp, C.c_size_t, _vp]),
+    ("mvsim_slab_adjust", C.c_int, [_vp, _vp, C.c_size_t, _vp, C.c_int, C.c_double, C.c_float, C.c_float]),
+    ("mvsim_slab_extract", C.c_int, [_vp, _vp, _i64p, C.c_int64, C.c_int64, C.c_int, C.c_float, C.c_uint64, C.c_uint64, _vp, _i64p]),
 ]
 
 _lib = None

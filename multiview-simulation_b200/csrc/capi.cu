@@ -5,9 +5,16 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <stdlib.h>
+#include <thread>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 
 #include "ctx.h"
 #include "fft/conv_plan.h"
@@ -186,6 +193,119 @@ struct Activate {
     mvsim::Activate act__(ctx);                                                              \
     if (!act__.ok) return mvsim::set_error((ctx), MVSIM_ECUDA, "cannot select CUDA device %d", (ctx)->device)
 
+// ---- host side of the uint16 count transport ------------------------------------------------------------------------
+// uint16 -> float32, streaming stores (the destination is written once and not read back by these threads)
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) static void widen_avx2(const unsigned short* src, float* dst, size_t n)
+{
+    size_t i = 0;
+    while (i < n && (reinterpret_cast<uintptr_t>(dst + i) & 31)) { dst[i] = (float)src[i]; ++i; }
+    for (; i + 16 <= n; i += 16) {
+        const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(src + i));
+        _mm256_stream_ps(dst + i, _mm256_cvtepi32_ps(_mm256_cvtepu16_epi32(_mm256_castsi256_si128(v))));
+        _mm256_stream_ps(dst + i + 8, _mm256_cvtepi32_ps(_mm256_cvtepu16_epi32(_mm256_extracti128_si256(v, 1))));
+    }
+    for (; i < n; ++i) dst[i] = (float)src[i];
+    _mm_sfence();
+}
+#endif
+static void widen_range(const unsigned short* src, float* dst, size_t n)
+{
+#if defined(__x86_64__)
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    if (avx2) { widen_avx2(src, dst, n); return; }
+#endif
+    for (size_t i = 0; i < n; ++i) dst[i] = (float)src[i];
+}
+
+// a few persistent threads per context; run() splits one view over them (and the caller) and returns when it is done
+class WidenPool {
+public:
+    explicit WidenPool(int threads) : stop_(false), job_(0), pending_(0)
+    {
+        for (int t = 0; t < threads; ++t) workers_.emplace_back([this, t] { loop(t); });
+    }
+    ~WidenPool()
+    {
+        { std::lock_guard<std::mutex> lk(m_); stop_ = true; }
+        cv_.notify_all();
+        for (auto& w : workers_) w.join();
+    }
+    void run(const unsigned short* src, float* dst, size_t n)
+    {
+        const size_t parts = workers_.size() + 1;
+        const size_t chunk = ((n + parts - 1) / parts + 63) / 64 * 64;
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            src_ = src; dst_ = dst; n_ = n; chunk_ = chunk;
+            pending_ = (int)workers_.size();
+            ++job_;
+        }
+        cv_.notify_all();
+        const size_t a = workers_.size() * chunk;               // the caller takes the last part
+        if (a < n) widen_range(src + a, dst + a, n - a);
+        std::unique_lock<std::mutex> lk(m_);
+        done_.wait(lk, [this] { return pending_ == 0; });
+    }
+private:
+    void loop(int t)
+    {
+        unsigned long long seen = 0;
+        for (;;) {
+            const unsigned short* src; float* dst; size_t n, chunk;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return stop_ || job_ != seen; });
+                if (stop_) return;
+                seen = job_; src = src_; dst = dst_; n = n_; chunk = chunk_;
+            }
+            const size_t a = (size_t)t * chunk, b = a + chunk < n ? a + chunk : n;
+            if (a < n) widen_range(src + a, dst + a, b - a);
+            {
+                std::lock_guard<std::mutex> lk(m_);
+                if (--pending_ == 0) done_.notify_all();
+            }
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    bool stop_;
+    unsigned long long job_;
+    int pending_;
+    const unsigned short* src_ = nullptr;
+    float* dst_ = nullptr;
+    size_t n_ = 0, chunk_ = 0;
+};
+
+static WidenPool* widen_pool(mvsim_ctx* ctx)
+{
+    if (!ctx->widen_pool) {
+        int t = ctx->host_threads;
+        if (t <= 0) {
+            const unsigned hw = std::thread::hardware_concurrency();
+            t = hw >= 16 ? 8 : (hw >= 4 ? (int)hw / 2 : 1);
+        }
+        ctx->widen_pool = new WidenPool(t > 1 ? t - 1 : 0);      // the calling thread is one of the t
+    }
+    return static_cast<WidenPool*>(ctx->widen_pool);
+}
+
+// pinned staging buffer #i of at least `bytes` (kept across calls: cudaHostAlloc of 200 MB costs tens of milliseconds)
+static int staging_buffer(mvsim_ctx* ctx, size_t i, size_t bytes, void** out)
+{
+    if (ctx->staging.size() <= i) ctx->staging.resize(i + 1, { nullptr, 0 });
+    auto& s = ctx->staging[i];
+    if (s.bytes < bytes) {
+        if (s.p) cudaFreeHost(s.p);
+        s.p = nullptr; s.bytes = 0;
+        MVSIM_CUDA(ctx, cudaHostAlloc(&s.p, bytes, cudaHostAllocDefault));
+        s.bytes = bytes;
+    }
+    *out = s.p;
+    return MVSIM_OK;
+}
+
 // ---- device-level building blocks ---------------------------------------------------------
 static int dev_rotate(mvsim_ctx* ctx, const float* in, float* out, const int64_t dims[3], int axis, int degrees)
 {
@@ -235,7 +355,8 @@ static int check_view(mvsim_ctx* ctx, const mvsim_view_params* p)
 }
 
 // loop body S/SimulateMultiViewDataset.java:570-585 on device pointers
-static int dev_simulate_view(mvsim_ctx* ctx, const mvsim_view_params* p, const float* gt, float* psf, float* out)
+static int dev_simulate_view(mvsim_ctx* ctx, const mvsim_view_params* p, const float* gt, float* psf, float* out,
+                             unsigned short* out16 = nullptr, int* d_overflow = nullptr)
 {
     const size_t n = elems(p->dims);
     DevBuf a(ctx), b(ctx);
@@ -268,9 +389,9 @@ static int dev_simulate_view(mvsim_ctx* ctx, const mvsim_view_params* p, const f
     if (planes != p->dims[2]) {
         // the convolution already delivered the kept slices compacted (plus the sum plane, unused here)
         const int64_t kept[3] = { p->dims[0], p->dims[1], (p->dims[2] - 1) / p->inc + 1 };
-        return k_extract(ctx, a.f(), kept, 1, ctx->d_scalars + 2, p->min_value, p->snr, p->seed, p->stream, out);
+        return k_extract_u16(ctx, a.f(), kept, 1, ctx->d_scalars + 2, p->min_value, p->snr, p->seed, p->stream, out, out16, d_overflow);
     }
-    return k_extract(ctx, a.f(), p->dims, p->inc, ctx->d_scalars + 2, p->min_value, p->snr, p->seed, p->stream, out);
+    return k_extract_u16(ctx, a.f(), p->dims, p->inc, ctx->d_scalars + 2, p->min_value, p->snr, p->seed, p->stream, out, out16, d_overflow);
 }
 
 }  // namespace mvsim
@@ -311,6 +432,9 @@ static int ctx_create(int device, bool own, void* cuda_stream, mvsim_ctx** out)
     ctx->psf_cache_tick = ctx->psf_cache_hits = ctx->psf_cache_misses = 0;
     ctx->d_hash = nullptr;
     ctx->h_hash = nullptr;
+    ctx->count_transport = 0;
+    ctx->host_threads = 0;
+    ctx->widen_pool = nullptr;
     ctx->profiling = false;
     memset(ctx->acc_ms, 0, sizeof(ctx->acc_ms));
     memset(ctx->acc_n, 0, sizeof(ctx->acc_n));
@@ -362,6 +486,8 @@ int mvsim_ctx_destroy(mvsim_ctx* ctx)
     for (auto& e : ctx->psf_cache) cudaFree(e.p2);
     if (ctx->d_hash) cudaFree(ctx->d_hash);
     if (ctx->h_hash) cudaFreeHost(ctx->h_hash);
+    for (auto& st : ctx->staging) if (st.p) cudaFreeHost(st.p);
+    delete static_cast<mvsim::WidenPool*>(ctx->widen_pool);
     for (auto& ev : ctx->events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
     for (auto& ev : ctx->pool) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
     cudaFree(ctx->d_scalars);
@@ -423,6 +549,23 @@ int mvsim_stage_times(mvsim_ctx* ctx, double ms[MVSIM_NSTAGES], int64_t launches
 }
 
 int64_t mvsim_kernel_launches(mvsim_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int mvsim_ctx_set_option(mvsim_ctx* ctx, int option, int64_t value)
+{
+    if (!ctx) return set_error(nullptr, MVSIM_EINVAL, "null context");
+    switch (option) {
+    case MVSIM_OPT_COUNT_TRANSPORT:
+        if (value != 0 && value != 1) return set_error(ctx, MVSIM_EINVAL, "count transport: 0 (float32) or 1 (uint16)");
+        ctx->count_transport = (int)value;
+        return MVSIM_OK;
+    case MVSIM_OPT_HOST_THREADS:
+        if (value < 0 || value > 256) return set_error(ctx, MVSIM_EINVAL, "host threads: 0 (default) .. 256");
+        if (ctx->widen_pool) { delete static_cast<mvsim::WidenPool*>(ctx->widen_pool); ctx->widen_pool = nullptr; }
+        ctx->host_threads = (int)value;
+        return MVSIM_OK;
+    }
+    return set_error(ctx, MVSIM_EINVAL, "unknown option %d", option);
+}
 
 int mvsim_psf_cache_configure(mvsim_ctx* ctx, size_t max_bytes)
 {
@@ -666,6 +809,54 @@ static int simulate_views_impl(mvsim_ctx* ctx, int n_views, const mvsim_view_par
         if ((st = dev_alloc(ctx, &o, obytes)) != MVSIM_OK) break;
         held.push_back(o);
     }
+    // Count transport (MVSIM_OPT_COUNT_TRANSPORT, views with Poisson noise): the sampler also writes the counts as uint16; those
+    // cross the link into a pinned staging buffer and host threads widen them into the caller's float32 buffer while later views
+    // still compute / copy.  A view whose counts exceed 65535 (flag) is fetched again as float32.
+    struct U16View { unsigned short* d16; unsigned short* h16; int* d_flag; int* h_flag; cudaEvent_t copied; bool on; };
+    std::vector<U16View> u16((size_t)n_views, U16View{ nullptr, nullptr, nullptr, nullptr, nullptr, false });
+    int* h_flags = nullptr;
+    if (st == MVSIM_OK && ctx->count_transport == 1) {
+        void* hf = nullptr;
+        st = staging_buffer(ctx, 0, (size_t)n_views * sizeof(int) + 64, &hf);
+        h_flags = static_cast<int*>(hf);
+        for (int v = 0; v < n_views && st == MVSIM_OK; ++v) {
+            if (!(params[v].snr >= 0.0f)) continue;
+            const size_t n_out = (size_t)(params[v].dims[0] * params[v].dims[1] * ((params[v].dims[2] - 1) / params[v].inc + 1));
+            void *d16 = nullptr, *dflag = nullptr, *h16 = nullptr;
+            if ((st = dev_alloc(ctx, &d16, n_out * sizeof(unsigned short))) != MVSIM_OK) break;
+            held.push_back(d16);
+            if ((st = dev_alloc(ctx, &dflag, 16)) != MVSIM_OK) break;
+            held.push_back(dflag);
+            if ((st = staging_buffer(ctx, (size_t)v + 1, n_out * sizeof(unsigned short), &h16)) != MVSIM_OK) break;
+            U16View& u = u16[(size_t)v];
+            u.d16 = static_cast<unsigned short*>(d16); u.h16 = static_cast<unsigned short*>(h16);
+            u.d_flag = static_cast<int*>(dflag); u.h_flag = h_flags + v;
+            if (cudaEventCreateWithFlags(&u.copied, cudaEventDisableTiming) != cudaSuccess) { st = set_error(ctx, MVSIM_ECUDA, "simulate_views: cannot create events"); break; }
+            u.on = true;
+        }
+    }
+    int next_u16 = 0;
+    auto finish_u16 = [&](int v) -> int {
+        U16View& u = u16[(size_t)v];
+        if (!u.on) return MVSIM_OK;
+        if (cudaEventSynchronize(u.copied) != cudaSuccess) return set_error(ctx, MVSIM_ECUDA, "simulate_views: download failed");
+        const mvsim_view_params* p = &params[v];
+        const size_t n_out = (size_t)(p->dims[0] * p->dims[1] * ((p->dims[2] - 1) / p->inc + 1));
+        if (*u.h_flag) {
+            // counts beyond uint16: this view travels as float32 after all
+            cudaError_t e = cudaMemcpyAsync(outs[v], held[2 * v + 1], n_out * sizeof(float), cudaMemcpyDeviceToHost, ctx->copy_stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->copy_stream);
+            if (e != cudaSuccess) return cuda_fail(ctx, e, "simulate_views: float32 fallback download");
+        } else {
+            const auto t0 = std::chrono::steady_clock::now();
+            widen_pool(ctx)->run(u.h16, outs[v], n_out);
+            if (ctx->profiling) {
+                ctx->acc_ms[MVSIM_T_WIDEN] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+                ctx->acc_n[MVSIM_T_WIDEN] += 1;
+            }
+        }
+        return MVSIM_OK;
+    };
     if (st == MVSIM_OK) {
         // upload gate: two contexts never share the host->device link, so the second caller's upload runs at full rate
         // under the first caller's kernels instead of both uploads at half rate followed by both kernel phases.  ALL of
@@ -685,25 +876,41 @@ static int simulate_views_impl(mvsim_ctx* ctx, int n_views, const mvsim_view_par
         for (int v = 0; v < n_views && st == MVSIM_OK; ++v) {
             const mvsim_view_params* p = &params[v];
             const size_t kbytes = elems(p->kdims) * sizeof(float);
-            const size_t obytes = (size_t)(p->dims[0] * p->dims[1] * ((p->dims[2] - 1) / p->inc + 1)) * sizeof(float);
+            const size_t n_out = (size_t)(p->dims[0] * p->dims[1] * ((p->dims[2] - 1) / p->inc + 1));
             void *k = held[2 * v], *o = held[2 * v + 1];
-            if ((st = dev_simulate_view(ctx, p, gt_dev, static_cast<float*>(k), static_cast<float*>(o))) != MVSIM_OK) break;
-            cudaError_t e = cudaEventRecord(done, ctx->stream);
+            U16View& u = u16[(size_t)v];
+            cudaError_t e = cudaSuccess;
+            if (u.on) e = cudaMemsetAsync(u.d_flag, 0, sizeof(int), ctx->stream);
+            if (e != cudaSuccess) { st = cuda_fail(ctx, e, "simulate_views: flag"); break; }
+            if ((st = dev_simulate_view(ctx, p, gt_dev, static_cast<float*>(k), static_cast<float*>(o), u.on ? u.d16 : nullptr, u.on ? u.d_flag : nullptr)) != MVSIM_OK) break;
+            e = cudaEventRecord(done, ctx->stream);
             if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy_stream, done, 0);
             if (e == cudaSuccess) e = cudaMemcpyAsync(psfs[v], k, kbytes, cudaMemcpyDeviceToHost, ctx->copy_stream);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(outs[v], o, obytes, cudaMemcpyDeviceToHost, ctx->copy_stream);
+            if (u.on) {
+                if (e == cudaSuccess) e = cudaMemcpyAsync(u.h_flag, u.d_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->copy_stream);
+                if (e == cudaSuccess) e = cudaMemcpyAsync(u.h16, u.d16, n_out * sizeof(unsigned short), cudaMemcpyDeviceToHost, ctx->copy_stream);
+                if (e == cudaSuccess) e = cudaEventRecord(u.copied, ctx->copy_stream);
+            } else if (e == cudaSuccess) {
+                e = cudaMemcpyAsync(outs[v], o, n_out * sizeof(float), cudaMemcpyDeviceToHost, ctx->copy_stream);
+            }
             if (e != cudaSuccess) st = cuda_fail(ctx, e, "simulate_views: download");
         }
-        // the gate opens when the last kernel has run; the tail of the downloads overlaps the next caller's kernels
         stamp("enqueued");
+        // uint16 views: as each copy lands, widen it into the caller's buffer while the later views still compute / copy -- but
+        // only until this call's last kernel has run: then the gate opens and the rest is finished outside it
+        while (st == MVSIM_OK && next_u16 < n_views - 1 && cudaEventQuery(done) == cudaErrorNotReady) st = finish_u16(next_u16++);
+        cudaGetLastError();     // cudaErrorNotReady from the query is not an error
+        // the gate opens when the last kernel has run; the tail of the downloads overlaps the next caller's kernels
         if (st == MVSIM_OK && cudaEventSynchronize(done) != cudaSuccess) st = set_error(ctx, MVSIM_ECUDA, "simulate_views: kernels failed");
         stamp("kernels done");
     }
+    while (st == MVSIM_OK && next_u16 < n_views) st = finish_u16(next_u16++);
     // the main stream waits for the copy stream before the buffers go back to the pool
     if (cudaEventRecord(copied, ctx->copy_stream) == cudaSuccess) cudaStreamWaitEvent(ctx->stream, copied, 0);
     for (void* q : held) dev_free(ctx, q);
     const int st2 = sync(ctx);
     stamp("downloads done");
+    for (auto& u : u16) if (u.copied) cudaEventDestroy(u.copied);
     cudaEventDestroy(done);
     cudaEventDestroy(copied);
     return st != MVSIM_OK ? st : st2;
@@ -1122,6 +1329,54 @@ int mvsim_dev_simulate_view(mvsim_ctx* ctx, const mvsim_view_params* p, const mv
     if (out->dims[0] != p->dims[0] || out->dims[1] != p->dims[1] || out->dims[2] != (p->dims[2] - 1) / p->inc + 1)
         return set_error(ctx, MVSIM_EINVAL, "dev_simulate_view: out dims must be (X, Y, (Z-1)/inc+1)");
     return dev_simulate_view(ctx, p, gt->d, psf->d, out->d);
+}
+
+
+// ---- the rest of the loop body (:570-585) for ONE view whose volume is decomposed by z slabs over ranks (BASELINE config 5) ------
+// convolve is mvsim_slabconv_*; these are the stages around it.  All pointers are DEVICE pointers.
+int mvsim_slab_rotate_attenuate(mvsim_ctx* ctx, const float* d_gt, const int64_t dims[3], int axis, int degrees, double delta, int strict_reference,
+                                int64_t z0, int64_t z_local, float* d_out_slab)
+{
+    MVSIM_ENTER(ctx);
+    if (!d_gt || !d_out_slab) return set_error(ctx, MVSIM_EINVAL, "slab_rotate_attenuate: null buffer");
+    MVSIM_TRY(check_dims(ctx, dims, "slab_rotate_attenuate"));
+    if (z0 < 0 || z_local < 1 || z0 + z_local > dims[2]) return set_error(ctx, MVSIM_EINVAL, "slab_rotate_attenuate: slab outside the volume");
+    double inv[12];
+    int steps = 0;
+    if (axis_rotation(dims, axis, degrees, nullptr, inv)) return set_error(ctx, MVSIM_EINVAL, "slab_rotate_attenuate: axis must be 0, 1 or 2");
+    MVSIM_TRY(attenuate_steps(ctx, dims, strict_reference, &steps));
+    StageTimer t(ctx, MVSIM_T_ROTATE);
+    const int st = k_rotate_attenuate(ctx, d_gt, d_out_slab, dims, axis, inv, delta, steps, z0, z_local);
+    if (st == MVSIM_EUNSUPPORTED) return set_error(ctx, MVSIM_EUNSUPPORTED, "slab_rotate_attenuate: only rotations about axis 0 (the reference's) are decomposed");
+    return st;
+}
+
+int mvsim_slab_sum(mvsim_ctx* ctx, const float* d_slab, size_t n_local, double* d_sum)
+{
+    MVSIM_ENTER(ctx);
+    if (!d_slab || !d_sum) return set_error(ctx, MVSIM_EINVAL, "slab_sum: null buffer");
+    StageTimer t(ctx, MVSIM_T_ADJUST);
+    return k_sum(ctx, d_slab, n_local, d_sum);
+}
+
+int mvsim_slab_adjust(mvsim_ctx* ctx, float* d_slab, size_t n_local, const double* d_sums, int world, double n_global, float min_value, float target_avg)
+{
+    MVSIM_ENTER(ctx);
+    if (!d_slab || !d_sums || world < 1 || !(n_global >= 1)) return set_error(ctx, MVSIM_EINVAL, "slab_adjust: bad argument");
+    StageTimer t(ctx, MVSIM_T_ADJUST);
+    MVSIM_TRY(k_adjust_corr_ranks(ctx, d_sums, world, n_global, min_value, target_avg, ctx->d_scalars + 2));
+    return k_adjust_apply(ctx, d_slab, n_local, ctx->d_scalars + 2, min_value);
+}
+
+int mvsim_slab_extract(mvsim_ctx* ctx, const float* d_slab, const int64_t dims[3], int64_t z0, int64_t z_local, int inc, float snr, uint64_t seed,
+                       uint64_t stream, float* d_out, int64_t* planes_out)
+{
+    MVSIM_ENTER(ctx);
+    if (!d_slab || !d_out) return set_error(ctx, MVSIM_EINVAL, "slab_extract: null buffer");
+    MVSIM_TRY(check_dims(ctx, dims, "slab_extract"));
+    if (inc < 1 || z0 < 0 || z_local < 1 || z0 + z_local > dims[2]) return set_error(ctx, MVSIM_EINVAL, "slab_extract: bad slab or inc");
+    StageTimer t(ctx, MVSIM_T_SAMPLE);
+    return k_extract_slab(ctx, d_slab, dims, z0, z_local, inc, nullptr, 0.f, snr, seed, stream, d_out, planes_out);
 }
 
 }  // extern "C"

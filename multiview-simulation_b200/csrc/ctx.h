@@ -40,6 +40,13 @@ struct mvsim_ctx {
     uint64_t psf_cache_tick, psf_cache_hits, psf_cache_misses;
     unsigned long long* d_hash;              // [2] device words
     unsigned long long* h_hash;              // [2] pinned host words
+    // count transport of the batch call (MVSIM_OPT_COUNT_TRANSPORT): Poisson counts cross the host link as uint16 and are widened to
+    // the float32 of the reference's API by host threads inside the call
+    int count_transport;                     // 0 = float32 (default), 1 = uint16 when snr >= 0
+    int host_threads;                        // widening threads (0 = default)
+    struct Staging { void* p; size_t bytes; };
+    std::vector<Staging> staging;            // pinned uint16 staging buffers, kept across calls
+    void* widen_pool;                        // mvsim::WidenPool*, lazily created
     int64_t launches;
     // profiling
     bool profiling;
@@ -79,14 +86,23 @@ int get_tables(mvsim_ctx* ctx, int n, mvsim_tables* t);
 
 // stage kernels (stages.cu); all enqueue on ctx->stream
 int k_rotate(mvsim_ctx* ctx, const float* in, float* out, const int64_t dims[3], int axis, const double inv[12]);
+// fused; MVSIM_EUNSUPPORTED when the rotation is not the axis-0 fast path.  z_local > 0: only the output planes [z0, z0 + z_local)
+// of the view (out = that slab), the source `in` stays the whole volume
 int k_rotate_attenuate(mvsim_ctx* ctx, const float* in, float* out, const int64_t dims[3], int axis, const double inv[12], double delta,
-                       int steps);      // fused; MVSIM_EUNSUPPORTED when the rotation is not the axis-0 fast path
+                       int steps, int64_t z0 = 0, int64_t z_local = 0);
 int k_attenuate(mvsim_ctx* ctx, const float* in, float* out, const int64_t dims[3], double delta, int steps);
 int k_sum(mvsim_ctx* ctx, const float* in, size_t n, double* d_sum);                 // deterministic double sum
 int k_sum_partials(mvsim_ctx* ctx, const double* partials, size_t n, double* d_sum);
 int k_divide_by_sum(mvsim_ctx* ctx, float* inout, size_t n, const double* d_sum);     // (float)((double)v / sum)
 int k_adjust_corr(mvsim_ctx* ctx, const double* d_sum, size_t n, float min_value, float target_avg, double* d_corr);
 int k_adjust_apply(mvsim_ctx* ctx, float* inout, size_t n, const double* d_corr, float min_value);
+int k_adjust_corr_ranks(mvsim_ctx* ctx, const double* d_sums, int world, double n_global, float min_value, float target_avg, double* d_corr);
+int k_extract_slab(mvsim_ctx* ctx, const float* in, const int64_t dims[3], int64_t z0, int64_t z_local, int inc, const double* d_corr,
+                   float min_value, float snr, uint64_t seed, uint64_t stream, float* out, int64_t* planes_out, unsigned short* out16 = nullptr,
+                   int* d_overflow = nullptr);
+// k_extract that also writes the counts as uint16 (count transport of the batch call) and ORs *d_overflow when one exceeds 65535
+int k_extract_u16(mvsim_ctx* ctx, const float* in, const int64_t dims[3], int inc, const double* d_corr, float min_value,
+                  float snr, uint64_t seed, uint64_t stream, float* out, unsigned short* out16, int* d_overflow);
 // out[x,y,cz] = f(in[x,y,cz*inc]); d_corr != null fuses adjustImage; snr >= 0 adds Poisson noise
 int k_extract(mvsim_ctx* ctx, const float* in, const int64_t dims[3], int inc, const double* d_corr, float min_value,
               float snr, uint64_t seed, uint64_t stream, float* out);

@@ -120,11 +120,12 @@ __global__ void __launch_bounds__(256) rotate_general_kernel(const float* __rest
 // ---------------------------------------------------------------------------------------------
 struct __align__(16) RowTaps { int iy, iz; float w00, w10, w11, w01; int pad0, pad1; };
 
-__global__ void __launch_bounds__(256) rotate_rowtable_kernel(RowTaps* __restrict__ tab, int Y, int Z, Affine a)
+// rows (y, z) of the output planes [z0, z0 + Zl): entry (z - z0) * Y + y
+__global__ void __launch_bounds__(256) rotate_rowtable_kernel(RowTaps* __restrict__ tab, int Y, int z0, int Zl, Affine a)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (long long)Y * Z) return;
-    const int y = (int)(i % Y), z = (int)(i / Y);
+    if (i >= (long long)Y * Zl) return;
+    const int y = (int)(i % Y), z = z0 + (int)(i / Y);
     const double ly = (double)y, lz = (double)z;
     const double py = __dadd_rn(__dadd_rn(__dmul_rn(ly, a.m[5]), __dmul_rn(lz, a.m[6])), a.m[7]);
     const double pz = __dadd_rn(__dadd_rn(__dmul_rn(ly, a.m[9]), __dmul_rn(lz, a.m[10])), a.m[11]);
@@ -160,15 +161,17 @@ template <int VEC> __device__ __forceinline__ void vload(float (&d)[VEC], const 
 
 // IDX32: the volume has < 2^31 voxels (every volume an ImgLib2 ArrayImg can hold), element offsets are 32-bit (wrapping unsigned
 // arithmetic: offsets of taps that are masked off may wrap, the ones that are dereferenced are exact)
-template <int VEC, int U, bool IDX32> __global__ void __launch_bounds__(128) rotate_attenuate_kernel(const float* __restrict__ in, float* __restrict__ out,
+template <int VEC, int U, bool IDX32, int TPB = 128> __global__ void __launch_bounds__(TPB) rotate_attenuate_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                                                         const RowTaps* __restrict__ tab, int X, int Y, int Z,
-                                                                                        double delta, int steps)
+                                                                                        double delta, int steps, int Zl)
 {
+    // `in` has Z planes; `out` and `tab` cover the Zl output planes this launch owns (Zl == Z on one GPU; a z slab of the view
+    // when the volume is decomposed over ranks -- the source stays whole: a rotation about x reads planes far outside the slab)
     using V = typename VecT<VEC>::type;
     const int XV = X / VEC;
     const long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (col >= (long long)XV * Z) return;
-    const int x0 = (int)(col % XV) * VEC, z = (int)(col / XV);
+    if (col >= (long long)XV * Zl) return;
+    const int x0 = (int)(col % XV) * VEC, z = (int)(col / XV);      // z: local plane
     using Off = typename std::conditional<IDX32, unsigned, long long>::type;
     const Off sy = (Off)X, sz = (Off)X * (Off)Y;
     const RowTaps* trow = tab + (long long)Y * z;
@@ -236,17 +239,19 @@ template <int VEC, int U, bool IDX32> __global__ void __launch_bounds__(128) rot
 }
 
 // returns MVSIM_EUNSUPPORTED when the fused path does not apply (caller falls back to the two kernels)
-int k_rotate_attenuate(mvsim_ctx* ctx, const float* in, float* out, const int64_t dims[3], int axis, const double inv[12], double delta, int steps)
+int k_rotate_attenuate(mvsim_ctx* ctx, const float* in, float* out, const int64_t dims[3], int axis, const double inv[12], double delta, int steps,
+                       int64_t z0, int64_t z_local)
 {
     const int X = (int)dims[0], Y = (int)dims[1], Z = (int)dims[2];
+    const int Zl = z_local > 0 ? (int)z_local : Z, zfirst = z_local > 0 ? (int)z0 : 0;
     const bool x_identity = axis == 0 && fabs(inv[0] - 1.0) < 1e-12 && inv[1] == 0.0 && inv[2] == 0.0 && inv[3] == 0.0 &&
                             inv[4] == 0.0 && inv[8] == 0.0;
     if (!x_identity) return MVSIM_EUNSUPPORTED;
     Affine a;
     for (int i = 0; i < 12; ++i) a.m[i] = inv[i];
     RowTaps* tab = nullptr;
-    MVSIM_TRY(dev_alloc(ctx, (void**)&tab, sizeof(RowTaps) * (size_t)Y * Z));
-    rotate_rowtable_kernel<<<blocks_for((size_t)Y * Z, 256), 256, 0, ctx->stream>>>(tab, Y, Z, a);
+    MVSIM_TRY(dev_alloc(ctx, (void**)&tab, sizeof(RowTaps) * (size_t)Y * Zl));
+    rotate_rowtable_kernel<<<blocks_for((size_t)Y * Zl, 256), 256, 0, ctx->stream>>>(tab, Y, zfirst, Zl, a);
     ctx->launches++;
     const bool aligned = (reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) % 16 == 0;
     // the march along y is sequential per column, so the grid is small (X*Z/VEC threads): pick the widest
@@ -256,15 +261,19 @@ int k_rotate_attenuate(mvsim_ctx* ctx, const float* in, float* out, const int64_
     // fifth, paced warp per CTA: 1.04 .. 1.06 ms, profiles/r02_experiments.txt -- the march already keeps 2 rows x 4 taps in
     // flight per thread and re-reads every source row from the L2.)
     if (X % 4 == 0 && aligned) {
-        const size_t cols = (size_t)(X / 4) * Z;
-        if (idx32) rotate_attenuate_kernel<4, 2, true><<<blocks_for(cols, 128), 128, 0, ctx->stream>>>(in, out, tab, X, Y, Z, delta, steps);
-        else rotate_attenuate_kernel<4, 2, false><<<blocks_for(cols, 128), 128, 0, ctx->stream>>>(in, out, tab, X, Y, Z, delta, steps);
+        const size_t cols = (size_t)(X / 4) * Zl;
+        static const int tpb_env = [] { const char* v = getenv("MVSIM_ROT_TPB"); return v ? atoi(v) : 128; }();     // experiment knob (r02)
+        if (idx32 && tpb_env == 256) rotate_attenuate_kernel<4, 2, true, 256><<<blocks_for(cols, 256), 256, 0, ctx->stream>>>(in, out, tab, X, Y, Z, delta, steps, Zl);
+        else if (idx32 && tpb_env == 512) rotate_attenuate_kernel<4, 2, true, 512><<<blocks_for(cols, 512), 512, 0, ctx->stream>>>(in, out, tab, X, Y, Z, delta, steps, Zl);
+        else if (idx32 && tpb_env == 1283) rotate_attenuate_kernel<4, 3, true><<<blocks_for(cols, 128), 128, 0, ctx->stream>>>(in, out, tab, X, Y, Z, delta, steps, Zl);
+        else if (idx32) rotate_attenuate_kernel<4, 2, true><<<blocks_for(cols, 128), 128, 0, ctx->stream>>>(in, out, tab, X, Y, Z, delta, steps, Zl);
+        else rotate_attenuate_kernel<4, 2, false><<<blocks_for(cols, 128), 128, 0, ctx->stream>>>(in, out, tab, X, Y, Z, delta, steps, Zl);
     } else if (X % 2 == 0 && aligned) {
-        const size_t cols = (size_t)(X / 2) * Z;
-        rotate_attenuate_kernel<2, 4, false><<<blocks_for(cols, 128), 128, 0, ctx->stream>>>(in, out, tab, X, Y, Z, delta, steps);
+        const size_t cols = (size_t)(X / 2) * Zl;
+        rotate_attenuate_kernel<2, 4, false><<<blocks_for(cols, 128), 128, 0, ctx->stream>>>(in, out, tab, X, Y, Z, delta, steps, Zl);
     } else {
-        const size_t cols = (size_t)X * Z;
-        rotate_attenuate_kernel<1, 4, false><<<blocks_for(cols, 128), 128, 0, ctx->stream>>>(in, out, tab, X, Y, Z, delta, steps);
+        const size_t cols = (size_t)X * Zl;
+        rotate_attenuate_kernel<1, 4, false><<<blocks_for(cols, 128), 128, 0, ctx->stream>>>(in, out, tab, X, Y, Z, delta, steps, Zl);
     }
     ctx->launches++;
     cudaError_t e = cudaGetLastError();
@@ -472,6 +481,22 @@ __global__ void adjust_corr_kernel(const double* __restrict__ d_sum, double n, f
     *d_corr = (double)__fsub_rn(target_avg, min_value) / avg;
 }
 
+// correction from the per-rank sums of a slab-decomposed volume, added in rank order (the result does not depend on the collective's
+// reduction order): avg = (sum_r s_r) / n_global
+__global__ void adjust_corr_ranks_kernel(const double* __restrict__ d_sums, int world, double n, float min_value, float target_avg, double* __restrict__ d_corr)
+{
+    double s = 0.0;
+    for (int r = 0; r < world; ++r) s += d_sums[r];
+    *d_corr = (double)__fsub_rn(target_avg, min_value) / (s / n);
+}
+
+int k_adjust_corr_ranks(mvsim_ctx* ctx, const double* d_sums, int world, double n_global, float min_value, float target_avg, double* d_corr)
+{
+    adjust_corr_ranks_kernel<<<1, 1, 0, ctx->stream>>>(d_sums, world, n_global, min_value, target_avg, d_corr);
+    MVSIM_LAUNCH_CHECK(ctx);
+    return MVSIM_OK;
+}
+
 int k_adjust_corr(mvsim_ctx* ctx, const double* d_sum, size_t n, float min_value, float target_avg, double* d_corr)
 {
     adjust_corr_kernel<<<1, 1, 0, ctx->stream>>>(d_sum, (double)n, min_value, target_avg, d_corr);
@@ -580,8 +605,13 @@ __device__ __forceinline__ void poisson_group4_block(const double (&lam)[4], uin
 // is a multiple of 4 so that the four voxels are also consecutive in the input).
 template <bool VEC4> __global__ void __launch_bounds__(kSamplerThreads) extract_kernel(const float* __restrict__ in, float* __restrict__ out, long long plane,
                                                                           long long n_out, int inc, const double* __restrict__ d_corr,
-                                                                          float min_value, int noise, double mul, PoissonKey key)
+                                                                          float min_value, int noise, double mul, PoissonKey key,
+                                                                          long long in_plane0, long long group0,
+                                                                          unsigned short* __restrict__ out16, int* __restrict__ overflow)
 {
+    // in_plane0 / group0 (slab-decomposed volume; 0 otherwise): the first kept plane of this slab is local input plane in_plane0,
+    // and the Philox counter of local voxel group g is the GLOBAL group index g + group0 -- the noise of a voxel does not depend on
+    // how the volume was decomposed
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long i0 = 4 * g;
     const bool valid = i0 < n_out;          // no early return: the sampler below is warp cooperative
@@ -589,14 +619,14 @@ template <bool VEC4> __global__ void __launch_bounds__(kSamplerThreads) extract_
     if (valid) {
         if (VEC4) {
             const long long cz = i0 / plane, r = i0 - cz * plane;
-            const float4 t = __ldg(reinterpret_cast<const float4*>(in + cz * inc * plane + r));
+            const float4 t = __ldg(reinterpret_cast<const float4*>(in + (cz * inc + in_plane0) * plane + r));
             v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
         } else {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const long long i = i0 + k < n_out ? i0 + k : n_out - 1;
                 const long long cz = i / plane, r = i - cz * plane;
-                v[k] = __ldg(in + cz * inc * plane + r);
+                v[k] = __ldg(in + (cz * inc + in_plane0) * plane + r);
             }
         }
         if (d_corr) {
@@ -610,7 +640,7 @@ template <bool VEC4> __global__ void __launch_bounds__(kSamplerThreads) extract_
         double lam[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) lam[k] = valid ? __dmul_rn((double)v[k], mul) : 0.0;
-        poisson_group4_block(lam, (uint64_t)g, key, v, sh);
+        poisson_group4_block(lam, (uint64_t)(g + group0), key, v, sh);
     }
     if (!valid) return;
     if (VEC4) {
@@ -620,6 +650,25 @@ template <bool VEC4> __global__ void __launch_bounds__(kSamplerThreads) extract_
         for (int k = 0; k < 4; ++k)
             if (i0 + k < n_out) out[i0 + k] = v[k];
     }
+    // count transport (opt-in, batch call): the same counts once more as uint16 -- half the bytes over the host link; a count
+    // beyond 65535 raises the flag and the host falls back to the float32 copy of that view
+    if (out16) {
+        bool over = false;
+        unsigned short q[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            over |= !(v[k] <= 65535.0f);
+            q[k] = (unsigned short)fminf(fmaxf(v[k], 0.f), 65535.0f);
+        }
+        if (VEC4) {
+            *reinterpret_cast<ushort4*>(out16 + i0) = make_ushort4(q[0], q[1], q[2], q[3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (i0 + k < n_out) out16[i0 + k] = q[k];
+        }
+        if (over) atomicOr(overflow, 1);
+    }
 }
 
 static double snr_to_mul(double snr) { const double q = snr / sqrt(5.0); return pow(q, 2.0); }
@@ -627,16 +676,39 @@ static double snr_to_mul(double snr) { const double q = snr / sqrt(5.0); return 
 int k_extract(mvsim_ctx* ctx, const float* in, const int64_t dims[3], int inc, const double* d_corr, float min_value,
               float snr, uint64_t seed, uint64_t stream, float* out)
 {
+    return k_extract_slab(ctx, in, dims, 0, dims[2], inc, d_corr, min_value, snr, seed, stream, out, nullptr);
+}
+
+int k_extract_u16(mvsim_ctx* ctx, const float* in, const int64_t dims[3], int inc, const double* d_corr, float min_value,
+                  float snr, uint64_t seed, uint64_t stream, float* out, unsigned short* out16, int* d_overflow)
+{
+    return k_extract_slab(ctx, in, dims, 0, dims[2], inc, d_corr, min_value, snr, seed, stream, out, nullptr, out16, d_overflow);
+}
+
+// extractSlices for the planes [z0, z0 + z_local) of a volume with global dims: keeps the global planes z % inc == 0 inside the
+// slab, compacted in order (in = the slab, z_local planes).  z0 == 0 and z_local == dims[2]: the whole volume.
+int k_extract_slab(mvsim_ctx* ctx, const float* in, const int64_t dims[3], int64_t z0, int64_t z_local, int inc, const double* d_corr,
+                   float min_value, float snr, uint64_t seed, uint64_t stream, float* out, int64_t* planes_out, unsigned short* out16,
+                   int* d_overflow)
+{
     const long long plane = (long long)dims[0] * dims[1];
-    const long long nz = (dims[2] - 1) / inc + 1;
+    const long long k0 = (z0 + inc - 1) / inc;                                  // first kept plane index >= z0 / inc
+    const long long k1 = (z0 + z_local - 1) / inc;                              // last kept plane index inside the slab
+    const long long nz = (z_local > 0 && k1 >= k0 && k0 * inc < z0 + z_local) ? k1 - k0 + 1 : 0;
+    if (planes_out) *planes_out = nz;
+    if (nz == 0) return MVSIM_OK;
     const long long n_out = plane * nz;
     const int noise = snr >= 0.0f ? 1 : 0;
+    const long long first = k0 * plane;                                         // global index of the slab's first output voxel
+    if (first % 4 != 0) return set_error(ctx, MVSIM_EUNSUPPORTED, "extract (slab): X*Y*first_kept_plane must be a multiple of 4");
     const bool vec4 = plane % 4 == 0 && (reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) % 16 == 0;
     const unsigned blocks = blocks_for((size_t)((n_out + 3) / 4), kSamplerThreads);
     const double mul = snr_to_mul((double)snr);
     const PoissonKey key = make_poisson_key(seed, stream);
-    if (vec4) extract_kernel<true><<<blocks, kSamplerThreads, 0, ctx->stream>>>(in, out, plane, n_out, inc, d_corr, min_value, noise, mul, key);
-    else extract_kernel<false><<<blocks, kSamplerThreads, 0, ctx->stream>>>(in, out, plane, n_out, inc, d_corr, min_value, noise, mul, key);
+    const long long in_plane0 = k0 * inc - z0, group0 = first / 4;
+    if (out16 && (reinterpret_cast<uintptr_t>(out16) % 8 != 0 || !d_overflow)) return set_error(ctx, MVSIM_EINVAL, "extract: uint16 buffer must be 8-byte aligned");
+    if (vec4) extract_kernel<true><<<blocks, kSamplerThreads, 0, ctx->stream>>>(in, out, plane, n_out, inc, d_corr, min_value, noise, mul, key, in_plane0, group0, out16, d_overflow);
+    else extract_kernel<false><<<blocks, kSamplerThreads, 0, ctx->stream>>>(in, out, plane, n_out, inc, d_corr, min_value, noise, mul, key, in_plane0, group0, out16, d_overflow);
     MVSIM_LAUNCH_CHECK(ctx);
     return MVSIM_OK;
 }

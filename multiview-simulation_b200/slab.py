@@ -135,3 +135,69 @@ class SlabConvolution:
         if self.h:
             self.ctx._lib.mvsim_slabconv_destroy(self.ctx.h, self.h)
             self.h = None
+
+
+class SlabView:
+    """ONE view (loop body S/SimulateMultiViewDataset.java:570-585) of a volume distributed by z slabs: rank r produces the
+    planes [z0, z0 + z_local) of every stage.  rotate + attenuate reads the WHOLE ground truth (a rotation about x reaches planes
+    far outside the slab; every rank holds the volume, e.g. from broadcast_ground_truth), the convolution is SlabConvolution,
+    adjustImage's mean (S/Tools.java:143-147) is an all-gather of one double per rank summed in rank order, and extractSlices keeps
+    the global planes z % inc == 0 with Philox counters of GLOBAL voxel indices -- so the result equals the undecomposed view."""
+
+    def __init__(self, ctx, shape_zyx, kshape_zyx, rank=0, world=1, dist=None, p2p=True):
+        self.ctx, self.rank, self.world, self.dist = ctx, rank, world, dist
+        self.shape = tuple(int(s) for s in shape_zyx)
+        self.conv = SlabConvolution(ctx, shape_zyx, kshape_zyx, rank, world, dist, p2p=p2p)
+        self.z0, self.z_local = self.conv.z0, self.conv.z_local
+
+    def kept_planes(self, inc):
+        """(first kept global plane index, number of kept planes) of this rank's slab."""
+        k0 = (self.z0 + inc - 1) // inc
+        k1 = (self.z0 + self.z_local - 1) // inc
+        return k0, max(0, k1 - k0 + 1) if k0 * inc < self.z0 + self.z_local else 0
+
+    def simulate(self, gt, psf, degrees, axis=0, delta=0.01, min_value=0.0001, target_avg=1.0, inc=3, snr=25.0, seed=0, stream=0,
+                 strict_reference=True):
+        """gt: float32 CUDA tensor (Z, Y, X), the whole ground truth; psf: raw float32 CUDA tensor, normalised IN PLACE like :255.
+        Returns (kept slices of this slab as a CUDA tensor (n_kept, Y, X), convolved + adjusted slab (z_local, Y, X))."""
+        import torch
+        lib, ctx = self.ctx._lib, self.ctx
+        z, y, x = self.shape
+        assert tuple(gt.shape) == self.shape and gt.is_contiguous() and psf.is_contiguous()
+        dev = gt.device
+        att = torch.empty((self.z_local, y, x), dtype=torch.float32, device=dev)
+        check(lib.mvsim_slab_rotate_attenuate(ctx.h, C.c_void_p(gt.data_ptr()), dims3(self.shape), axis, int(degrees), float(delta),
+                                              int(strict_reference), self.z0, self.z_local, C.c_void_p(att.data_ptr())), ctx.h)
+        from .api import DeviceVolume
+        k = DeviceVolume.wrap(ctx, tuple(psf.shape), psf.data_ptr(), keepalive=psf)
+        check(lib.mvsim_dev_psf_normalize(ctx.h, k.h, None), ctx.h)              # every rank normalises its copy identically
+        k.free()
+        con = torch.empty_like(att)
+        self.conv.convolve(att, psf, con)
+        del att
+        # adjustImage over the WHOLE volume: one double per rank, gathered and added in rank order
+        mine = torch.zeros(1, dtype=torch.float64, device=dev)
+        check(lib.mvsim_slab_sum(ctx.h, C.c_void_p(con.data_ptr()), con.numel(), C.c_void_p(mine.data_ptr())), ctx.h)
+        if self.world > 1:
+            if self.conv.host_plane:
+                torch.cuda.current_stream().synchronize()
+                parts = [torch.zeros(1, dtype=torch.float64) for _ in range(self.world)]
+                self.dist.all_gather(parts, mine.cpu())
+                sums = torch.cat(parts).to(dev)
+            else:
+                sums = torch.empty(self.world, dtype=torch.float64, device=dev)
+                self.dist.all_gather_into_tensor(sums, mine)
+        else:
+            sums = mine
+        check(lib.mvsim_slab_adjust(ctx.h, C.c_void_p(con.data_ptr()), con.numel(), C.c_void_p(sums.data_ptr()), self.world,
+                                    float(z) * y * x, min_value, target_avg), ctx.h)
+        _, nk = self.kept_planes(inc)
+        out = torch.empty((max(nk, 1), y, x), dtype=torch.float32, device=dev)
+        n = C.c_int64(0)
+        check(lib.mvsim_slab_extract(ctx.h, C.c_void_p(con.data_ptr()), dims3(self.shape), self.z0, self.z_local, inc, float(snr),
+                                     seed & ((1 << 64) - 1), stream, C.c_void_p(out.data_ptr()), C.byref(n)), ctx.h)
+        assert n.value == nk
+        return out[:nk], con
+
+    def close(self):
+        self.conv.close()
