@@ -424,12 +424,16 @@ def run_ours(args, rank, world, local_rank):
     modes_u16, result_checksum = run_modes(True)
     if chk_f32 != result_checksum:
         raise SystemExit(f"bench.py: the uint16 count transport changed the result ({result_checksum} vs {chk_f32})")
-    e2e_key = min(modes_u16, key=modes_u16.get)
-    e2e_ms = modes_u16[e2e_key]
+    # headline: the fastest (mode, transport) pair; every other pair is printed beside it
+    best_u16, best_f32 = min(modes_u16, key=modes_u16.get), min(modes_f32, key=modes_f32.get)
+    use_u16 = modes_u16[best_u16] < modes_f32[best_f32]
+    e2e_key = best_u16 if use_u16 else best_f32
+    e2e_ms = (modes_u16 if use_u16 else modes_f32)[e2e_key]
     e2e_mode = MODE_TEXT[e2e_key]
     h2d = (4 * vox_per_view // world if e2e_key == "broadcast" else 4 * vox_per_view) + nv * 4 * kvox      # per rank (broadcast: one upload for all)
-    d2h = nv * (2 * ovox + 4 * kvox + 4)            # uint16 counts + the normalised PSFs + the overflow flags
+    d2h_u16 = nv * (2 * ovox + 4 * kvox + 4)        # uint16 counts + the normalised PSFs + the overflow flags
     d2h_f32 = nv * 4 * (ovox + kvox)
+    d2h = d2h_u16 if use_u16 else d2h_f32
     link = host_link_probe(torch) if rank == 0 else None
 
     if rank != 0:
@@ -509,11 +513,12 @@ def run_ours(args, rank, world, local_rank):
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "views_per_s": world * nv / (e2e_ms * 1e-3),
                     "api": "mvsim_simulate_views / mvsim_dev_simulate_views (pinned host buffers in, float32 volumes out)",
                     "steps": pipe_steps if e2e_key == "pipelined" else e2e_steps, "mode": e2e_mode, "callers": n_callers,
-                    "count_transport": ("uint16 (opt-in MVSIM_OPT_COUNT_TRANSPORT): Poisson counts cross the host link as uint16 and host threads widen "
-                                        "them to the caller's float32 buffers inside the timed call; results bit-identical to the float32 transport"),
-                    "ms_per_step_by_mode": modes_u16, "ms_per_step_by_mode_float32_transport": modes_f32,
-                    "float32_transport": {"value": world * nv * vox_per_view / (min(modes_f32.values()) * 1e-3), "ms_per_step": min(modes_f32.values()),
-                                          "d2h_bytes_per_step": d2h_f32},
+                    "count_transport": "uint16" if use_u16 else "float32",
+                    "count_transport_note": ("uint16 = opt-in MVSIM_OPT_COUNT_TRANSPORT: Poisson counts cross the host link as uint16 and host threads widen "
+                                             "them to the caller's float32 buffers inside the timed call (bit-identical results, half the D2H bytes, but "
+                                             "3x the host-memory traffic of the results); both transports are timed in every mode, the headline is the fastest pair"),
+                    "ms_per_step_by_mode_uint16_transport": modes_u16, "ms_per_step_by_mode_float32_transport": modes_f32,
+                    "d2h_bytes_per_step_uint16_transport": d2h_u16, "d2h_bytes_per_step_float32_transport": d2h_f32,
                     "host_link": link,
                     "frac_of_host_link": (max(h2d / link["h2d_concurrent_GBps"], d2h / link["d2h_concurrent_GBps"]) / 1e9 / (e2e_ms * 1e-3)) if link else None,
                     "frac_of_host_link_basis": "time the busier direction needs at the rate measured with both directions active / e2e time per step (1 GPU active)",

@@ -118,7 +118,7 @@ def test_whole_view_of_a_slab_decomposed_volume_equals_the_undecomposed_view(tmp
     indices -- against mvsim_simulate_view of the same volume (loop body S/SimulateMultiViewDataset.java:570-585)."""
     out = tmp_path / f"view_{world}.json"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-           "--master-port", str(29900 + (os.getpid() + world) % 90), os.path.join(HERE, "slab_view_worker.py"), "40x56x64", "9x7x11", str(out),
+           "--master-port", str(29900 + (os.getpid() + world) % 90), os.path.join(HERE, "slab_view_worker.py"), "40x56x52", "9x7x11", str(out),      # X + KX - 1 = 62 -> 32 complex columns = 4 kx tiles
            str(inc), "shared"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-3000:]
