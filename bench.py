@@ -378,10 +378,10 @@ def run_ours(args, rank, world, local_rank):
     def checksum(outs):
         return float(outs[0].array[::7, ::31, ::29].astype(np.float64).mean())
 
-    def run_modes(uint16):
+    def run_modes(uint16, host_threads=0):
         """All e2e modes with one count transport; returns {mode: ms per step (max over ranks)} and the result checksum."""
         for c, _, _ in callers:
-            c.count_transport(uint16)
+            c.count_transport(uint16, host_threads=host_threads)
         res = {}
         for i in range(n_callers):           # warm every context (workspaces, staging buffers)
             caller_loop(i, 1)
@@ -421,7 +421,10 @@ def run_ours(args, rank, world, local_rank):
                  "pipelined": f"{n_callers} caller threads x 1 context each per rank, steps dealt round-robin (H2D of one step runs under the kernels and D2H of the others)",
                  "broadcast": "views of one dataset sharded over the ranks: ground truth uploaded once by rank 0 and NCCL-broadcast over NVLink, 1 caller per rank"}
     modes_f32, chk_f32 = run_modes(False)
-    modes_u16, result_checksum = run_modes(True)
+    modes_u16, result_checksum = run_modes(True, args.widen_threads)
+    widen_sweep = {}
+    for t in (args.widen_sweep or []):          # investigation only: other widening thread counts
+        widen_sweep[str(t)], _ = run_modes(True, t)
     if chk_f32 != result_checksum:
         raise SystemExit(f"bench.py: the uint16 count transport changed the result ({result_checksum} vs {chk_f32})")
     # headline: the fastest (mode, transport) pair; every other pair is printed beside it
@@ -519,6 +522,7 @@ def run_ours(args, rank, world, local_rank):
                                              "3x the host-memory traffic of the results); both transports are timed in every mode, the headline is the fastest pair"),
                     "ms_per_step_by_mode_uint16_transport": modes_u16, "ms_per_step_by_mode_float32_transport": modes_f32,
                     "d2h_bytes_per_step_uint16_transport": d2h_u16, "d2h_bytes_per_step_float32_transport": d2h_f32,
+                    "widen_threads": args.widen_threads, "widen_sweep_ms_per_step": widen_sweep or None,
                     "host_link": link,
                     "frac_of_host_link": (max(h2d / link["h2d_concurrent_GBps"], d2h / link["d2h_concurrent_GBps"]) / 1e9 / (e2e_ms * 1e-3)) if link else None,
                     "frac_of_host_link_basis": "time the busier direction needs at the rate measured with both directions active / e2e time per step (1 GPU active)",
@@ -591,6 +595,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS) + ["cfg5", "cfg5small"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--widen-threads", type=int, default=0, help="host threads per context that widen uint16 counts (0 = library default)")
+    ap.add_argument("--widen-sweep", type=int, nargs="*", help="also time the uint16 transport with these widening thread counts")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

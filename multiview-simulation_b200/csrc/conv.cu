@@ -95,15 +95,15 @@ static bool otf_default()
     return on;
 }
 
-// D table of the decimated fused z pass (zfused_dec_table, fft/conv_driver.h), built once per (n, crop0, n_src) and kept in the
+// D' table of the decimated fused z pass (zfused_dec_table, fft/conv_driver.h), built once per (n, crop0, n_src, inc) and kept in the
 // context like the twiddle tables (synchronous upload from pageable memory: the host vector may die right after)
-static int get_dec_table(mvsim_ctx* ctx, int n, int crop0, int n_src, const float2** out)
+static int get_dec_table(mvsim_ctx* ctx, int n, int crop0, int n_src, int inc, const float2** out)
 {
-    const std::array<int, 3> key = { n, crop0, n_src };
+    const std::array<int, 4> key = { n, crop0, n_src, inc };
     auto it = ctx->dec_tables.find(key);
     if (it != ctx->dec_tables.end()) { *out = it->second; return MVSIM_OK; }
     std::vector<float2> h((size_t)n);
-    zfused_dec_table(n, crop0, n_src, h.data());
+    zfused_dec_table(n, crop0, n_src, inc, h.data());
     float2* d = nullptr;
     MVSIM_CUDA(ctx, cudaMalloc((void**)&d, sizeof(float2) * (size_t)n));
     const cudaError_t e = cudaMemcpy(d, h.data(), sizeof(float2) * (size_t)n, cudaMemcpyHostToDevice);
@@ -177,7 +177,7 @@ struct CudaLauncher {
     int launch_zfused_dec(const FftSize& s, const ZFusedParams& q0, int n_tiles, int n_outer, int inc)
     {
         ZFusedParams q = q0;
-        MVSIM_TRY(get_dec_table(ctx, s.n, q.crop0, q.n_src, &q.dtab));       // cached per (n, crop0, n_src) in the context
+        MVSIM_TRY(get_dec_table(ctx, s.n, q.crop0, q.n_src, inc, &q.dtab));  // cached per (n, crop0, n_src, inc) in the context
         StageTimer t(ctx, MVSIM_T_FFT_ZFUSED);
         q.use_tma = (zfused_otf_tma_fits(s.b, s.a, lanes, q.k_src) && make_h_tensor_map(q.p2, lanes, n_tiles, q.k_src, n_outer, q.h_tmap)) ? 1 : 0;
         const int zthreads = lanes * (s.a > s.b ? s.a : s.b);

@@ -30,7 +30,7 @@ struct mvsim_ctx {
     std::string err;
     double* d_scalars;                       // [8] device doubles: sums, corrections
     std::map<int, mvsim_tables> tables;      // by complex line length
-    std::map<std::array<int, 3>, float2*> dec_tables;   // decimated fused z pass: D table by (n, crop0, n_src)
+    std::map<std::array<int, 4>, float2*> dec_tables;   // decimated fused z pass: D' table by (n, crop0, n_src, inc)
     // PSF-spectrum cache: partial spectra P2 keyed by a device-computed content hash of the NORMALISED PSF + the plan.
     // The reference rebuilds the kernel FFT on every call (S/SimulateMultiViewDataset.java:257) although its callers reuse one
     // PSF across SNR sweeps and tile pairs (S/SimulateTileStitching.java:71,95,110); results are bit-identical either way.

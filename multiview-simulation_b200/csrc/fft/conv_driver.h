@@ -149,21 +149,24 @@ template <class L> int conv_middle_z(L& l, const ConvPlan& pl, const SlabGeom& g
     return l.launch_zfused(pl.sz, zp, g.tiles_own, pl.sy.n);
 }
 
-// D[k] = sum_{n = crop0}^{crop0 + n_src - 1} exp(+2 pi i n k / N), k < N (ZFusedDec: the sum of the cropped outputs of the unscaled
-// inverse transform is sum_k Yhat[k] D[k]); double arithmetic, stored as float2
-inline void zfused_dec_table(int n, int crop0, int n_src, float2* out)
+// D'[k] = sum over the cropped outputs n in [crop0, crop0 + n_src) that are NOT kept (kept: n = crop0 + inc m) of exp(+2 pi i n k / N),
+// k < N.  ZFusedDec: the sum of the dropped slices of the unscaled inverse transform is sum_k Yhat[k] D'[k].  Exact integer phase
+// reduction (n k mod N) into a double sine / cosine table; stored as float2.
+inline void zfused_dec_table(int n, int crop0, int n_src, int inc, float2* out)
 {
-    // closed form of the geometric sum: exp(i t (crop0 + (n_src - 1)/2)) sin(n_src t / 2) / sin(t / 2), t = 2 pi k / n
-    const double pi = 3.14159265358979323846;
-    out[0].x = (float)n_src; out[0].y = 0.f;
-    for (int k = 1; k < n; ++k) {
-        const double half = pi * (double)k / (double)n;                                  // t / 2
-        const long long m2 = ((long long)(2 * crop0 + n_src - 1) * k) % (2LL * n);       // phase t (crop0 + (n_src-1)/2) = pi m2 / n, reduced exactly
-        const double ph = pi * (double)m2 / (double)n;
-        const long long ms = ((long long)n_src * k) % (2LL * n);                         // n_src t / 2 = pi ms / n
-        const double amp = sin(pi * (double)ms / (double)n) / sin(half);
-        out[k].x = (float)(amp * cos(ph)); out[k].y = (float)(amp * sin(ph));
+    const double two_pi = 6.283185307179586476925286766559;
+    double* cs = new double[2 * (size_t)n];
+    for (int m = 0; m < n; ++m) { cs[2 * m] = cos(two_pi * (double)m / (double)n); cs[2 * m + 1] = sin(two_pi * (double)m / (double)n); }
+    for (int k = 0; k < n; ++k) {
+        double re = 0.0, im = 0.0;
+        for (int o = 0; o < n_src; ++o) {
+            if (inc > 1 && o % inc == 0) continue;
+            const long long ph = ((long long)(crop0 + o) * k) % n;
+            re += cs[2 * ph]; im += cs[2 * ph + 1];
+        }
+        out[k].x = (float)re; out[k].y = (float)im;
     }
+    delete[] cs;
 }
 
 // y inverse of block b: ws.u2 (tile-major [KT][Zl][Ny][T], `planes` of the Zl planes in use) -> rows of ws.u1o

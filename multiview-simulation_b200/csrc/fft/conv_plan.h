@@ -33,7 +33,9 @@ struct FftSize { int n, a, b; };
     X(1600, 40, 40)
 
 #ifdef MVSIM_EMU_SMALL_ONLY
-#define MVSIM_FFT_SIZES(X) MVSIM_FFT_SIZES_SMALL(X)
+// CPU emulation (tests/emu): the small sizes plus the z-line lengths of the BASELINE configs (360: configs 1 / 4 at inc 3,
+// 576, 640: config 3), so that the decimated fused z pass is emulated with the splits it runs with on the GPU
+#define MVSIM_FFT_SIZES(X) MVSIM_FFT_SIZES_SMALL(X) X(360, 18, 20) X(576, 24, 24) X(640, 20, 32)
 #else
 #define MVSIM_FFT_SIZES(X) \
     MVSIM_FFT_SIZES_SMALL(X) MVSIM_FFT_SIZES_G1(X) MVSIM_FFT_SIZES_G2(X) MVSIM_FFT_SIZES_G3(X) MVSIM_FFT_SIZES_G4(X)

@@ -692,9 +692,29 @@ template <int A_, int B_, int T_> struct ZFusedOTF : ZFused<A_, B_, T_> {
 //   - the plane that carries the sum of the dropped slices (adjustImage's mean) comes from ONE dot product: the sum of all
 //     cropped outputs is sum_k Yhat[k] D[k] with D[k] = sum_{n in crop} exp(+2 pi i n k / N), minus the kept outputs.
 // A_, B_ are the planner's (b, a): the first level has the larger transform here (config 3: A = 32, B = 20, INC = 5).
-// Phases: image first half | image second half, park | PSF first half | PSF second half, multiply, dot with D |
-//         pruned inverse first half | inverse second half of the kept columns, stores | sum plane.
-// ==============================================================================================
+// Phases: image first half | image second half, park | PSF first half | PSF second half, multiply, dot with D' |
+//         pruned inverse first half | second inverse half of the kept columns, SPLIT sub-transforms per column |
+//         combine + stores | sum plane.
+// The second inverse half used to run as ONE A-point transform per kept column on KEEP of the P threads of a line -- a single
+// warp per CTA for ~600 dependent instructions while seven warps waited (ncu source view r02b: 15 % of all warp samples sat at
+// that barrier, the phase was ~20 % of a CTA's lifetime).  It is now a radix-SPLIT step spread over SPLIT x as many threads:
+// thread (column, q) transforms the inputs k1 = SPLIT k' + q (an A/SPLIT-point inverse), twiddles, parks G_q in the free H area;
+// after a barrier thread (column, m[, half]) combines x[n' + (A/SPLIT) m] = sum_q G_q[n'] e^{+2 pi i m q / SPLIT} and stores.
+// The plane that carries the sum of the DROPPED slices is one dot product with D'[k] = sum over the cropped, non-kept n of
+// e^{+2 pi i n k / N} (host table): no bookkeeping of the kept outputs is needed.
+constexpr bool dec_regfft_size(int m)
+{
+    return m == 2 || m == 3 || m == 4 || m == 5 || m == 6 || m == 8 || m == 9 || m == 10 || m == 12;
+}
+// radix of the split of the second inverse half: the largest of 4, 3, 5, 2 that divides a, leaves a generated sub-transform and
+// fits the threads of a line (keep columns x split <= p); 1 = no split
+constexpr int dec_split(int a, int keep, int p)
+{
+    const int cand[4] = { 4, 3, 5, 2 };
+    for (int i = 0; i < 4; ++i)
+        if (a % cand[i] == 0 && dec_regfft_size(a / cand[i]) && keep * cand[i] <= p) return cand[i];
+    return 1;
+}
 // may the planner's split (a, b) of a z line run the decimated kernel ZFusedDec<b, a, T, inc>?
 constexpr bool zfused_dec_ok(int a, int b, int inc) { return (inc == 3 || inc == 5) && a % inc == 0 && a / inc >= 2 && a + b <= a * b; }
 
@@ -704,14 +724,19 @@ template <int A_, int B_, int T_, int INC_> struct ZFusedDec : LineShape<A_, B_>
     static_assert(B_ % INC_ == 0 && B_ / INC_ >= 2, "the kept outputs must be whole columns of the exchange");
     static constexpr int KEEP = B / INC;          // kept columns per line
     static constexpr int THREADS = T * S::P;
-    static constexpr int NPH = 7;
+    static constexpr int NPH = 8;
+    static constexpr int SPLIT = dec_split(A_, B_ / INC_, S::P);    // radix of the split second inverse half
+    static constexpr int M = A / SPLIT;                             // sub-transform length
+    static constexpr int RS = (S::P / (KEEP * SPLIT) >= 2 && M % 2 == 0) ? 2 : 1;     // threads per (column, m) in the combine phase
+    // H area after the multiply (float2 elements): [0, A T) dot partials | [G0, G0 + KEEP A T) the twiddled sub-transform outputs G_q
+    static constexpr int G0 = A * T;
+    static_assert(G0 + KEEP * A * T <= S::N * T, "G area must fit the parked-spectrum area");
     static constexpr int EXCH_ELEMS = (S::ELEMS * T + 15) / 16 * 16;
     static constexpr int H_ROWS = (S::N + kTmaBoxRows - 1) / kTmaBoxRows * kTmaBoxRows;
     static constexpr int BAR_ELEMS = EXCH_ELEMS + H_ROWS * T;
     static constexpr int PSF_ELEMS0 = BAR_ELEMS + 16;
     static constexpr int SMEM_BYTES = PSF_ELEMS0 * (int)sizeof(float2);
     static_assert(SMEM_BYTES == zfused_otf_smem_base(A_, B_, T_), "host-side shared memory formula out of sync");
-    static_assert(A_ + B_ <= S::N, "partial sums live in the parked-spectrum area");
     using Params = ZFusedParams;
     using State = RegState<B>;
     static int smem_bytes(const Params& q) { return SMEM_BYTES + (q.use_tma ? zfused_otf_psf_tile_bytes(q.k_src, T) : 0); }
@@ -857,32 +882,59 @@ template <int A_, int B_, int T_, int INC_> struct ZFusedDec : LineShape<A_, B_>
                 }
             }
         } else if (PH == 5) {
-            // the KEEP kept columns of every line, packed into the first warps: thread (j, lane) owns column n2 = r + INC j
-            const int j = tid / T;
-            if (j < KEEP && active) {
+            // second inverse half, part 1: thread (column j, q, lane) runs the M-point inverse over the inputs k1 = SPLIT k' + q of
+            // column n2 = r + INC j, multiplies by e^{+2 pi i n' q / A} = conj(tw[n' q B]) and parks G_q[n'] in the H area
+            const int grp = tid / T;
+            if (grp < KEEP * SPLIT && active) {
+                const int j = grp / SPLIT, qq = grp - j * SPLIT;
                 const int n2 = r + INC * j;
-                float2 x[A];
-                inv_second<A, B, kPackedStrided>(n2, x, sm, lane, T);
+                constexpr int BP = B | 1;
+                float2 x[M];
+                MVSIM_UNROLL
+                for (int k = 0; k < M; ++k) x[k] = sm[lane + ((SPLIT * k + qq) * BP + n2) * T];
+                RegSel<M, 1, kPackedStrided>::run(x);
+                float2* g = smh + G0 + (j * SPLIT + qq) * M * T + lane;
+                MVSIM_UNROLL
+                for (int n = 0; n < M; ++n) g[n * T] = (n == 0 || SPLIT == 1) ? x[n] : cmulc(x[n], q.tw[n * qq * B]);
+            }
+        } else if (PH == 6) {
+            // part 2: thread (column j, m, half h, lane) combines x[n' + M m] = sum_q G_q[n'] e^{+2 pi i m q / SPLIT} for its n' and
+            // stores the kept planes (o = n2 + n1 B - crop0 = INC kz exactly)
+            const int grp = tid / T;
+            if (grp < KEEP * SPLIT * RS && active) {
+                const int h = grp % RS, jm = grp / RS;
+                const int j = jm / SPLIT, m = jm - j * SPLIT;
+                const int n2 = r + INC * j;
+                float2 c[SPLIT];
+                MVSIM_UNROLL
+                for (int qq = 1; qq < SPLIT; ++qq) c[qq] = q.tw[((m * qq) % SPLIT) * (S::N / SPLIT)];      // conj applied below
+                const float2* g = smh + G0 + j * SPLIT * M * T + lane;
                 float2* dst = q.u + tile * q.u_tstride + outer * q.ostride + lane;
                 const unsigned e = (unsigned)q.estride32;
-                float2 ksum = make_float2(0.f, 0.f);
+                constexpr int CNT = M / RS;
                 MVSIM_UNROLL
-                for (int n1 = 0; n1 < A; ++n1) {
-                    const int o = n2 + n1 * B - q.crop0;                   // = INC * kz exactly
-                    if ((unsigned)o < (unsigned)q.n_src) {
-                        const unsigned kz = umulhi32((uint32_t)o, q.keep_magic);
-                        *at32(dst, kz, e) = x[n1];
-                        ksum.x += x[n1].x; ksum.y += x[n1].y;
+                for (int i = 0; i < CNT; ++i) {
+                    const int n = h * CNT + i;
+                    float2 acc = g[n * T];
+                    MVSIM_UNROLL
+                    for (int qq = 1; qq < SPLIT; ++qq) {
+                        const float2 v = cmulc(g[(qq * M + n) * T], c[qq]);
+                        acc.x += v.x; acc.y += v.y;
                     }
+                    const int o = n2 + (n + M * m) * B - q.crop0;
+                    if ((unsigned)o < (unsigned)q.n_src) *at32(dst, umulhi32((uint32_t)o, q.keep_magic), e) = acc;
                 }
-                smh[(A + j) * T + lane] = ksum;
             }
         } else {
+            // the plane with the sum of the dropped slices: the A partial dot products with D' (phase 3), two chains
             if (p == 0 && active) {
-                float2 s = make_float2(0.f, 0.f);
-                for (int k = 0; k < A; ++k) { s.x += smh[k * T + lane].x; s.y += smh[k * T + lane].y; }
-                for (int j = 0; j < KEEP; ++j) { s.x -= smh[(A + j) * T + lane].x; s.y -= smh[(A + j) * T + lane].y; }
-                q.u[tile * q.u_tstride + outer * q.ostride + lane + q.n_keep * q.estride] = s;
+                float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
+                for (int k = 0; k + 1 < A; k += 2) {
+                    s0.x += smh[k * T + lane].x; s0.y += smh[k * T + lane].y;
+                    s1.x += smh[(k + 1) * T + lane].x; s1.y += smh[(k + 1) * T + lane].y;
+                }
+                if (A % 2) { s0.x += smh[(A - 1) * T + lane].x; s0.y += smh[(A - 1) * T + lane].y; }
+                q.u[tile * q.u_tstride + outer * q.ostride + lane + q.n_keep * q.estride] = make_float2(s0.x + s1.x, s0.y + s1.y);
             }
         }
     }

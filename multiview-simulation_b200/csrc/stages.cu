@@ -683,6 +683,134 @@ template <bool VEC4> __global__ void __launch_bounds__(kSamplerThreads) extract_
     }
 }
 
+// Warp-cooperative variant: one thread = G groups of four consecutive voxels (a warp owns 128 G consecutive voxels), the pending
+// PTRS voxels of the WARP are compacted into the warp's own shared-memory list (ballot-free inclusive scan by shuffles) and
+// finished with full warps -- no block barrier anywhere.  With G = 2 a warp's list is as long as the 64-thread CTA's list of the
+// block-cooperative kernel above (same lane utilisation of the slow path) without its three __syncthreads.
+constexpr int kWarpSamplerThreads = 128;
+template <int G> struct WarpSamplerShared {
+    PendingItem items[32 * 4 * G];
+    float results[32 * 4 * G];
+    int count;
+};
+
+template <bool VEC4, int G> __global__ void __launch_bounds__(kWarpSamplerThreads) extract_warp_kernel(const float* __restrict__ in, float* __restrict__ out, long long plane,
+                                                                          long long n_out, int inc, const double* __restrict__ d_corr,
+                                                                          float min_value, int noise, double mul, PoissonKey key,
+                                                                          long long in_plane0, long long group0,
+                                                                          unsigned short* __restrict__ out16, int* __restrict__ overflow)
+{
+    __shared__ WarpSamplerShared<G> shw[kWarpSamplerThreads / 32];
+    const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    const long long gbase = ((long long)blockIdx.x * (kWarpSamplerThreads / 32) + w) * (32 * G);
+    float v[G][4];
+    bool valid[G];
+    long long g[G];
+#pragma unroll
+    for (int k = 0; k < G; ++k) {
+        g[k] = gbase + k * 32 + lane;
+        const long long i0 = 4 * g[k];
+        valid[k] = i0 < n_out;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[k][j] = 0.f;
+        if (valid[k]) {
+            if (VEC4) {
+                const long long cz = i0 / plane, r = i0 - cz * plane;
+                const float4 t = __ldg(reinterpret_cast<const float4*>(in + (cz * inc + in_plane0) * plane + r));
+                v[k][0] = t.x; v[k][1] = t.y; v[k][2] = t.z; v[k][3] = t.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const long long i = i0 + j < n_out ? i0 + j : n_out - 1;
+                    const long long cz = i / plane, r = i - cz * plane;
+                    v[k][j] = __ldg(in + (cz * inc + in_plane0) * plane + r);
+                }
+            }
+        }
+    }
+    if (d_corr) {
+        const double corr = *d_corr;
+#pragma unroll
+        for (int k = 0; k < G; ++k)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[k][j] = adjust_one(v[k][j], corr, min_value);
+    }
+    if (noise) {
+        // slots are handed out by a shared-memory counter as the pending voxels turn up (group by group, so nothing but the slot
+        // numbers stays live in registers); a voxel's result depends on (seed, stream, voxel index) only, not on its slot
+        WarpSamplerShared<G>& sh = shw[w];
+        if (lane == 0) sh.count = 0;
+        __syncwarp();
+        unsigned long long slots[G];
+#pragma unroll
+        for (int k = 0; k < G; ++k) {
+            double lam[4];
+            Philox4 r0, r1;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) lam[j] = valid[k] ? __dmul_rn((double)v[k][j], mul) : 0.0;
+            const unsigned pending = poisson_group4_fast(lam, (uint64_t)(g[k] + group0), key, v[k], r0, r1);
+            slots[k] = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (pending & (1u << j)) {
+                    const int pos = atomicAdd(&sh.count, 1);
+                    PendingItem it;
+                    it.lam = lam[j];
+                    it.index = 4ull * (unsigned long long)(g[k] + group0) + (unsigned)j;
+                    it.ru = j == 0 ? r0.x : j == 1 ? r0.y : j == 2 ? r0.z : r0.w;
+                    it.rv = j == 0 ? r1.x : j == 1 ? r1.y : j == 2 ? r1.z : r1.w;
+                    sh.items[pos] = it;
+                    slots[k] |= (unsigned long long)(pos + 1) << (16 * j);      // 0 = not pending
+                }
+        }
+        __syncwarp();
+        const int total = sh.count;
+        if (total > 0) {                          // warp uniform
+            for (int j = (int)lane; j < total; j += 32) {
+                const PendingItem it = sh.items[j];
+                sh.results[j] = ptrs_resolve(it.lam, it.ru, it.rv, it.index, key);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < G; ++k)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const unsigned sl = (unsigned)(slots[k] >> (16 * j)) & 0xffffu;
+                    if (sl) v[k][j] = sh.results[sl - 1];
+                }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < G; ++k) {
+        if (!valid[k]) continue;
+        const long long i0 = 4 * g[k];
+        if (VEC4) {
+            *reinterpret_cast<float4*>(out + i0) = make_float4(v[k][0], v[k][1], v[k][2], v[k][3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (i0 + j < n_out) out[i0 + j] = v[k][j];
+        }
+        if (out16) {
+            bool over = false;
+            unsigned short q[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                over |= !(v[k][j] <= 65535.0f);
+                q[j] = (unsigned short)fminf(fmaxf(v[k][j], 0.f), 65535.0f);
+            }
+            if (VEC4) {
+                *reinterpret_cast<ushort4*>(out16 + i0) = make_ushort4(q[0], q[1], q[2], q[3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (i0 + j < n_out) out16[i0 + j] = q[j];
+            }
+            if (over) atomicOr(overflow, 1);
+        }
+    }
+}
+
 static double snr_to_mul(double snr) { const double q = snr / sqrt(5.0); return pow(q, 2.0); }
 
 int k_extract(mvsim_ctx* ctx, const float* in, const int64_t dims[3], int inc, const double* d_corr, float min_value,
@@ -719,6 +847,14 @@ int k_extract_slab(mvsim_ctx* ctx, const float* in, const int64_t dims[3], int64
     const PoissonKey key = make_poisson_key(seed, stream);
     const long long in_plane0 = k0 * inc - z0, group0 = first / 4;
     if (out16 && (reinterpret_cast<uintptr_t>(out16) % 8 != 0 || !d_overflow)) return set_error(ctx, MVSIM_EINVAL, "extract: uint16 buffer must be 8-byte aligned");
+    static const int variant = [] { const char* e = getenv("MVSIM_SAMPLER"); return e ? atoi(e) : 0; }();     // experiment knob (r02): 0 block-cooperative, 2 warp-cooperative with 2 groups per thread
+    if (variant == 2) {
+        const unsigned wblocks = blocks_for((size_t)((n_out + 3) / 4), (unsigned)(kWarpSamplerThreads * 2));
+        if (vec4) extract_warp_kernel<true, 2><<<wblocks, kWarpSamplerThreads, 0, ctx->stream>>>(in, out, plane, n_out, inc, d_corr, min_value, noise, mul, key, in_plane0, group0, out16, d_overflow);
+        else extract_warp_kernel<false, 2><<<wblocks, kWarpSamplerThreads, 0, ctx->stream>>>(in, out, plane, n_out, inc, d_corr, min_value, noise, mul, key, in_plane0, group0, out16, d_overflow);
+        MVSIM_LAUNCH_CHECK(ctx);
+        return MVSIM_OK;
+    }
     if (vec4) extract_kernel<true><<<blocks, kSamplerThreads, 0, ctx->stream>>>(in, out, plane, n_out, inc, d_corr, min_value, noise, mul, key, in_plane0, group0, out16, d_overflow);
     else extract_kernel<false><<<blocks, kSamplerThreads, 0, ctx->stream>>>(in, out, plane, n_out, inc, d_corr, min_value, noise, mul, key, in_plane0, group0, out16, d_overflow);
     MVSIM_LAUNCH_CHECK(ctx);

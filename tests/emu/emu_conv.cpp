@@ -72,7 +72,7 @@ struct EmuLauncher {
     {
         ZFusedParams q = q0;
         std::vector<float2> d((size_t)s.n);
-        zfused_dec_table(s.n, q.crop0, q.n_src, d.data());
+        zfused_dec_table(s.n, q.crop0, q.n_src, inc, d.data());
         q.dtab = d.data();
         ++decimated_launches;
         switch (s.n) {

@@ -77,11 +77,12 @@ def test_plan_sizes_cover_dim_plus_kdim_minus_one(emu):
     for dims, kdims in [((1024, 1024, 512), (128, 128, 128)), ((289, 289, 289), (51, 51, 51)),
                         ((512, 512, 512), (64, 64, 128)), ((1, 1, 1), (1, 1, 1))]:
         err = emu.emu_plan((C.c_int64 * 3)(*dims), (C.c_int64 * 3)(*kdims), out, 0)
-        if err == 5:        # emulator is built with the small size table only
+        if err == 5:        # the emulator's size table ends at 640 points
             continue
         assert err == 0
         assert 2 * out[0] >= dims[0] + kdims[0] - 1
-        assert out[1] >= dims[1] + kdims[1] - 1 and out[2] >= dims[2] + kdims[2] - 1
+        # y lines beyond the table are convolved in out[9] overlap-save blocks of out[10] rows each
+        assert out[1] >= out[10] + kdims[1] - 1 and out[9] * out[10] >= dims[1] and out[2] >= dims[2] + kdims[2] - 1
         assert out[3] * out[4] == out[0] and out[5] * out[6] == out[1] and out[7] * out[8] == out[2]
 
 
@@ -174,6 +175,9 @@ def test_generated_butterflies_are_in_sync_with_the_generator(tmp_path):
     ((80, 4, 9), (21, 3, 2), 5),       # 100 = 10 x 10 -> ZFusedDec<10, 10, T, 5>, crop0 = 20: r = 0
     ((100, 3, 10), (19, 2, 3), 5),     # 120 = 10 x 12 -> ZFusedDec<12, 10, T, 5>, crop0 = 18: r = 3
     ((101, 3, 20), (17, 1, 2), 5),     # 120, crop0 = 16: r = 1; partial last kx tile
+    ((599, 2, 3), (42, 1, 2), 5),      # 640 = 20 x 32 (BASELINE config 3's z line) -> ZFusedDec<32, 20, T, 5>: second inverse half split 4 x 8, two threads per (column, m); r = 1
+    ((344, 2, 3), (17, 1, 2), 3),      # 360 = 18 x 20 (config 1 / 4 z lines at inc 3) -> ZFusedDec<20, 18, T, 3>: split 2 x 10
+    ((560, 1, 3), (17, 1, 1), 3),      # 576 = 24 x 24 -> ZFusedDec<24, 24, T, 3>: split 3 x 8, every thread of a line busy
 ])
 def test_decimated_inverse_of_the_fused_z_pass(emu, oracle, monkeypatch, psf_spectrum_mode, request, shape, kshape, inc):
     """ZFusedDec (the whole-view default where the split allows it): kept planes = whole columns of the exchange, pruned first

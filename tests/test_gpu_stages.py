@@ -287,3 +287,15 @@ def test_two_threads_with_their_own_contexts(mv, S):
     assert not errs, errs
     for d, _ in jobs:
         assert np.array_equal(out[d], serial[d])
+
+
+def test_cooperative_and_per_thread_sampler_paths_agree_bit_for_bit(mv, S):
+    """extractSlices finishes the PTRS voxels cooperatively (compacted in shared memory), Tools.poissonProcess thread by thread:
+    a voxel's count depends on (seed, stream, voxel index) only, so both must return the same volume."""
+    rng = np.random.default_rng(31)
+    v = (rng.random((5, 37, 52), dtype=np.float32) * 3).astype(np.float32)      # lambda 0 .. 375 at SNR 25: every regime, ragged size
+    v[0, :5] = 0
+    a = S.extractSlices(v, 1, 25.0, rnd=99, stream=6)
+    b = v.copy()
+    mv.Tools.poissonProcess(b, 25.0, 99, stream=6)
+    assert np.array_equal(a, b)
