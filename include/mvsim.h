@@ -83,7 +83,7 @@ enum {
      * reference's API (Img<FloatType>) by host threads inside the call, overlapped with the later views.  Results are bit-identical to
      * the float32 transport; a view with a count above 65535 is fetched as float32 instead.  0 (default): float32. */
     MVSIM_OPT_COUNT_TRANSPORT = 1,
-    /* host threads that widen (0 = default: half the processors, at most 8) */
+    /* host threads that widen (0 = default: 4) */
     MVSIM_OPT_HOST_THREADS = 2
 };
 int mvsim_ctx_set_option(mvsim_ctx* ctx, int option, int64_t value);

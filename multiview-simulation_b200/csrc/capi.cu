@@ -284,7 +284,7 @@ static WidenPool* widen_pool(mvsim_ctx* ctx)
         int t = ctx->host_threads;
         if (t <= 0) {
             const unsigned hw = std::thread::hardware_concurrency();
-            t = hw >= 16 ? 8 : (hw >= 4 ? (int)hw / 2 : 1);
+            t = hw >= 8 ? 4 : (hw >= 4 ? 2 : 1);       // measured (profiles/r02_notes.md): 4 threads per context beat 2 and 8
         }
         ctx->widen_pool = new WidenPool(t > 1 ? t - 1 : 0);      // the calling thread is one of the t
     }

@@ -959,39 +959,72 @@ struct XParams {
     double* partials;       // inverse: per-block sums of the stored voxels (may be null)
     int X, n_rows, left, ext, crop0;
     int prefetch_dist;      // forward: thread 0 of CTA i prefetches the rows of CTA i + prefetch_dist into the L2 (0 = off)
+    int use_bulk;           // forward: the CTA's rows are staged in shared memory by one TMA bulk copy (X % 4 == 0, 16-byte aligned source)
 };
 
+template <int A> struct XFwdState { float a[A], b[A]; };
+
+// Forward x pass.  The R rows of a CTA are contiguous in the source, so ONE thread asks the TMA unit for them (cp.async.bulk, no
+// tensor map) and the threads pick their 2 A samples from shared memory: the per-thread gather of 2 A scalar loads with 64-bit
+// address arithmetic kept the L1 / LSU pipe at 82 % of its peak and a quarter of the instructions were index arithmetic (ncu,
+// profiles/r02b).  The staged rows alias the exchange area (a row of X <= 2N floats is never larger than its A x (B|1) complex
+// exchange slots), hence one more barrier between the last read of a row and the first write of the exchange.
 template <int A_, int B_, int R_> struct XFwd : LineShape<A_, B_> {
     using S = LineShape<A_, B_>;
     static constexpr bool IS_X = true;
     static constexpr int A = A_, B = B_, R = R_;
     static constexpr int THREADS = R * S::P;
-    static constexpr int SMEM_BYTES = S::ELEMS * R * (int)sizeof(float2);
-    static constexpr int NPH = 2;
+    static constexpr int EXCH = S::ELEMS * R;                                      // float2 elements
+    static constexpr int SMEM_BYTES = EXCH * (int)sizeof(float2) + 16;             // + the mbarrier
+    static constexpr int NPH = 3;
     using Params = XParams;
-    using State = NoState;
+    using State = XFwdState<A_>;
 
-    template <int PH> static MVSIM_HD void phase(const Params& q, int bx, int, int tid, float2* sm, State&)
+    template <int PH> static MVSIM_HD void phase(const Params& q, int bx, int, int tid, float2* sm, State& st)
     {
         constexpr int N = S::N;
         const int r = tid / S::P, p = tid % S::P;
-        const long long row = (long long)bx * R + r;
+        const long long row0 = (long long)bx * R;
+        const long long row = row0 + r;
         const bool active = row < q.n_rows;
         if (PH == 0) {
+            const long long nr = q.n_rows - row0 < R ? q.n_rows - row0 : R;
+            const float* __restrict__ src = q.rin + row * q.X;
+            if (q.use_bulk) {
+                float* rows = reinterpret_cast<float*>(sm);
 #ifdef __CUDA_ARCH__
-            if (tid == 0 && q.prefetch_dist > 0) {
-                const long long r0 = ((long long)bx + q.prefetch_dist) * R;
-                if (r0 < q.n_rows) {
-                    const long long nr = q.n_rows - r0 < R ? q.n_rows - r0 : R;
-                    bulk_prefetch_l2(q.rin + r0 * q.X, (unsigned)(nr * q.X * sizeof(float)));
+                uint64_t* bar = reinterpret_cast<uint64_t*>(sm + EXCH);
+                if (tid == 0) {
+                    mbar_init(bar, 1);
+                    mbar_expect_tx(bar, (unsigned)(nr * q.X * sizeof(float)));
+                    bulk_load(rows, q.rin + row0 * q.X, (unsigned)(nr * q.X * sizeof(float)), bar);
+                    if (q.prefetch_dist > 0) {
+                        const long long r2 = ((long long)bx + q.prefetch_dist) * R;
+                        if (r2 < q.n_rows) {
+                            const long long n2 = q.n_rows - r2 < R ? q.n_rows - r2 : R;
+                            bulk_prefetch_l2(q.rin + r2 * q.X, (unsigned)(n2 * q.X * sizeof(float)));
+                        }
+                    }
+                }
+                __syncthreads();            // the mbarrier's initialisation is visible before anybody waits on it
+                mbar_wait(bar, 0);
+#else
+                if (tid == 0)
+                    for (long long i = 0; i < nr * q.X; ++i) rows[i] = q.rin[row0 * q.X + i];      // (emulation: thread 0 runs first)
+#endif
+                src = rows + (long long)r * q.X;
+            }
+#ifdef __CUDA_ARCH__
+            else if (tid == 0 && q.prefetch_dist > 0) {
+                const long long r2 = ((long long)bx + q.prefetch_dist) * R;
+                if (r2 < q.n_rows) {
+                    const long long n2 = q.n_rows - r2 < R ? q.n_rows - r2 : R;
+                    bulk_prefetch_l2(q.rin + r2 * q.X, (unsigned)(n2 * q.X * sizeof(float)));
                 }
             }
 #endif
             if (p < B && active) {
-                float2 x[A];
-                const float* __restrict__ src = q.rin + row * q.X;
-                // indices first (branch free in the common modes), then all loads, then the fold + twist
-                float a[A], b[A];
+                // indices first (branch free in the common modes), then all loads
                 if (q.ext == EXT_MIRROR1) {
                     int ia[A], ib[A];
                     MVSIM_UNROLL
@@ -1000,27 +1033,31 @@ template <int A_, int B_, int R_> struct XFwd : LineShape<A_, B_> {
                         ib[n1] = mirror_once(p + n1 * B + N - q.left, q.X);
                     }
                     MVSIM_UNROLL
-                    for (int n1 = 0; n1 < A; ++n1) { a[n1] = src[ia[n1]]; b[n1] = src[ib[n1]]; }
+                    for (int n1 = 0; n1 < A; ++n1) { st.a[n1] = src[ia[n1]]; st.b[n1] = src[ib[n1]]; }
                 } else if (q.ext == EXT_ZERO) {
                     MVSIM_UNROLL
                     for (int n1 = 0; n1 < A; ++n1) {
                         const int i0 = p + n1 * B - q.left, i1 = i0 + N;
                         const bool ok0 = (unsigned)i0 < (unsigned)q.X, ok1 = (unsigned)i1 < (unsigned)q.X;
                         const float v0 = src[ok0 ? i0 : 0], v1 = src[ok1 ? i1 : 0];
-                        a[n1] = ok0 ? v0 : 0.f;
-                        b[n1] = ok1 ? v1 : 0.f;
+                        st.a[n1] = ok0 ? v0 : 0.f;
+                        st.b[n1] = ok1 ? v1 : 0.f;
                     }
                 } else {
                     MVSIM_UNROLL
                     for (int n1 = 0; n1 < A; ++n1) {
-                        a[n1] = src[mirror_single(p + n1 * B - q.left, q.X)];
-                        b[n1] = src[mirror_single(p + n1 * B + N - q.left, q.X)];
+                        st.a[n1] = src[mirror_single(p + n1 * B - q.left, q.X)];
+                        st.b[n1] = src[mirror_single(p + n1 * B + N - q.left, q.X)];
                     }
                 }
+            }
+        } else if (PH == 1) {
+            if (p < B && active) {
+                float2 x[A];
                 MVSIM_UNROLL
                 for (int n1 = 0; n1 < A; ++n1) {
                     const float2 t = q.twist[p + n1 * B];
-                    x[n1] = make_float2(a[n1] * t.x + b[n1] * t.y, a[n1] * t.y - b[n1] * t.x);   // (a - i b) * t
+                    x[n1] = make_float2(st.a[n1] * t.x + st.b[n1] * t.y, st.a[n1] * t.y - st.b[n1] * t.x);   // (a - i b) * t
                 }
                 fwd_first<A, B>(p, x, sm, r * S::ELEMS, 1, q.tw);
             }

@@ -161,7 +161,7 @@ template <int VEC> __device__ __forceinline__ void vload(float (&d)[VEC], const 
 
 // IDX32: the volume has < 2^31 voxels (every volume an ImgLib2 ArrayImg can hold), element offsets are 32-bit (wrapping unsigned
 // arithmetic: offsets of taps that are masked off may wrap, the ones that are dereferenced are exact)
-template <int VEC, int U, bool IDX32, int TPB = 128> __global__ void __launch_bounds__(TPB) rotate_attenuate_kernel(const float* __restrict__ in, float* __restrict__ out,
+template <int VEC, int U, bool IDX32> __global__ void __launch_bounds__(128) rotate_attenuate_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                                                         const RowTaps* __restrict__ tab, int X, int Y, int Z,
                                                                                         double delta, int steps, int Zl)
 {
@@ -274,11 +274,9 @@ int k_rotate_attenuate(mvsim_ctx* ctx, const float* in, float* out, const int64_
     // flight per thread and re-reads every source row from the L2.)
     if (X % 4 == 0 && aligned) {
         const size_t cols = (size_t)(X / 4) * Zl;
-        static const int tpb_env = [] { const char* v = getenv("MVSIM_ROT_TPB"); return v ? atoi(v) : 128; }();     // experiment knob (r02)
-        if (idx32 && tpb_env == 256) rotate_attenuate_kernel<4, 2, true, 256><<<blocks_for(cols, 256), 256, 0, ctx->stream>>>(in, out, tab, X, Y, Z, delta, steps, Zl);
-        else if (idx32 && tpb_env == 512) rotate_attenuate_kernel<4, 2, true, 512><<<blocks_for(cols, 512), 512, 0, ctx->stream>>>(in, out, tab, X, Y, Z, delta, steps, Zl);
-        else if (idx32 && tpb_env == 1283) rotate_attenuate_kernel<4, 3, true><<<blocks_for(cols, 128), 128, 0, ctx->stream>>>(in, out, tab, X, Y, Z, delta, steps, Zl);
-        else if (idx32) rotate_attenuate_kernel<4, 2, true><<<blocks_for(cols, 128), 128, 0, ctx->stream>>>(in, out, tab, X, Y, Z, delta, steps, Zl);
+        // measured on B200, config 3 (profiles/r02_notes.md): <4, 2> 0.904 ms, <4, 3> 0.882, with the row taps of the next batch
+        // requested early <4, 2> 0.96 / <4, 3> 0.857; CTAs of 256 / 512 threads 0.950 / 0.956
+        if (idx32) rotate_attenuate_kernel<4, 3, true><<<blocks_for(cols, 128), 128, 0, ctx->stream>>>(in, out, tab, X, Y, Z, delta, steps, Zl);
         else rotate_attenuate_kernel<4, 2, false><<<blocks_for(cols, 128), 128, 0, ctx->stream>>>(in, out, tab, X, Y, Z, delta, steps, Zl);
     } else if (X % 2 == 0 && aligned) {
         const size_t cols = (size_t)(X / 2) * Zl;
@@ -549,144 +547,18 @@ int k_adjust_apply(mvsim_ctx* ctx, float* inout, size_t n, const double* d_corr,
 // slice cz*inc of the input (:206, integer, bit exact).  lambda = v * mul, mul = (SNR/sqrt 5)^2
 // (S/Tools.java:76); the output is the raw count (S/Tools.java:84).
 // ---------------------------------------------------------------------------------------------
-// Block-cooperative finish of the voxels whose first PTRS proposal was not accepted by the squeeze (about 20 % of the
-// voxels with lambda >= 10).  Left to each thread, a warp would run the slow code up to four times with a handful of
-// active lanes; compacted per warp, the slow code still ran with ~9 of 32 lanes (ncu: 35 % of the kernel's instructions).
-// So the whole CTA compacts its pending voxels into shared memory (warp scans + a scan over the warp totals), all threads
-// work through the compact list with full warps, and the owners read their results back.  (Re-compacting the survivors
-// after every attempt was measured slower: 1.39 vs 1.00 ms, the extra block barriers cost more than the idle lanes.)
-// The result of a voxel still depends on (seed, stream, voxel index) only.  Every thread of the CTA must call this.
+// Cooperative finish of the voxels whose first PTRS proposal was not accepted by the squeeze (about 20 % of the voxels with
+// lambda >= 10).  Left to each thread, a warp would run the slow code up to four times with a handful of active lanes, so the
+// pending voxels are compacted into shared memory and finished with (nearly) full warps.  History: per-warp lists of one group per
+// thread ran the slow code with ~9 of 32 lanes; a CTA-wide list (64 threads, three __syncthreads) 0.93 ms on the profiling volume,
+// 23 % of the stall samples at the barriers (ncu r02b); the kernel below -- per-warp lists of TWO groups per thread, the same list
+// length without any block barrier -- 0.90 ms.  Re-compacting the survivors after every attempt was measured slower (1.39 ms).
+// The result of a voxel depends on (seed, stream, voxel index) only.
 struct PendingItem { double lam; unsigned long long index; uint32_t ru, rv; };
-#ifndef MVSIM_SAMPLER_THREADS
-#define MVSIM_SAMPLER_THREADS 64       // measured on B200 (config 3): 256 -> 1.00 ms, 128 -> 0.94, 64 -> 0.93 (fewer warps per block barrier)
-#endif
-constexpr int kSamplerThreads = MVSIM_SAMPLER_THREADS;
-struct SamplerShared {
-    PendingItem items[kSamplerThreads * 4];
-    float results[kSamplerThreads * 4];
-    int warp_total[kSamplerThreads / 32];
-};
 
-__device__ __forceinline__ void poisson_group4_block(const double (&lam)[4], uint64_t group, PoissonKey key, float (&out)[4], SamplerShared& sh)
-{
-    Philox4 r0, r1;
-    const unsigned pending = poisson_group4_fast(lam, group, key, out, r0, r1);
-    const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
-    const int cnt = __popc(pending);
-    int incl = cnt;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, d);
-        if ((int)lane >= d) incl += v;
-    }
-    if (lane == 31) sh.warp_total[w] = incl;
-    __syncthreads();
-    int base = 0, total = 0;
-#pragma unroll
-    for (int i = 0; i < kSamplerThreads / 32; ++i) {
-        const int t = sh.warp_total[i];
-        if (i < (int)w) base += t;
-        total += t;
-    }
-    if (total == 0) return;                 // block uniform (most background blocks)
-    const int first = base + incl - cnt;
-    int pos = first;
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-        if (pending & (1u << i)) {
-            PendingItem it;
-            it.lam = lam[i];
-            it.index = 4ull * group + (unsigned)i;
-            it.ru = i == 0 ? r0.x : i == 1 ? r0.y : i == 2 ? r0.z : r0.w;
-            it.rv = i == 0 ? r1.x : i == 1 ? r1.y : i == 2 ? r1.z : r1.w;
-            sh.items[pos++] = it;
-        }
-    __syncthreads();
-    for (int j = (int)threadIdx.x; j < total; j += kSamplerThreads) {
-        const PendingItem it = sh.items[j];
-        sh.results[j] = ptrs_resolve(it.lam, it.ru, it.rv, it.index, key);
-    }
-    __syncthreads();
-    pos = first;
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-        if (pending & (1u << i)) out[i] = sh.results[pos++];
-}
-
-// One thread = four consecutive output voxels (one Philox block pair, float4 traffic when the plane size
-// is a multiple of 4 so that the four voxels are also consecutive in the input).
-template <bool VEC4> __global__ void __launch_bounds__(kSamplerThreads) extract_kernel(const float* __restrict__ in, float* __restrict__ out, long long plane,
-                                                                          long long n_out, int inc, const double* __restrict__ d_corr,
-                                                                          float min_value, int noise, double mul, PoissonKey key,
-                                                                          long long in_plane0, long long group0,
-                                                                          unsigned short* __restrict__ out16, int* __restrict__ overflow)
-{
-    // in_plane0 / group0 (slab-decomposed volume; 0 otherwise): the first kept plane of this slab is local input plane in_plane0,
-    // and the Philox counter of local voxel group g is the GLOBAL group index g + group0 -- the noise of a voxel does not depend on
-    // how the volume was decomposed
-    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long i0 = 4 * g;
-    const bool valid = i0 < n_out;          // no early return: the sampler below is warp cooperative
-    float v[4] = { 0.f, 0.f, 0.f, 0.f };
-    if (valid) {
-        if (VEC4) {
-            const long long cz = i0 / plane, r = i0 - cz * plane;
-            const float4 t = __ldg(reinterpret_cast<const float4*>(in + (cz * inc + in_plane0) * plane + r));
-            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-        } else {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const long long i = i0 + k < n_out ? i0 + k : n_out - 1;
-                const long long cz = i / plane, r = i - cz * plane;
-                v[k] = __ldg(in + (cz * inc + in_plane0) * plane + r);
-            }
-        }
-        if (d_corr) {
-            const double corr = *d_corr;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) v[k] = adjust_one(v[k], corr, min_value);
-        }
-    }
-    if (noise) {
-        __shared__ SamplerShared sh;
-        double lam[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) lam[k] = valid ? __dmul_rn((double)v[k], mul) : 0.0;
-        poisson_group4_block(lam, (uint64_t)(g + group0), key, v, sh);
-    }
-    if (!valid) return;
-    if (VEC4) {
-        *reinterpret_cast<float4*>(out + i0) = make_float4(v[0], v[1], v[2], v[3]);
-    } else {
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (i0 + k < n_out) out[i0 + k] = v[k];
-    }
-    // count transport (opt-in, batch call): the same counts once more as uint16 -- half the bytes over the host link; a count
-    // beyond 65535 raises the flag and the host falls back to the float32 copy of that view
-    if (out16) {
-        bool over = false;
-        unsigned short q[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            over |= !(v[k] <= 65535.0f);
-            q[k] = (unsigned short)fminf(fmaxf(v[k], 0.f), 65535.0f);
-        }
-        if (VEC4) {
-            *reinterpret_cast<ushort4*>(out16 + i0) = make_ushort4(q[0], q[1], q[2], q[3]);
-        } else {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (i0 + k < n_out) out16[i0 + k] = q[k];
-        }
-        if (over) atomicOr(overflow, 1);
-    }
-}
-
-// Warp-cooperative variant: one thread = G groups of four consecutive voxels (a warp owns 128 G consecutive voxels), the pending
-// PTRS voxels of the WARP are compacted into the warp's own shared-memory list (ballot-free inclusive scan by shuffles) and
-// finished with full warps -- no block barrier anywhere.  With G = 2 a warp's list is as long as the 64-thread CTA's list of the
-// block-cooperative kernel above (same lane utilisation of the slow path) without its three __syncthreads.
+// One thread = G groups of four consecutive voxels (a warp owns 128 G consecutive voxels: float4 traffic when the plane size is a
+// multiple of 4); the pending PTRS voxels of the WARP go to the warp's own shared-memory list (slots from a shared counter) and are
+// finished with full warps -- no block barrier anywhere.
 constexpr int kWarpSamplerThreads = 128;
 template <int G> struct WarpSamplerShared {
     PendingItem items[32 * 4 * G];
@@ -842,21 +714,13 @@ int k_extract_slab(mvsim_ctx* ctx, const float* in, const int64_t dims[3], int64
     const long long first = k0 * plane;                                         // global index of the slab's first output voxel
     if (first % 4 != 0) return set_error(ctx, MVSIM_EUNSUPPORTED, "extract (slab): X*Y*first_kept_plane must be a multiple of 4");
     const bool vec4 = plane % 4 == 0 && (reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) % 16 == 0;
-    const unsigned blocks = blocks_for((size_t)((n_out + 3) / 4), kSamplerThreads);
     const double mul = snr_to_mul((double)snr);
     const PoissonKey key = make_poisson_key(seed, stream);
     const long long in_plane0 = k0 * inc - z0, group0 = first / 4;
     if (out16 && (reinterpret_cast<uintptr_t>(out16) % 8 != 0 || !d_overflow)) return set_error(ctx, MVSIM_EINVAL, "extract: uint16 buffer must be 8-byte aligned");
-    static const int variant = [] { const char* e = getenv("MVSIM_SAMPLER"); return e ? atoi(e) : 0; }();     // experiment knob (r02): 0 block-cooperative, 2 warp-cooperative with 2 groups per thread
-    if (variant == 2) {
-        const unsigned wblocks = blocks_for((size_t)((n_out + 3) / 4), (unsigned)(kWarpSamplerThreads * 2));
-        if (vec4) extract_warp_kernel<true, 2><<<wblocks, kWarpSamplerThreads, 0, ctx->stream>>>(in, out, plane, n_out, inc, d_corr, min_value, noise, mul, key, in_plane0, group0, out16, d_overflow);
-        else extract_warp_kernel<false, 2><<<wblocks, kWarpSamplerThreads, 0, ctx->stream>>>(in, out, plane, n_out, inc, d_corr, min_value, noise, mul, key, in_plane0, group0, out16, d_overflow);
-        MVSIM_LAUNCH_CHECK(ctx);
-        return MVSIM_OK;
-    }
-    if (vec4) extract_kernel<true><<<blocks, kSamplerThreads, 0, ctx->stream>>>(in, out, plane, n_out, inc, d_corr, min_value, noise, mul, key, in_plane0, group0, out16, d_overflow);
-    else extract_kernel<false><<<blocks, kSamplerThreads, 0, ctx->stream>>>(in, out, plane, n_out, inc, d_corr, min_value, noise, mul, key, in_plane0, group0, out16, d_overflow);
+    const unsigned wblocks = blocks_for((size_t)((n_out + 3) / 4), (unsigned)(kWarpSamplerThreads * 2));
+    if (vec4) extract_warp_kernel<true, 2><<<wblocks, kWarpSamplerThreads, 0, ctx->stream>>>(in, out, plane, n_out, inc, d_corr, min_value, noise, mul, key, in_plane0, group0, out16, d_overflow);
+    else extract_warp_kernel<false, 2><<<wblocks, kWarpSamplerThreads, 0, ctx->stream>>>(in, out, plane, n_out, inc, d_corr, min_value, noise, mul, key, in_plane0, group0, out16, d_overflow);
     MVSIM_LAUNCH_CHECK(ctx);
     return MVSIM_OK;
 }
