@@ -138,12 +138,7 @@ struct CudaLauncher {
         static const int xdist = prefetch_dist(3);
         static const int xidist = prefetch_dist(3);
         if (inverse) q.prefetch_dist = ((s.n * 8) % 16 == 0 && (reinterpret_cast<uintptr_t>(q.cin) & 15) == 0) ? xidist : 0;
-        else {
-            const bool aligned = q.X % 4 == 0 && (reinterpret_cast<uintptr_t>(q.rin) & 15) == 0;
-            q.prefetch_dist = (!psf_phase && aligned) ? xdist : 0;
-            static const bool bulk_on = env_int("MVSIM_X_BULK", 1) != 0;        // A/B knob (r02): 0 = per-thread gather from global memory
-            q.use_bulk = (aligned && bulk_on) ? 1 : 0;
-        }
+        else q.prefetch_dist = (!psf_phase && q.X % 4 == 0 && (reinterpret_cast<uintptr_t>(q.rin) & 15) == 0) ? xdist : 0;
         StageTimer t(ctx, psf_phase ? MVSIM_T_PSF : (inverse ? MVSIM_T_FFT_XINV : MVSIM_T_FFT_XFWD));
         return finish(fft_launch(inverse ? FFT_XINV : FFT_XFWD, lanes, s.n, &q, (unsigned)x_blocks(s, q.n_rows), 1, ctx->stream), "x pass");
     }

@@ -136,13 +136,6 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* tmap, in
                  ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(tmap), "r"((unsigned)__cvta_generic_to_shared(bar)),
                    "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
-// contiguous bulk copy global -> shared by the TMA unit (no tensor map), completion signalled on the mbarrier; 16-byte aligned
-// addresses, size a multiple of 16
-__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, unsigned bytes, uint64_t* bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
-                 ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
-}
 // L2 prefetches issued by ONE thread for the data a later CTA will gather: a whole tile (tensor form) or a contiguous range
 __device__ __forceinline__ void tma_prefetch_4d(const void* tmap, int c0, int c1, int c2, int c3)
 {

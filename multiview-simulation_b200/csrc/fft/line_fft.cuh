@@ -247,8 +247,22 @@ template <int A_, int B_, int T_> struct StridedFwd : LineShape<A_, B_> {
             if (p < B && active) {
                 float2 x[A];
                 const float2* src = q.in + tin * q.in_tstride + outer * q.in_ostride + lane;
-                gather_line<A, B>(x, src, q.in_estride, q.in_e32, p, q.left, q.n_src, q.ext);
-                fwd_first<A, B, kPackedStrided>(p, x, sm, lane, T, q.tw);
+                constexpr int K = RegSelZ<A, kPackedStrided>::K;
+                if (q.ext == EXT_ZERO && q.left == 0 && q.n_src <= K * B) {
+                    // zero-extended line no longer than a fifth of the padded length (the PSF's y pass: 128 of 1152 samples):
+                    // only x[0..K) carry data, first half with the zero terms removed at generation time
+                    MVSIM_UNROLL
+                    for (int n1 = 0; n1 < K; ++n1) {
+                        const int n = p + n1 * B;
+                        const bool ok = n < q.n_src;
+                        const float2 v = src[(long long)(ok ? n : 0) * q.in_estride];
+                        x[n1] = ok ? v : make_float2(0.f, 0.f);
+                    }
+                    fwd_first_zext<A, B, kPackedStrided>(p, x, sm, lane, T, q.tw);
+                } else {
+                    gather_line<A, B>(x, src, q.in_estride, q.in_e32, p, q.left, q.n_src, q.ext);
+                    fwd_first<A, B, kPackedStrided>(p, x, sm, lane, T, q.tw);
+                }
             }
         } else {
             if (p < A && active) {
@@ -959,23 +973,21 @@ struct XParams {
     double* partials;       // inverse: per-block sums of the stored voxels (may be null)
     int X, n_rows, left, ext, crop0;
     int prefetch_dist;      // forward: thread 0 of CTA i prefetches the rows of CTA i + prefetch_dist into the L2 (0 = off)
-    int use_bulk;           // forward: the CTA's rows are staged in shared memory by one TMA bulk copy (X % 4 == 0, 16-byte aligned source)
 };
 
 template <int A> struct XFwdState { float a[A], b[A]; };
 
-// Forward x pass.  The R rows of a CTA are contiguous in the source, so ONE thread asks the TMA unit for them (cp.async.bulk, no
-// tensor map) and the threads pick their 2 A samples from shared memory: the per-thread gather of 2 A scalar loads with 64-bit
-// address arithmetic kept the L1 / LSU pipe at 82 % of its peak and a quarter of the instructions were index arithmetic (ncu,
-// profiles/r02b).  The staged rows alias the exchange area (a row of X <= 2N floats is never larger than its A x (B|1) complex
-// exchange slots), hence one more barrier between the last read of a row and the first write of the exchange.
+// Forward x pass in three phases: (0) every thread gathers its 2 A samples into registers (indices first, then all loads),
+// (1) fold + twist + first half, (2) second half + stores.  Splitting the gather from the transform at a barrier took the pass
+// from 0.952 to 0.894 ms at config 3 (8 instead of 64 bytes of spills under the 80-register cap).  Measured and dropped in round 2:
+// staging the CTA's ten contiguous rows in shared memory with one TMA bulk copy (0.903 ms: the L1 / LSU pressure of the 48 scalar
+// loads per thread, 82 % of that pipe's peak under ncu, is not what bounds the pass).
 template <int A_, int B_, int R_> struct XFwd : LineShape<A_, B_> {
     using S = LineShape<A_, B_>;
     static constexpr bool IS_X = true;
     static constexpr int A = A_, B = B_, R = R_;
     static constexpr int THREADS = R * S::P;
-    static constexpr int EXCH = S::ELEMS * R;                                      // float2 elements
-    static constexpr int SMEM_BYTES = EXCH * (int)sizeof(float2) + 16;             // + the mbarrier
+    static constexpr int SMEM_BYTES = S::ELEMS * R * (int)sizeof(float2);
     static constexpr int NPH = 3;
     using Params = XParams;
     using State = XFwdState<A_>;
@@ -984,46 +996,20 @@ template <int A_, int B_, int R_> struct XFwd : LineShape<A_, B_> {
     {
         constexpr int N = S::N;
         const int r = tid / S::P, p = tid % S::P;
-        const long long row0 = (long long)bx * R;
-        const long long row = row0 + r;
+        const long long row = (long long)bx * R + r;
         const bool active = row < q.n_rows;
         if (PH == 0) {
-            const long long nr = q.n_rows - row0 < R ? q.n_rows - row0 : R;
-            const float* __restrict__ src = q.rin + row * q.X;
-            if (q.use_bulk) {
-                float* rows = reinterpret_cast<float*>(sm);
 #ifdef __CUDA_ARCH__
-                uint64_t* bar = reinterpret_cast<uint64_t*>(sm + EXCH);
-                if (tid == 0) {
-                    mbar_init(bar, 1);
-                    mbar_expect_tx(bar, (unsigned)(nr * q.X * sizeof(float)));
-                    bulk_load(rows, q.rin + row0 * q.X, (unsigned)(nr * q.X * sizeof(float)), bar);
-                    if (q.prefetch_dist > 0) {
-                        const long long r2 = ((long long)bx + q.prefetch_dist) * R;
-                        if (r2 < q.n_rows) {
-                            const long long n2 = q.n_rows - r2 < R ? q.n_rows - r2 : R;
-                            bulk_prefetch_l2(q.rin + r2 * q.X, (unsigned)(n2 * q.X * sizeof(float)));
-                        }
-                    }
-                }
-                __syncthreads();            // the mbarrier's initialisation is visible before anybody waits on it
-                mbar_wait(bar, 0);
-#else
-                if (tid == 0)
-                    for (long long i = 0; i < nr * q.X; ++i) rows[i] = q.rin[row0 * q.X + i];      // (emulation: thread 0 runs first)
-#endif
-                src = rows + (long long)r * q.X;
-            }
-#ifdef __CUDA_ARCH__
-            else if (tid == 0 && q.prefetch_dist > 0) {
-                const long long r2 = ((long long)bx + q.prefetch_dist) * R;
-                if (r2 < q.n_rows) {
-                    const long long n2 = q.n_rows - r2 < R ? q.n_rows - r2 : R;
-                    bulk_prefetch_l2(q.rin + r2 * q.X, (unsigned)(n2 * q.X * sizeof(float)));
+            if (tid == 0 && q.prefetch_dist > 0) {
+                const long long r0 = ((long long)bx + q.prefetch_dist) * R;
+                if (r0 < q.n_rows) {
+                    const long long nr = q.n_rows - r0 < R ? q.n_rows - r0 : R;
+                    bulk_prefetch_l2(q.rin + r0 * q.X, (unsigned)(nr * q.X * sizeof(float)));
                 }
             }
 #endif
             if (p < B && active) {
+                const float* __restrict__ src = q.rin + row * q.X;
                 // indices first (branch free in the common modes), then all loads
                 if (q.ext == EXT_MIRROR1) {
                     int ia[A], ib[A];

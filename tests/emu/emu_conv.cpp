@@ -45,10 +45,8 @@ struct EmuLauncher {
         const int r = 256 / p > 0 ? 256 / p : 1;
         return (n_rows + r - 1) / r;
     }
-    int launch_x(bool inverse, const FftSize& s, const XParams& q0)
+    int launch_x(bool inverse, const FftSize& s, const XParams& q)
     {
-        XParams q = q0;
-        q.use_bulk = (!inverse && q.X % 4 == 0) ? 1 : 0;       // like the CUDA launcher: rows staged in shared memory when they can be bulk-copied
         const int gx = x_blocks(s, q.n_rows);
         switch (s.n) {
 #define MVSIM_X(n_, a_, b_) case n_: if (inverse) emulate<XInv<a_, b_, Rows<a_, b_>::R>>(q, gx, 1); else emulate<XFwd<a_, b_, Rows<a_, b_>::R>>(q, gx, 1); return 0;
