@@ -180,6 +180,8 @@ template <class L> int conv_inverse_y(L& l, const ConvPlan& pl, const SlabGeom& 
     ip.n_out = pl.dims[1] - y0 < pl.y_block ? pl.dims[1] - y0 : pl.y_block;
     ip.out_offset = y0;
     ip.in_tstride = (long long)g.z_local * ny * T; ip.in_estride = T; ip.in_ostride = ny * T;
+    // peer-to-peer slab mode: the fused z pass delivered [KT][Ny][Zl][T] (each owner's z range of a line in one bulk copy)
+    if (ws.n_peers > 1) { ip.in_estride = (long long)g.z_local * T; ip.in_ostride = T; }
     ip.out_tstride = T; ip.out_estride = kxc; ip.out_ostride = (long long)pl.dims[1] * kxc;
     ip.swap_grid = 0; ip.scale = 1.0f;
     ip.tile0 = 0; ip.in_tile_global = 1; ip.out_tile_global = 1;

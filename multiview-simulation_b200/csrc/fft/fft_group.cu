@@ -13,7 +13,7 @@ namespace mvsim {
 // different tiles overlap: x passes 3 (<= 85 registers at 256 threads), strided passes 2 (T=8) / 4 (T=4).
 template <class K> constexpr int min_blocks()
 {
-    return K::IS_X ? (K::THREADS <= 256 ? 3 : 1) : (K::THREADS <= 160 ? 4 : (K::THREADS <= 288 ? 2 : 1));
+    return K::IS_X ? (K::THREADS <= 256 ? MVSIM_X_MINBLOCKS : 1) : (K::THREADS <= 160 ? 4 : (K::THREADS <= 288 ? 2 : 1));
 }
 
 template <class K> __global__ void __launch_bounds__(K::THREADS, min_blocks<K>()) fft_kernel(const __grid_constant__ typename K::Params q)

@@ -13,7 +13,13 @@ enum FftKind { FFT_XFWD = 0, FFT_XINV = 1, FFT_SFWD = 2, FFT_SINV = 3, FFT_ZFUSE
 // the decimated fused z kernels are built only for z lines of these lengths (build time): covers the BASELINE
 // configs (339 -> 360 with inc 3, 639 -> 640 with inc 5)
 constexpr int kDecMinLine = 300, kDecMaxLine = 660;
-constexpr int kXThreadsTarget = 256; // x passes: rows per CTA = kXThreadsTarget / threads-per-line
+#ifndef MVSIM_X_THREADS
+#define MVSIM_X_THREADS 256
+#endif
+#ifndef MVSIM_X_MINBLOCKS
+#define MVSIM_X_MINBLOCKS 3
+#endif
+constexpr int kXThreadsTarget = MVSIM_X_THREADS; // x passes: rows per CTA = kXThreadsTarget / threads-per-line
 
 constexpr int x_rows_per_block(int a, int b) { return (kXThreadsTarget / (a > b ? a : b)) > 0 ? kXThreadsTarget / (a > b ? a : b) : 1; }
 

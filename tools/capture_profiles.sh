@@ -12,7 +12,7 @@ out=gpurun_out
 mkdir -p $out
 python tools/prof_conv.py 1 > $out/${tag}_plain.log 2>&1 || { echo "plain run failed"; cat $out/${tag}_plain.log; exit 1; }
 # name : regex on the demangled kernel name : launches of that name to skip (the PSF's x / y passes come before the image's)
-kernels="zfused:ZFused:0 sample:extract_kernel:0 rotate:rotate_attenuate_kernel:0 xfwd:XFwd:1 yfwd:StridedFwd:1 xinv:XInv:0 yinv:StridedInv:0"
+kernels="zfused:ZFused:0 sample:extract_:0 rotate:rotate_attenuate_kernel:0 xfwd:XFwd:1 yfwd:StridedFwd:1 xinv:XInv:0 yinv:StridedInv:0"
 : > $out/${tag}_kernels.md
 for k in $kernels; do
     name=${k%%:*}; rest=${k#*:}; rx=${rest%%:*}; skip=${rest##*:}
