@@ -119,9 +119,9 @@ struct CudaLauncher {
     int lanes;
     bool h_on_the_fly = otf_default();
 
-    static int x_blocks(const FftSize& s, int n_rows)
+    static int x_blocks(const FftSize& s, int n_rows, bool inverse)
     {
-        const int r = x_rows_per_block(s.a, s.b);
+        const int r = x_rows_per_block(s.a, s.b, inverse);
         return (n_rows + r - 1) / r;
     }
     int finish(int r, const char* what)
@@ -140,7 +140,7 @@ struct CudaLauncher {
         if (inverse) q.prefetch_dist = ((s.n * 8) % 16 == 0 && (reinterpret_cast<uintptr_t>(q.cin) & 15) == 0) ? xidist : 0;
         else q.prefetch_dist = (!psf_phase && q.X % 4 == 0 && (reinterpret_cast<uintptr_t>(q.rin) & 15) == 0) ? xdist : 0;
         StageTimer t(ctx, psf_phase ? MVSIM_T_PSF : (inverse ? MVSIM_T_FFT_XINV : MVSIM_T_FFT_XFWD));
-        return finish(fft_launch(inverse ? FFT_XINV : FFT_XFWD, lanes, s.n, &q, (unsigned)x_blocks(s, q.n_rows), 1, ctx->stream), "x pass");
+        return finish(fft_launch(inverse ? FFT_XINV : FFT_XFWD, lanes, s.n, &q, (unsigned)x_blocks(s, q.n_rows, inverse), 1, ctx->stream), "x pass");
     }
     int launch_strided(bool inverse, const FftSize& s, const StridedParams& q0, int n_tiles, int n_outer)
     {
@@ -319,7 +319,7 @@ int conv_device(mvsim_ctx* ctx, const float* img, const int64_t dims[3], const f
     double* partials = nullptr;
     const int planes = conv_out_planes(pl, g, keep_inc);
     if (out_planes) *out_planes = planes;
-    const int nblocks = CudaLauncher::x_blocks(pl.sx, pl.dims[1] * planes);
+    const int nblocks = CudaLauncher::x_blocks(pl.sx, pl.dims[1] * planes, true);      // per-block sums of the inverse x pass
     if (d_sum) MVSIM_TRY(buf.get(&partials, (size_t)nblocks));
     MVSIM_TRY(conv_apply(l, pl, g, ws, img, out, partials, keep_inc));
     if (d_sum) {

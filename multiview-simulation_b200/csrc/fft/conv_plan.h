@@ -13,6 +13,14 @@ namespace mvsim {
 
 struct FftSize { int n, a, b; };
 
+// x passes: rows per CTA = thread target / threads per line.  Measured on B200 at config 3 (576-point rows, 24 threads per line,
+// profiles/r02_notes.md): the forward pass wants ~120 registers and spills under the 80-register cap of 3 CTAs x 10 rows; 6 rows x
+// 4 CTAs per SM (96 registers) 0.962 -> 0.920 ms.  The inverse pass is fastest with 10 rows x 3 CTAs (0.252 ms; 0.277 with 6 x 4).
+constexpr int kXThreadsFwd = 144, kXThreadsInv = 256;
+constexpr int x_rows_for(int target, int a, int b) { return (target / (a > b ? a : b)) > 0 ? target / (a > b ? a : b) : 1; }
+constexpr int x_rows_per_block(int a, int b, bool inverse) { return x_rows_for(inverse ? kXThreadsInv : kXThreadsFwd, a, b); }
+
+
 // X(n, a, b): supported complex line lengths n = a*b, ascending; a, b are in-register sub-transform sizes
 // (tools/gen_regfft.py).  Balanced splits (a ~ b) keep all threads of a line busy in both halves of the
 // two-level transform, so the planner prefers e.g. 648 = 24*27 over 640 = 20*32 for a 639-point minimum.

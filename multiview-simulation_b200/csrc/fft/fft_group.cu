@@ -10,10 +10,10 @@
 namespace mvsim {
 
 // resident CTAs per SM the register allocator must allow, so that the load, exchange and store phases of
-// different tiles overlap: x passes 3 (<= 85 registers at 256 threads), strided passes 2 (T=8) / 4 (T=4).
+// different tiles overlap: x passes 4 (<= 160 threads, forward) / 3 (<= 256 threads, inverse), strided passes 2 (T=8) / 4 (T=4).
 template <class K> constexpr int min_blocks()
 {
-    return K::IS_X ? (K::THREADS <= 256 ? MVSIM_X_MINBLOCKS : 1) : (K::THREADS <= 160 ? 4 : (K::THREADS <= 288 ? 2 : 1));
+    return K::IS_X ? (K::THREADS <= 160 ? 4 : (K::THREADS <= 256 ? 3 : 1)) : (K::THREADS <= 160 ? 4 : (K::THREADS <= 288 ? 2 : 1));
 }
 
 template <class K> __global__ void __launch_bounds__(K::THREADS, min_blocks<K>()) fft_kernel(const __grid_constant__ typename K::Params q)
@@ -60,9 +60,9 @@ template <class K> static int launch(const void* params, unsigned gx, unsigned g
 
 template <int A, int B> static int launch_size(int kind, const void* params, unsigned gx, unsigned gy, cudaStream_t s)
 {
-    constexpr int R = x_rows_per_block(A, B);
+    constexpr int RF = x_rows_per_block(A, B, false), RI = x_rows_per_block(A, B, true);
     constexpr int T = MVSIM_LANES;
-    (void)R;
+    (void)RF; (void)RI;
 #if MVSIM_DEC_UNIT
     // the decimated fused z kernels live in their own translation units (build time)
     constexpr bool built = A * B >= kDecMinLine && A * B <= kDecMaxLine;
@@ -77,8 +77,8 @@ template <int A, int B> static int launch_size(int kind, const void* params, uns
 #else
     switch (kind) {
 #if MVSIM_LANES == 8
-    case FFT_XFWD: return launch<XFwd<A, B, R>>(params, gx, gy, s);
-    case FFT_XINV: return launch<XInv<A, B, R>>(params, gx, gy, s);
+    case FFT_XFWD: return launch<XFwd<A, B, RF>>(params, gx, gy, s);
+    case FFT_XINV: return launch<XInv<A, B, RI>>(params, gx, gy, s);
 #endif
     case FFT_SFWD: return launch<StridedFwd<A, B, T>>(params, gx, gy, s);
     case FFT_SINV: return launch<StridedInv<A, B, T>>(params, gx, gy, s);

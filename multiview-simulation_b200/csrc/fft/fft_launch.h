@@ -13,16 +13,6 @@ enum FftKind { FFT_XFWD = 0, FFT_XINV = 1, FFT_SFWD = 2, FFT_SINV = 3, FFT_ZFUSE
 // the decimated fused z kernels are built only for z lines of these lengths (build time): covers the BASELINE
 // configs (339 -> 360 with inc 3, 639 -> 640 with inc 5)
 constexpr int kDecMinLine = 300, kDecMaxLine = 660;
-#ifndef MVSIM_X_THREADS
-#define MVSIM_X_THREADS 256
-#endif
-#ifndef MVSIM_X_MINBLOCKS
-#define MVSIM_X_MINBLOCKS 3
-#endif
-constexpr int kXThreadsTarget = MVSIM_X_THREADS; // x passes: rows per CTA = kXThreadsTarget / threads-per-line
-
-constexpr int x_rows_per_block(int a, int b) { return (kXThreadsTarget / (a > b ? a : b)) > 0 ? kXThreadsTarget / (a > b ? a : b) : 1; }
-
 // Lanes (T) = neighbouring kx columns a CTA of the strided passes owns: 8 complex = 64-byte segments.
 // (T = 4 with 4 CTAs/SM was measured on B200 and gave the same throughput; only T = 8 is built.)
 int strided_lanes();

@@ -34,22 +34,22 @@ template <class K> static void emulate(const typename K::Params& q, int gx, int 
 }
 
 static constexpr int T = 8;
-template <int A, int B> struct Rows { static constexpr int R = (256 / LineShape<A, B>::P) > 0 ? 256 / LineShape<A, B>::P : 1; };
+// x_rows_per_block (fft/conv_plan.h): the emulation uses the CUDA launcher's rows per CTA
+template <int A, int B> struct Rows { static constexpr int RF = x_rows_per_block(A, B, false), RI = x_rows_per_block(A, B, true); };
 
 struct EmuLauncher {
     int lanes = T;
     bool h_on_the_fly = false;
-    int x_blocks(const FftSize& s, int n_rows) const
+    int x_blocks(const FftSize& s, int n_rows, bool inverse) const
     {
-        const int p = s.a > s.b ? s.a : s.b;
-        const int r = 256 / p > 0 ? 256 / p : 1;
+        const int r = x_rows_per_block(s.a, s.b, inverse);
         return (n_rows + r - 1) / r;
     }
     int launch_x(bool inverse, const FftSize& s, const XParams& q)
     {
-        const int gx = x_blocks(s, q.n_rows);
+        const int gx = x_blocks(s, q.n_rows, inverse);
         switch (s.n) {
-#define MVSIM_X(n_, a_, b_) case n_: if (inverse) emulate<XInv<a_, b_, Rows<a_, b_>::R>>(q, gx, 1); else emulate<XFwd<a_, b_, Rows<a_, b_>::R>>(q, gx, 1); return 0;
+#define MVSIM_X(n_, a_, b_) case n_: if (inverse) emulate<XInv<a_, b_, Rows<a_, b_>::RI>>(q, gx, 1); else emulate<XFwd<a_, b_, Rows<a_, b_>::RF>>(q, gx, 1); return 0;
             MVSIM_FFT_SIZES(MVSIM_X)
 #undef MVSIM_X
         }
@@ -202,7 +202,7 @@ extern "C" int emu_convolve(const float* img, const int64_t dims[3], const float
     }
     double total = 0;
     for (int r = 0; r < world; ++r) {
-        std::vector<double> partials(l.x_blocks(pl.sx, pl.dims[1] * planes), 0.0);
+        std::vector<double> partials(l.x_blocks(pl.sx, pl.dims[1] * planes, true), 0.0);
         float* o = out + (size_t)(world > 1 ? rk[r].g.z0 : 0) * pl.dims[1] * pl.dims[0];
         if ((err = conv_inverse_x(l, pl, rk[r].ws, o, partials.data(), planes))) return err;
         for (double v : partials) total += v;
