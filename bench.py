@@ -598,10 +598,10 @@ def run_slab(args, rank, world, local_rank):
         torch.cuda.synchronize()
     for _ in range(args.warmup):
         sc.convolve(img, d_psf, out)
+    nv0 = nvlink_counters(local_rank)       # (NVML queries take milliseconds: before the barrier, so that no rank enters the timed loop late)
     barrier()
     ctx.profile(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    nv0 = nvlink_counters(local_rank)
     e0.record(stream)
     for _ in range(args.steps):
         sc.convolve(img, d_psf, out)
