@@ -394,6 +394,7 @@ def run_ours(args, rank, world, local_rank):
     callers = callers[:n_callers]
     pipe_steps = 4 * n_callers
     gt_tensor = torch.empty(shape, dtype=torch.float32, device=torch.device("cuda", local_rank)) if world > 1 else None
+    gt_tensor_b = torch.empty_like(gt_tensor) if world > 1 else None
 
     def caller_loop(i, n):
         for _ in range(n):
@@ -447,11 +448,50 @@ def run_ours(args, rank, world, local_rank):
             res["broadcast"] = max_over_ranks((time.perf_counter() - t0) * 1e3 / e2e_steps)
             if checksum(out_pin) != chk:
                 raise SystemExit("bench.py: broadcast ground truth changed the result")
+            # the same, with the NEXT dataset's ground truth uploaded (rank 0) and broadcast on a side stream while the current one is
+            # simulated and its results drain: the host link is full duplex and the results' direction is the busy one
+            bufs = [gt_tensor, gt_tensor_b]
+            side = torch.cuda.Stream()
+
+            def issue(i):
+                with torch.cuda.stream(side):
+                    if rank == 0:
+                        bufs[i].copy_(torch.from_numpy(gt_pin.array), non_blocking=True)
+                    return grp.dist.broadcast(bufs[i], src=0, async_op=True)
+
+            def run_prefetched(n):
+                w = issue(0)
+                for k in range(n):
+                    w.wait()
+                    side.synchronize()
+                    torch.cuda.current_stream().synchronize()
+                    cur = bufs[k % 2]
+                    w = issue((k + 1) % 2)              # every step issues one upload + broadcast (the last one is waited for below)
+                    for v in range(nv):
+                        psf_pin[v].array[...] = psf_raw[v]
+                    vol = mv.DeviceVolume.wrap(ctx, shape, cur.data_ptr(), keepalive=cur)
+                    S.simulateViews(vol, [p.array for p in psf_pin], degrees, inc=inc, poissonSNR=snr, rnd=464232194, ctx=ctx,
+                                    outs=[o.array for o in out_pin], first_stream=rank * nv)
+                    vol.free()
+                w.wait()
+                side.synchronize()
+                torch.cuda.current_stream().synchronize()
+            run_prefetched(1)
+            barrier()
+            t0 = time.perf_counter()
+            run_prefetched(e2e_steps)
+            barrier()
+            # n steps contain n + 1 uploads, the first of them not overlapped: a conservative figure
+            res["broadcast_prefetch"] = max_over_ranks((time.perf_counter() - t0) * 1e3 / e2e_steps)
+            if checksum(out_pin) != chk:
+                raise SystemExit("bench.py: prefetched broadcast changed the result")
         return res, chk
 
     MODE_TEXT = {"serial": "1 caller thread per rank, ground truth uploaded by every rank",
                  "pipelined": f"{n_callers} caller threads x 1 context each per rank, steps dealt round-robin (H2D of one step runs under the kernels and D2H of the others)",
-                 "broadcast": "views of one dataset sharded over the ranks: ground truth uploaded once by rank 0 and NCCL-broadcast over NVLink, 1 caller per rank"}
+                 "broadcast": "views of one dataset sharded over the ranks: ground truth uploaded once by rank 0 and NCCL-broadcast over NVLink, 1 caller per rank",
+                 "broadcast_prefetch": ("views of one dataset sharded over the ranks, one dataset per step: the next dataset's ground truth is uploaded by rank 0 and "
+                                        "NCCL-broadcast on a side stream while the current one is simulated and its results drain, 1 caller per rank")}
     modes_f32, chk_f32 = run_modes(False)
     modes_u16, result_checksum = run_modes(True, args.widen_threads)
     widen_sweep = {}
@@ -465,11 +505,13 @@ def run_ours(args, rank, world, local_rank):
     e2e_key = best_u16 if use_u16 else best_f32
     e2e_ms = (modes_u16 if use_u16 else modes_f32)[e2e_key]
     e2e_mode = MODE_TEXT[e2e_key]
-    h2d = (4 * vox_per_view // world if e2e_key == "broadcast" else 4 * vox_per_view) + nv * 4 * kvox      # per rank (broadcast: one upload for all)
+    h2d = (4 * vox_per_view // world if e2e_key.startswith("broadcast") else 4 * vox_per_view) + nv * 4 * kvox      # per rank (broadcast: one upload for all)
     d2h_u16 = nv * (2 * ovox + 4 * kvox + 4)        # uint16 counts + the normalised PSFs + the overflow flags
     d2h_f32 = nv * 4 * (ovox + kvox)
     d2h = d2h_u16 if use_u16 else d2h_f32
-    link = host_link_probe(torch) if rank == 0 else None
+    barrier()
+    link = host_link_probe(torch)            # every rank at the same time: the rates a GPU gets while its neighbours use the host too
+    barrier()
 
     if rank != 0:
         grp.close()
@@ -552,7 +594,7 @@ def run_ours(args, rank, world, local_rank):
             "e2e": {"value": world * nv * vox_per_view / (e2e_ms * 1e-3), "unit": "voxels/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "views_per_s": world * nv / (e2e_ms * 1e-3),
                     "api": "mvsim_simulate_views / mvsim_dev_simulate_views (pinned host buffers in, float32 volumes out)",
-                    "steps": pipe_steps if e2e_key == "pipelined" else e2e_steps, "mode": e2e_mode, "callers": n_callers,
+                    "steps": pipe_steps if e2e_key == "pipelined" else e2e_steps, "mode": e2e_mode, "mode_key": e2e_key, "callers": n_callers,
                     "count_transport": "uint16" if use_u16 else "float32",
                     "count_transport_note": ("uint16 = opt-in MVSIM_OPT_COUNT_TRANSPORT: Poisson counts cross the host link as uint16 and host threads widen "
                                              "them to the caller's float32 buffers inside the timed call (bit-identical results, half the D2H bytes, but "
@@ -562,7 +604,8 @@ def run_ours(args, rank, world, local_rank):
                     "widen_threads": args.widen_threads, "widen_sweep_ms_per_step": widen_sweep or None,
                     "host_link": link,
                     "frac_of_host_link": (max(h2d / link["h2d_concurrent_GBps"], d2h / link["d2h_concurrent_GBps"]) / 1e9 / (e2e_ms * 1e-3)) if link else None,
-                    "frac_of_host_link_basis": "time the busier direction needs at the rate measured with both directions active / e2e time per step (1 GPU active)",
+                    "frac_of_host_link_basis": ("time the busier direction needs at rank 0's rate with both directions active and all N GPUs copying at once "
+                                                "/ e2e time per step"),
                     "result_checksum": result_checksum},
             "gpu_launches": launches, "roofline": roofline, "stages": stages_ms, "fft_ms_per_launch": fft_passes,
             "fft_padded_xyz": [int(nfft[0]), int(ny), int(nz)], "cpu_baseline": cpu, "clocks": clk}

@@ -71,18 +71,6 @@ void dev_free(mvsim_ctx* ctx, void* p)
     if (p) cudaFreeAsync(p, ctx->stream);
 }
 
-int side_fork(mvsim_ctx* ctx)
-{
-    if (!ctx->side_stream) {
-        MVSIM_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
-        MVSIM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
-        MVSIM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
-    }
-    MVSIM_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
-    MVSIM_CUDA(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
-    return MVSIM_OK;
-}
-
 int get_tables(mvsim_ctx* ctx, int n, mvsim_tables* t)
 {
     auto it = ctx->tables.find(n);
@@ -374,22 +362,6 @@ static int dev_simulate_view(mvsim_ctx* ctx, const mvsim_view_params* p, const f
     DevBuf a(ctx), b(ctx);
     MVSIM_TRY(a.alloc(n * sizeof(float)));
     MVSIM_TRY(b.alloc(n * sizeof(float)));
-    // :255.  With the PSF-spectrum cache off the PSF chain runs on the side stream, under rotate_attenuate and the image's forward
-    // passes (MVSIM_PSF_OVERLAP=0: on the main stream, A/B runs); the cache needs the hash on the host first, so it stays in line
-    static const bool overlap_on = [] { const char* e = getenv("MVSIM_PSF_OVERLAP"); return !e || atoi(e) != 0; }();
-    const bool overlap = overlap_on && ctx->psf_cache_max_bytes == 0;
-    struct SideJoin {       // whatever happens below, the main stream ends up ordered after the side stream's work on this view
-        mvsim_ctx* c; bool on;
-        ~SideJoin() { if (on && cudaEventRecord(c->ev_join, c->side_stream) == cudaSuccess) cudaStreamWaitEvent(c->stream, c->ev_join, 0); }
-    } join = { ctx, false };
-    if (overlap) {
-        MVSIM_TRY(side_fork(ctx));
-        join.on = true;
-        StreamSwap sw(ctx, ctx->side_stream);
-        MVSIM_TRY(dev_psf_normalize(ctx, psf, elems(p->kdims)));
-    } else {
-        MVSIM_TRY(dev_psf_normalize(ctx, psf, elems(p->kdims)));
-    }
     {
         // :570 + :573 in one pass (the rotated volume is not part of this entry point's output)
         double inv[12];
@@ -406,11 +378,12 @@ static int dev_simulate_view(mvsim_ctx* ctx, const mvsim_view_params* p, const f
             MVSIM_TRY(dev_attenuate(ctx, a.f(), b.f(), p->dims, p->delta, p->strict_reference));
         } else if (st != MVSIM_OK) return st;
     }
+    // (Measured and dropped in round 2: the PSF chain -- normalise, x and y transforms, 0.26 ms -- on a side stream under
+    // rotate_attenuate and the image's forward passes: 6.385 -> 6.345 ms per view with tools/time_view.py, but 6.2 -> 8.1 ms inside
+    // bench.py's loop on a torch stream; the saturating main-stream kernels leave it nothing to hide behind.)
+    MVSIM_TRY(dev_psf_normalize(ctx, psf, elems(p->kdims)));                                   // :255
     int planes = 0;
-    ctx->psf_on_side = overlap;
-    const int conv_st = conv_device(ctx, b.f(), p->dims, psf, p->kdims, a.f(), ctx->d_scalars + 1, p->inc, &planes);   // :580
-    ctx->psf_on_side = false;
-    MVSIM_TRY(conv_st);
+    MVSIM_TRY(conv_device(ctx, b.f(), p->dims, psf, p->kdims, a.f(), ctx->d_scalars + 1, p->inc, &planes));   // :580
     {
         StageTimer t(ctx, MVSIM_T_ADJUST);                                                     // :582, applied inside the sampler
         MVSIM_TRY(k_adjust_corr(ctx, ctx->d_scalars + 1, n, p->min_value, p->target_avg, ctx->d_scalars + 2));
@@ -455,9 +428,6 @@ static int ctx_create(int device, bool own, void* cuda_stream, mvsim_ctx** out)
     ctx->stream = nullptr;
     ctx->own_stream = false;
     ctx->copy_stream = nullptr;
-    ctx->side_stream = nullptr;
-    ctx->ev_fork = ctx->ev_join = nullptr;
-    ctx->psf_on_side = false;
     ctx->mempool = nullptr;
     ctx->d_scalars = nullptr;
     ctx->launches = 0;
@@ -525,7 +495,6 @@ int mvsim_ctx_destroy(mvsim_ctx* ctx)
     for (auto& ev : ctx->pool) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
     cudaFree(ctx->d_scalars);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
-    if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join); }
     if (ctx->mempool) cudaMemPoolDestroy(ctx->mempool);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

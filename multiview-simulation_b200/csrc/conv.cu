@@ -308,10 +308,9 @@ int conv_device(mvsim_ctx* ctx, const float* img, const int64_t dims[3], const f
         StageTimer t(ctx, MVSIM_T_PSF);
         MVSIM_TRY(psf_cache_lookup(ctx, psf, pl, lanes, (size_t)pl.p2_elems(lanes, g.tiles_own), &cached, &psf_hit));
     }
-    const bool side = ctx->psf_on_side && !cached && !psf_hit;      // whole-view call, cache off: the PSF chain lives on the side stream
     if (cached) ws.p2 = cached;
-    else if (!side) MVSIM_TRY(buf.get(&ws.p2, (size_t)pl.p2_elems(lanes, g.tiles_own)));
-    if (!psf_hit && !side) MVSIM_TRY(buf.get(&ws.p1, (size_t)pl.p1_elems()));
+    else MVSIM_TRY(buf.get(&ws.p2, (size_t)pl.p2_elems(lanes, g.tiles_own)));
+    if (!psf_hit) MVSIM_TRY(buf.get(&ws.p1, (size_t)pl.p1_elems()));
     ws.tw_x = tx.tw; ws.twist_x = tx.twist; ws.tw_y = ty.tw; ws.tw_z = tz.tw;
 
     CudaLauncher l = { ctx, true, lanes };
@@ -320,35 +319,9 @@ int conv_device(mvsim_ctx* ctx, const float* img, const int64_t dims[3], const f
     if (out_planes) *out_planes = planes;
     const int nblocks = CudaLauncher::x_blocks(pl.sx, pl.dims[1] * planes, true);      // per-block sums of the inverse x pass
     if (d_sum) MVSIM_TRY(buf.get(&partials, (size_t)nblocks));
-    if (side) {
-        // the PSF's x and y transforms follow its normalisation on the side stream (forked from the main stream by the caller) and
-        // run under rotate_attenuate and the image's forward passes; the fused z pass is the first consumer and waits for them.
-        // Their workspaces are allocated in side-stream order (a main-stream allocation would order them behind rotate_attenuate).
-        int st;
-        {
-            StreamSwap sw(ctx, ctx->side_stream);
-            st = buf.get(&ws.p2, (size_t)pl.p2_elems(lanes, g.tiles_own));
-            if (st == MVSIM_OK) st = buf.get(&ws.p1, (size_t)pl.p1_elems());
-            if (st == MVSIM_OK) st = conv_psf_spectrum(l, pl, g, ws, psf);
-        }
-        cudaError_t e = cudaEventRecord(ctx->ev_join, ctx->side_stream);
-        l.psf_phase = false;
-        if (st == MVSIM_OK && e == cudaSuccess) st = conv_forward_x(l, pl, g, ws, img);
-        for (int b = 0; b < pl.y_blocks && st == MVSIM_OK && e == cudaSuccess; ++b) {
-            st = conv_forward_y(l, pl, g, ws, b);
-            if (b == 0 && st == MVSIM_OK) e = cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
-            if (st == MVSIM_OK && e == cudaSuccess) st = conv_middle_z(l, pl, g, ws, ws.u2, keep_inc);
-            if (st == MVSIM_OK && e == cudaSuccess) st = conv_inverse_y(l, pl, g, ws, b, planes);
-        }
-        cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);      // (again, for the error paths: nothing is freed under the side stream)
-        if (e != cudaSuccess) return cuda_fail(ctx, e, "PSF side stream");
-        MVSIM_TRY(st);
-        MVSIM_TRY(conv_inverse_x(l, pl, ws, out, partials, planes));
-    } else {
-        if (!psf_hit) MVSIM_TRY(conv_psf_spectrum(l, pl, g, ws, psf));
-        l.psf_phase = false;
-        MVSIM_TRY(conv_apply(l, pl, g, ws, img, out, partials, keep_inc));
-    }
+    if (!psf_hit) MVSIM_TRY(conv_psf_spectrum(l, pl, g, ws, psf));
+    l.psf_phase = false;
+    MVSIM_TRY(conv_apply(l, pl, g, ws, img, out, partials, keep_inc));
     if (d_sum) {
         StageTimer t(ctx, MVSIM_T_ADJUST);
         MVSIM_TRY(k_sum_partials(ctx, partials, (size_t)nblocks, d_sum));

@@ -25,11 +25,6 @@ struct mvsim_ctx {
     cudaStream_t stream;
     bool own_stream;
     cudaStream_t copy_stream;                // lazily created: result downloads overlapping the next view
-    // whole-view call: the PSF chain (normalise, x and y transforms: a few small kernels, 0.26 ms at config 3) is enqueued on a side
-    // stream so that it runs under rotate_attenuate and the image's forward passes; the fused z pass waits for it
-    cudaStream_t side_stream;                // lazily created
-    cudaEvent_t ev_fork, ev_join;
-    bool psf_on_side;                        // set by the whole-view call around conv_device
     cudaMemPool_t mempool;                   // this context's own stream-ordered pool: workspaces are never traded between
                                              // the streams of two contexts (callers run contexts concurrently)
     std::string err;
@@ -84,14 +79,6 @@ struct StageTimer {
     StageTimer(mvsim_ctx* c, int stage);
     ~StageTimer();
 };
-
-// RAII: work enqueued inside the scope goes to `s` instead of the context's stream (kernels, stage timers, pool allocations)
-struct StreamSwap {
-    mvsim_ctx* ctx; cudaStream_t saved;
-    StreamSwap(mvsim_ctx* c, cudaStream_t s) : ctx(c), saved(c->stream) { c->stream = s; }
-    ~StreamSwap() { ctx->stream = saved; }
-};
-int side_fork(mvsim_ctx* ctx);      // creates the side stream on first use; the side stream waits for everything enqueued on the main one
 
 int dev_alloc(mvsim_ctx* ctx, void** p, size_t bytes);      // stream-ordered (cudaMallocAsync)
 void dev_free(mvsim_ctx* ctx, void* p);
