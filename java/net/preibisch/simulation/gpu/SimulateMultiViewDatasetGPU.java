@@ -66,6 +66,21 @@ public class SimulateMultiViewDatasetGPU
 
 	static long ctx() { return CTX.get(); }
 
+	/**
+	 * Keeps the FFT spectra of repeated PSFs of the calling thread's context in up to maxBytes of GPU memory (0 = off, like the
+	 * reference, which rebuilds the kernel FFT in every convolve, S/SimulateMultiViewDataset.java:257).  Results are unchanged.
+	 */
+	public static void setPsfCache( final long maxBytes )
+	{
+		check( Mvsim.psfCacheConfigure( ctx(), maxBytes ) );
+	}
+
+	/** simulateViews only: Poisson counts travel from the GPU as uint16 and are widened to the FloatType images on host threads */
+	public static void setCountTransport( final boolean uint16 )
+	{
+		check( Mvsim.ctxSetOption( ctx(), Mvsim.OPT_COUNT_TRANSPORT, uint16 ? 1 : 0 ) );
+	}
+
 	/** releases the calling thread's context (device workspaces, stream); the next call creates a new one */
 	public static void closeThreadContext()
 	{

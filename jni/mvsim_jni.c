@@ -116,6 +116,32 @@ MVSIM_JNI(jint, convPaddedDims)(JNIEnv* env, jclass c, jlongArray dims, jlongArr
     return st;
 }
 
+MVSIM_JNI(jint, ctxSetOption)(JNIEnv* env, jclass c, jlong ctx, jint option, jlong value)
+{
+    (void)env; (void)c;
+    return mvsim_ctx_set_option(ctx_of(ctx), option, (int64_t)value);
+}
+
+MVSIM_JNI(jint, psfCacheConfigure)(JNIEnv* env, jclass c, jlong ctx, jlong max_bytes)
+{
+    (void)env; (void)c;
+    if (max_bytes < 0) return MVSIM_EINVAL;
+    return mvsim_psf_cache_configure(ctx_of(ctx), (size_t)max_bytes);
+}
+
+MVSIM_JNI(jint, psfCacheStats)(JNIEnv* env, jclass c, jlong ctx, jlongArray stats4)
+{
+    (void)c;
+    if (!stats4 || (*env)->GetArrayLength(env, stats4) < 4) return MVSIM_EINVAL;
+    int64_t st[4];
+    const int rc = mvsim_psf_cache_stats(ctx_of(ctx), st);
+    if (rc == MVSIM_OK) {
+        const jlong out[4] = { (jlong)st[0], (jlong)st[1], (jlong)st[2], (jlong)st[3] };
+        (*env)->SetLongArrayRegion(env, stats4, 0, 4, out);
+    }
+    return rc;
+}
+
 /* ---- stage entry points -------------------------------------------------------------------------------------------- */
 MVSIM_JNI(jint, axisRotation)(JNIEnv* env, jclass c, jlongArray dims, jint axis, jint degrees, jdoubleArray fwd12, jdoubleArray inv12)
 {
