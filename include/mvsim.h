@@ -84,7 +84,11 @@ enum {
      * the float32 transport; a view with a count above 65535 is fetched as float32 instead.  0 (default): float32. */
     MVSIM_OPT_COUNT_TRANSPORT = 1,
     /* host threads that widen (0 = default: 4) */
-    MVSIM_OPT_HOST_THREADS = 2
+    MVSIM_OPT_HOST_THREADS = 2,
+    /* fused z pass of the whole-view calls: 0 (default) = the kernel measured fastest for the shape, 1 = decimated inverse where the
+     * split allows it, else full spectral (no polyphase kernel), 2 = full spectral kernel only, 3 = polyphase kernel where the shape
+     * allows it.  The variants agree to float32 rounding; the option exists for A/B measurements and cross-checks. */
+    MVSIM_OPT_Z_KERNEL = 3
 };
 int mvsim_ctx_set_option(mvsim_ctx* ctx, int option, int64_t value);
 

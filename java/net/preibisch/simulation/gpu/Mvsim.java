@@ -40,9 +40,10 @@ final class Mvsim
 	static native ByteBuffer allocPinned( long bytes );             // NewDirectByteBuffer over mvsim_alloc_pinned; null on failure
 	static native void freePinned( Buffer buffer );                 // mvsim_free_pinned; any view of an allocPinned buffer that starts at its base
 	static native int convPaddedDims( long[] dims, long[] kdims, long[] nfftOut ); // mvsim_conv_padded_dims
-	/** mvsim_ctx_set_option: OPT_COUNT_TRANSPORT (1: Poisson counts cross the host link as uint16), OPT_HOST_THREADS */
+	/** mvsim_ctx_set_option: OPT_COUNT_TRANSPORT (1: Poisson counts cross the host link as uint16), OPT_HOST_THREADS,
+	 * OPT_Z_KERNEL (fused z kernel: 0 auto, 1 decimated inverse, 2 full spectral, 3 polyphase: A/B runs) */
 	static native int ctxSetOption( long ctx, int option, long value );
-	static final int OPT_COUNT_TRANSPORT = 1, OPT_HOST_THREADS = 2;
+	static final int OPT_COUNT_TRANSPORT = 1, OPT_HOST_THREADS = 2, OPT_Z_KERNEL = 3;
 	/** mvsim_psf_cache_configure: keep the spectra of repeated PSFs in up to maxBytes of HBM (0 = off, the reference's behaviour) */
 	static native int psfCacheConfigure( long ctx, long maxBytes );
 	/** mvsim_psf_cache_stats: { hits, misses, entries, bytes held } */

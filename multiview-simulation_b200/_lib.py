@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("MVSIM_LIB") or os.path.join(_PKG, "libmvsim.so")
 MVSIM_OK, MVSIM_EINVAL, MVSIM_ENOMEM, MVSIM_ECUDA, MVSIM_ENCCL, MVSIM_EUNSUPPORTED = range(6)
 STAGE_NAMES = ["h2d", "rotate", "attenuate", "psf", "fft_xfwd", "fft_yfwd", "fft_zfused", "fft_yinv", "fft_xinv",
                "adjust", "sample", "d2h", "widen"]
-OPT_COUNT_TRANSPORT, OPT_HOST_THREADS = 1, 2
+OPT_COUNT_TRANSPORT, OPT_HOST_THREADS, OPT_Z_KERNEL = 1, 2, 3
 NSTAGES = len(STAGE_NAMES)
 
 

@@ -100,6 +100,12 @@ class Context:
         check(self._lib.mvsim_ctx_set_option(self.h, _lib.OPT_COUNT_TRANSPORT, int(bool(uint16))), self.h)
         return self
 
+    def z_kernel(self, which=0):
+        """Fused z pass of the whole-view calls (mvsim_ctx_set_option MVSIM_OPT_Z_KERNEL): 0 = the kernel measured fastest for the
+        shape, 1 = decimated inverse / full spectral (no polyphase kernel), 2 = full spectral kernel only, 3 = polyphase kernel."""
+        check(self._lib.mvsim_ctx_set_option(self.h, _lib.OPT_Z_KERNEL, int(which)), self.h)
+        return self
+
     def psf_cache(self, max_bytes):
         """PSF-spectrum cache of this context (mvsim_psf_cache_configure): keep the spectra of repeated PSFs in up to
         `max_bytes` of HBM (0 = off, the library default: the reference rebuilds the kernel FFT per call, :257)."""

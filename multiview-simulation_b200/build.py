@@ -26,7 +26,8 @@ FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", CSRC, "-
 UNITS = [("stages", "stages.cu", []), ("phantom", "phantom.cu", []), ("conv", "conv.cu", []), ("capi", "capi.cu", [])] + \
         [(f"fft_g{g}_t{t}", os.path.join("fft", "fft_group.cu"), [f"-DMVSIM_GROUP={g}", f"-DMVSIM_LANES={t}"])
          for g in (4, 3, 2, 1, 0) for t in (8,)] + \
-        [(f"fft_dec_g{g}_t8", os.path.join("fft", "fft_group.cu"), [f"-DMVSIM_GROUP={g}", "-DMVSIM_LANES=8", "-DMVSIM_DEC_UNIT=1"]) for g in (2, 1)]
+        [(f"fft_dec_g{g}_t8", os.path.join("fft", "fft_group.cu"), [f"-DMVSIM_GROUP={g}", "-DMVSIM_LANES=8", "-DMVSIM_DEC_UNIT=1"]) for g in (2, 1)] + \
+        [(f"fft_poly_g{g}_t8", os.path.join("fft", "fft_group.cu"), [f"-DMVSIM_GROUP={g}", "-DMVSIM_LANES=8", "-DMVSIM_POLY_UNIT=1"]) for g in (2, 1)]
 
 
 def _nvcc():

@@ -437,6 +437,7 @@ static int ctx_create(int device, bool own, void* cuda_stream, mvsim_ctx** out)
     ctx->h_hash = nullptr;
     ctx->count_transport = 0;
     ctx->host_threads = 0;
+    ctx->z_kernel = 0;
     ctx->widen_pool = nullptr;
     ctx->profiling = false;
     memset(ctx->acc_ms, 0, sizeof(ctx->acc_ms));
@@ -565,6 +566,10 @@ int mvsim_ctx_set_option(mvsim_ctx* ctx, int option, int64_t value)
         if (value < 0 || value > 256) return set_error(ctx, MVSIM_EINVAL, "host threads: 0 (default) .. 256");
         if (ctx->widen_pool) { delete static_cast<mvsim::WidenPool*>(ctx->widen_pool); ctx->widen_pool = nullptr; }
         ctx->host_threads = (int)value;
+        return MVSIM_OK;
+    case MVSIM_OPT_Z_KERNEL:
+        if (value < 0 || value > 3) return set_error(ctx, MVSIM_EINVAL, "z kernel: 0 (auto), 1 (no polyphase), 2 (full spectral), 3 (polyphase)");
+        ctx->z_kernel = (int)value;
         return MVSIM_OK;
     }
     return set_error(ctx, MVSIM_EINVAL, "unknown option %d", option);

@@ -113,6 +113,9 @@ static int get_dec_table(mvsim_ctx* ctx, int n, int crop0, int n_src, int inc, c
     return MVSIM_OK;
 }
 
+// does MVSIM_OPT_Z_KERNEL = 0 (auto) pick the polyphase kernel where it applies?  Measured on B200 at config 3 (profiles/r02_notes.md)
+constexpr bool kPolyphaseDefault = false;
+
 struct CudaLauncher {
     mvsim_ctx* ctx;
     bool psf_phase;
@@ -172,7 +175,7 @@ struct CudaLauncher {
     bool z_decimate(const FftSize& s) const
     {
         static const bool on = MVSIM_PACKED_FFT != 0 && env_int("MVSIM_Z_DECIMATE", 1) != 0;
-        return on && s.n >= kDecMinLine && s.n <= kDecMaxLine;
+        return on && ctx->z_kernel != 2 && s.n >= kDecMinLine && s.n <= kDecMaxLine;
     }
     int launch_zfused_dec(const FftSize& s, const ZFusedParams& q0, int n_tiles, int n_outer, int inc)
     {
@@ -187,6 +190,27 @@ struct CudaLauncher {
         q.prefetch_dist = (q.use_tma && zdist > 0 && make_h_tensor_map(q.u, lanes, n_tiles, q.zg, n_outer, q.u_tmap)) ? zdist : 0;
         return finish(fft_launch(inc == 3 ? FFT_ZFUSED_DEC3 : FFT_ZFUSED_DEC5, lanes, s.n, &q, (unsigned)n_outer, (unsigned)n_tiles, ctx->stream),
                       "fused z pass (decimated inverse)");
+    }
+    // Polyphase form of the whole-view fused z pass (ZFusedPoly in fft/zfused_poly.cuh).
+    bool z_polyphase(const FftSize& s, int inc, int k_src) const
+    {
+        // (auto = the measured winner at BASELINE config 3, see kPolyphaseDefault; MVSIM_Z_POLY=0/1 overrides it for A/B runs)
+        static const bool dflt = MVSIM_PACKED_FFT != 0 && env_int("MVSIM_Z_POLY", kPolyphaseDefault ? 1 : 0) != 0;
+        const bool want = ctx->z_kernel == 3 || (ctx->z_kernel == 0 && dflt);
+        if (!want || MVSIM_PACKED_FFT == 0 || s.n < kDecMinLine || s.n > kDecMaxLine) return false;
+        return zfused_poly_fits(s.n, inc, lanes, k_src);
+    }
+    int launch_zfused_poly(const FftSize& s, const ZFusedParams& q0, int n_tiles, int n_outer, int inc)
+    {
+        ZFusedParams q = q0;
+        if (!make_h_tensor_map(q.p2, lanes, n_tiles, q.k_src, n_outer, q.h_tmap)) return -2;      // the kernel needs the TMA-fed PSF tile
+        q.use_tma = 1;
+        StageTimer t(ctx, MVSIM_T_FFT_ZFUSED);
+        static const int zdist2 = prefetch_dist(2);
+        q.grid_x = n_outer; q.grid_y = n_tiles;
+        q.prefetch_dist = (q.use_tma && zdist2 > 0 && make_h_tensor_map(q.u, lanes, n_tiles, q.zg, n_outer, q.u_tmap)) ? zdist2 : 0;
+        return finish(fft_launch(inc == 3 ? FFT_ZFUSED_POLY3 : FFT_ZFUSED_POLY5, lanes, s.n, &q, (unsigned)n_outer, (unsigned)n_tiles, ctx->stream),
+                      "fused z pass (polyphase)");
     }
     int launch_zfused(const FftSize& s, const ZFusedParams& q0, int n_tiles, int n_outer)
     {

@@ -44,6 +44,7 @@ struct mvsim_ctx {
     // the float32 of the reference's API by host threads inside the call
     int count_transport;                     // 0 = float32 (default), 1 = uint16 when snr >= 0
     int host_threads;                        // widening threads (0 = default)
+    int z_kernel;                            // MVSIM_OPT_Z_KERNEL: 0 auto, 1 no polyphase kernel, 2 full spectral kernel only
     struct Staging { void* p; size_t bytes; };
     std::vector<Staging> staging;            // pinned uint16 staging buffers, kept across calls
     void* widen_pool;                        // mvsim::WidenPool*, lazily created

@@ -143,6 +143,13 @@ template <class L> int conv_middle_z(L& l, const ConvPlan& pl, const SlabGeom& g
         zp.n_peers = ws.n_peers;
         for (int r = 0; r < ws.n_peers; ++r) zp.out_peers[r] = ws.peers_y[r];
     }
+    // polyphase form (ZFusedPoly): inc phases of sz.n / inc points, sum plane from the time domain.  Needs a mirror extension that
+    // reaches every padded index and an image line at least as long as the PSF line (the launcher may veto: line length, A/B knob)
+    if (pruned && l.h_on_the_fly && zp.estride32 != 0 && zp.ext == EXT_MIRROR1 && zfused_poly_ok(pl.sz.n, keep_inc) && pl.dims[2] >= pl.kdims[2] &&
+        l.z_polyphase(pl.sz, keep_inc, pl.kdims[2])) {
+        const int perr = l.launch_zfused_poly(pl.sz, zp, g.tiles_own, pl.sy.n, keep_inc);
+        if (perr != -2) return perr;        // -2: the launcher could not set the kernel up (no TMA descriptor): spectral kernels below
+    }
     // decimated inverse when the kept planes are whole columns of the exchange (the launcher may veto: line length, A/B knob)
     if (pruned && l.h_on_the_fly && zp.estride32 != 0 && zfused_dec_ok(pl.sz.a, pl.sz.b, keep_inc) && l.z_decimate(pl.sz))
         return l.launch_zfused_dec(pl.sz, zp, g.tiles_own, pl.sy.n, keep_inc);

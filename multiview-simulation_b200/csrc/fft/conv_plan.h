@@ -49,6 +49,15 @@ constexpr int x_rows_per_block(int a, int b, bool inverse) { return x_rows_for(i
     MVSIM_FFT_SIZES_SMALL(X) MVSIM_FFT_SIZES_G1(X) MVSIM_FFT_SIZES_G2(X) MVSIM_FFT_SIZES_G3(X) MVSIM_FFT_SIZES_G4(X)
 #endif
 
+// compile-time lookup in the FULL table (also under MVSIM_EMU_SMALL_ONLY): {0, 0, 0} when n is not a supported size
+constexpr FftSize fft_size_lookup(int n)
+{
+#define MVSIM_X(n_, a_, b_) if (n == n_) return FftSize{ n_, a_, b_ };
+    MVSIM_FFT_SIZES_SMALL(MVSIM_X) MVSIM_FFT_SIZES_G1(MVSIM_X) MVSIM_FFT_SIZES_G2(MVSIM_X) MVSIM_FFT_SIZES_G3(MVSIM_X) MVSIM_FFT_SIZES_G4(MVSIM_X)
+#undef MVSIM_X
+    return FftSize{ 0, 0, 0 };
+}
+
 inline const FftSize* fft_size_table(int* count)
 {
 #define MVSIM_X(n, a, b) { n, a, b },

@@ -16,7 +16,11 @@ template <class K> constexpr int min_blocks()
     return K::IS_X ? (K::THREADS <= 160 ? 4 : (K::THREADS <= 256 ? 3 : 1)) : (K::THREADS <= 160 ? 4 : (K::THREADS <= 288 ? 2 : 1));
 }
 
-template <class K> __global__ void __launch_bounds__(K::THREADS, min_blocks<K>()) fft_kernel(const __grid_constant__ typename K::Params q)
+// a kernel may state its own residency target (K::MIN_BLOCKS)
+template <class K, class = void> struct MinBlocksOf { static constexpr int value = min_blocks<K>(); };
+template <class K> struct MinBlocksOf<K, std::void_t<decltype(K::MIN_BLOCKS)>> { static constexpr int value = K::MIN_BLOCKS; };
+
+template <class K> __global__ void __launch_bounds__(K::THREADS, MinBlocksOf<K>::value) fft_kernel(const __grid_constant__ typename K::Params q)
 {
     extern __shared__ __align__(128) unsigned char smraw[];
     float2* sm = reinterpret_cast<float2*>(smraw);
@@ -57,13 +61,26 @@ template <class K> static int launch(const void* params, unsigned gx, unsigned g
 #ifndef MVSIM_DEC_UNIT
 #define MVSIM_DEC_UNIT 0
 #endif
+#ifndef MVSIM_POLY_UNIT
+#define MVSIM_POLY_UNIT 0
+#endif
 
 template <int A, int B> static int launch_size(int kind, const void* params, unsigned gx, unsigned gy, cudaStream_t s)
 {
     constexpr int RF = x_rows_per_block(A, B, false), RI = x_rows_per_block(A, B, true);
     constexpr int T = MVSIM_LANES;
     (void)RF; (void)RI;
-#if MVSIM_DEC_UNIT
+#if MVSIM_POLY_UNIT
+    constexpr bool built = A * B >= kDecMinLine && A * B <= kDecMaxLine;
+    switch (kind) {
+    case FFT_ZFUSED_POLY3:
+        if constexpr (built && zfused_poly_ok(A * B, 3)) return launch<ZFusedPoly<A * B, 3, T>>(params, gx, gy, s);
+        break;
+    case FFT_ZFUSED_POLY5:
+        if constexpr (built && zfused_poly_ok(A * B, 5)) return launch<ZFusedPoly<A * B, 5, T>>(params, gx, gy, s);
+        break;
+    }
+#elif MVSIM_DEC_UNIT
     // the decimated fused z kernels live in their own translation units (build time)
     constexpr bool built = A * B >= kDecMinLine && A * B <= kDecMaxLine;
     switch (kind) {
@@ -104,7 +121,9 @@ template <int A, int B> static int launch_size(int kind, const void* params, uns
 #define MVSIM_GROUP_SIZES(X) MVSIM_FFT_SIZES_G4(X)
 #endif
 
-#if MVSIM_DEC_UNIT
+#if MVSIM_POLY_UNIT
+#define MVSIM_FN MVSIM_CAT(MVSIM_CAT(MVSIM_CAT(fft_launch_poly_g, MVSIM_GROUP), _t), MVSIM_LANES)
+#elif MVSIM_DEC_UNIT
 #define MVSIM_FN MVSIM_CAT(MVSIM_CAT(MVSIM_CAT(fft_launch_dec_g, MVSIM_GROUP), _t), MVSIM_LANES)
 #else
 #define MVSIM_FN MVSIM_CAT(MVSIM_CAT(MVSIM_CAT(fft_launch_g, MVSIM_GROUP), _t), MVSIM_LANES)

@@ -8,7 +8,8 @@
 namespace mvsim {
 
 enum FftKind { FFT_XFWD = 0, FFT_XINV = 1, FFT_SFWD = 2, FFT_SINV = 3, FFT_ZFUSED = 4, FFT_ZFUSED_OTF = 5,
-               FFT_ZFUSED_DEC3 = 6, FFT_ZFUSED_DEC5 = 7 };   // decimated inverse (ZFusedDec): the planner's (a, b) with 3 | a resp. 5 | a
+               FFT_ZFUSED_DEC3 = 6, FFT_ZFUSED_DEC5 = 7,     // decimated inverse (ZFusedDec): the planner's (a, b) with 3 | a resp. 5 | a
+               FFT_ZFUSED_POLY3 = 8, FFT_ZFUSED_POLY5 = 9 }; // polyphase form (ZFusedPoly): 3 resp. 5 phases of n / inc points
 
 // the decimated fused z kernels are built only for z lines of these lengths (build time): covers the BASELINE
 // configs (339 -> 360 with inc 3, 639 -> 640 with inc 5)
@@ -24,10 +25,18 @@ MVSIM_DECL(0, 8) MVSIM_DECL(1, 8) MVSIM_DECL(2, 8) MVSIM_DECL(3, 8) MVSIM_DECL(4
 // decimated fused z kernels (kinds FFT_ZFUSED_DEC*): line lengths kDecMinLine..kDecMaxLine live in groups 1 and 2
 int fft_launch_dec_g1_t8(int kind, int n, const void* params, unsigned gx, unsigned gy, cudaStream_t s);
 int fft_launch_dec_g2_t8(int kind, int n, const void* params, unsigned gx, unsigned gy, cudaStream_t s);
+// polyphase fused z kernels (kinds FFT_ZFUSED_POLY*), same line lengths, their own translation units
+int fft_launch_poly_g1_t8(int kind, int n, const void* params, unsigned gx, unsigned gy, cudaStream_t s);
+int fft_launch_poly_g2_t8(int kind, int n, const void* params, unsigned gx, unsigned gy, cudaStream_t s);
 
 inline int fft_launch(int kind, int lanes, int n, const void* params, unsigned gx, unsigned gy, cudaStream_t s)
 {
     (void)lanes;
+    if (kind >= FFT_ZFUSED_POLY3) {
+        int d = fft_launch_poly_g1_t8(kind, n, params, gx, gy, s);
+        if (d == -1) d = fft_launch_poly_g2_t8(kind, n, params, gx, gy, s);
+        return d;
+    }
     if (kind >= FFT_ZFUSED_DEC3) {
         int d = fft_launch_dec_g1_t8(kind, n, params, gx, gy, s);
         if (d == -1) d = fft_launch_dec_g2_t8(kind, n, params, gx, gy, s);

@@ -1153,3 +1153,5 @@ template <int A_, int B_, int R_> struct XInv : LineShape<A_, B_> {
 };
 
 }  // namespace mvsim
+
+#include "zfused_poly.cuh"         // ZFusedPoly: the whole-view fused z pass in polyphase form

@@ -1,0 +1,372 @@
+// Fused z pass of the whole-view call in POLYPHASE form (included at the end of line_fft.cuh).
+//
+// extractSlices keeps the planes z = 0, INC, 2 INC, ... of the convolved volume (S/SimulateMultiViewDataset.java:206) and
+// adjustImage (S/Tools.java:143-147) needs, of all the other planes, only their sum.  With the padded z line length N = INC * M
+// the kept outputs of the cyclic convolution c = a' (*) b  (a' = mirror-extended image line, b = zero-extended PSF line) are
+//
+//     c[crop0 + INC k] = sum_s ( beta_s (*)_M alpha_s )[k],     alpha_s[m] = a'[(crop0 - s + INC m) mod N],  beta_s[q] = b[INC q + s],
+//
+// i.e. INC cyclic convolutions of length M = N / INC.  So the pass runs INC M-point forward transforms of the image phases, INC
+// (heavily pruned: ceil(KZ / INC) of M samples are non-zero) M-point transforms of the PSF phases, INC M multiply-adds, a sum over
+// the phases and ONE M-point inverse -- no radix-INC combine stage on either forward side and a fifth (third) of an inverse,
+// against three N-point transforms of the spectral kernels (ZFusedOTF) or two and a pruned one (ZFusedDec).
+//
+// The plane with the sum of the DROPPED slices comes from the time domain: with Bpre[i] = sum_{j < i} b[j], B0 = Bpre[KZ],
+//
+//     sum_{o < n_src} c[crop0 + o] = B0 * sum_{n < n_src} a'[n] + sum_{i = 1}^{KZ-1} Bpre[i] (a'[n_src + KZ-1 - i] - a'[KZ-1 - i])
+//
+// (each a'[n] is weighted by the part of the PSF line whose taps land inside the cropped range), and
+// sum_{n < n_src} a'[n] = sum_s DFT(alpha_s)[0] - sum_{n >= n_src} a'[n].  The 2 (KZ - 1) border samples are loaded a second time
+// (L1 / L2 hits: the same CTA gathers them in the same phase): group A + c owns the taps j = 4 c .. 4 c + 3, keeps their differences
+// DD[j] in registers, and in the next phase (PSF tile present) forms its local share L_c = sum_u (b[4c] + .. + b[4c+u-1]) DD[4c+u]
+// and its chunk sums CS_c = sum b, DS_c = sum DD.  What is left, sum_c (CS_0 + .. + CS_{c-1}) DS_c + L_c, is a scan over the NCH
+// chunks, run by ONE warp beside the two warps of the first inverse half.
+//
+// Work items of a CTA (T neighbouring kx columns of one ky; G = THREADS / T groups, group g works on `lane` = tid % T):
+//   level 1 : (phase s, n2 < B): A-point transform over n1 of alpha_s[n1 B + n2]      -> INC B items, R1 rounds over the G groups
+//   level 2 : (phase s, k1 < A): B-point transform                                     -> INC A items <= G, one per group
+// so every warp works in the four transform phases; only the single inverse runs on A, then B groups.
+// Phases: image level 1, border differences | image level 2 (spectrum stays in registers), PSF level 1, chunk terms |
+//         PSF level 2, multiply | sum over the phases | inverse level 1, chunk scan | inverse level 2 + stores | sum plane.
+#pragma once
+
+namespace mvsim {
+
+// groups per CTA for the split M = a * b (a <= b) with inc phases
+constexpr int poly_groups(int a, int b, int inc)
+{
+    const int l1 = inc * b, l2 = inc * a;
+    if (l1 <= 48) return l1;
+    const int half = (l1 + 1) / 2;
+    return l2 > half ? l2 : half;
+}
+constexpr int kPolyTaps = 4;        // PSF taps per border group (their differences live in registers)
+// may a z line of n points run ZFusedPoly<n, inc, T>?  (inc phases of a supported length n / inc, enough groups for the border terms)
+constexpr bool zfused_poly_ok(int n, int inc)
+{
+    if (!(inc == 3 || inc == 5) || n % inc != 0) return false;
+    const FftSize s = fft_size_lookup(n / inc);
+    if (s.n < 64 || s.a > s.b) return false;
+    const int g = poly_groups(s.a, s.b, inc);
+    return g >= inc * s.a && g >= s.b && g - s.a >= 8 && g * 8 <= 512;
+}
+// PSF taps the border groups of a launch can take
+constexpr int zfused_poly_max_taps(int n, int inc)
+{
+    const FftSize s = fft_size_lookup(n / inc);
+    return kPolyTaps * (poly_groups(s.a, s.b, inc) - s.a);
+}
+
+// shared memory without the PSF tile (the host needs it without the template)
+constexpr int poly_smem_base(int a, int b, int inc, int t)
+{
+    const int g = poly_groups(a, b, inc), aux_rows = 4 * (g - a) + inc + 8 + b + 1;
+    return ((2 * inc * a * (b | 1) * t + aux_rows * t + 15) / 16 * 16 + 16) * (int)sizeof(float2);
+}
+constexpr int poly_psf_tile_bytes(int k_src, int t) { return (k_src + kTmaBoxRows - 1) / kTmaBoxRows * kTmaBoxRows * t * (int)sizeof(float2); }
+constexpr int kPolySmemMax = (kSmemLimit - 2048) / 2;      // two CTAs per SM (1 KB reserved per CTA)
+// the PSF tile (TMA) fits beside the exchange areas without costing the second resident CTA, and the border groups cover the taps
+inline bool zfused_poly_fits(int n, int inc, int t, int k_src)
+{
+    const FftSize m = fft_size_lookup(n / inc);
+    return k_src <= zfused_poly_max_taps(n, inc) && poly_smem_base(m.a, m.b, inc, t) + poly_psf_tile_bytes(k_src, t) <= kPolySmemMax;
+}
+
+template <int B> struct PolyState { float2 y[B]; float2 dd[kPolyTaps]; };
+
+template <int N_, int INC_, int T_> struct ZFusedPoly {
+    static constexpr bool IS_X = false;
+    static constexpr int N = N_, INC = INC_, T = T_, M = N_ / INC_;
+    static constexpr FftSize SZ = fft_size_lookup(M);
+    static constexpr int A = SZ.a, B = SZ.b, BP = B | 1;
+    static constexpr int L1 = INC * B, L2 = INC * A;
+    static constexpr int G = poly_groups(A, B, INC);
+    static constexpr int R1 = (L1 + G - 1) / G;           // level-1 items per group
+    static constexpr int THREADS = G * T;
+    static constexpr int MIN_BLOCKS = 2;
+    static constexpr int NCH = G - A;                     // border groups: A .. G-1 (they idle during the first inverse half)
+    static constexpr int NSC = 4, QSC = (NCH + NSC - 1) / NSC;      // the chunk scan runs on NSC groups (one warp at T = 8)
+    static_assert(N_ % INC_ == 0 && A * B == M && G >= L2 && G >= B && NCH >= NSC, "unsupported split");
+    // shared memory (float2 elements): [E1: INC x (A x BP) x T][E2: the same][AUX rows of T][mbarrier][PSF tile (TMA)]
+    static constexpr int E_ELEMS = INC * A * BP * T;
+    static constexpr int AUX_CS = 0, AUX_DS = NCH, AUX_L = 2 * NCH, AUX_TS = 3 * NCH, AUX_TOT = 4 * NCH, AUX_SC = AUX_TOT + INC,
+                         AUX_KEPT = AUX_SC + 2 * NSC, AUX_B0 = AUX_KEPT + B, AUX_ROWS = AUX_B0 + 1;
+    static constexpr int AUX0 = 2 * E_ELEMS;
+    static constexpr int BAR_ELEMS = (AUX0 + AUX_ROWS * T + 15) / 16 * 16;
+    static constexpr int PSF_ELEMS0 = BAR_ELEMS + 16;
+    static constexpr int SMEM_BYTES = PSF_ELEMS0 * (int)sizeof(float2);       // without the PSF tile
+    static constexpr int NPH = 7;
+    using Params = ZFusedParams;
+    using State = PolyState<B>;
+    static_assert(SMEM_BYTES == poly_smem_base(A, B, INC_, T_), "host-side shared memory formula out of sync");
+    static int smem_bytes(const Params& q) { return SMEM_BYTES + (q.use_tma ? poly_psf_tile_bytes(q.k_src, T) : 0); }
+    static int smem_bytes_max() { return kPolySmemMax > SMEM_BYTES ? kPolySmemMax : SMEM_BYTES; }
+
+    // PSF sample j of this thread's column: TMA-fetched tile in shared memory (rows beyond KZ are zero filled by the unit); global in
+    // the CPU emulation
+    static MVSIM_HD float2 psf_at(const Params& q, const float2* sm, const float2* __restrict__ gsrc, int lane, int j)
+    {
+#ifdef __CUDA_ARCH__
+        // on the device the kernel is only launched with the TMA-fed tile (the host falls back to the spectral kernels otherwise)
+        (void)gsrc;
+        const int rows = (q.k_src + kTmaBoxRows - 1) / kTmaBoxRows * kTmaBoxRows;
+        return j < rows ? sm[PSF_ELEMS0 + j * T + lane] : make_float2(0.f, 0.f);
+#else
+        (void)sm; (void)lane;
+        const bool ok = j < q.k_src;
+        const float2 v = gsrc[(long long)(ok ? j : 0) * q.estride];
+        return ok ? v : make_float2(0.f, 0.f);
+#endif
+    }
+
+    template <int PH> static MVSIM_HD void phase(const Params& q, int bx, int by, int tid, float2* sm, State& st)
+    {
+        const int lane = tid % T, g = tid / T;
+        const int tile = by, outer = bx;
+        const bool active = (tile + q.tile0) * T + lane < q.kx_count;
+        float2* e1 = sm;
+        float2* e2 = sm + E_ELEMS;
+        float2* aux = sm + AUX0 + lane;            // row r of the AUX area: aux[r * T]
+        const float2* __restrict__ src = q.u + tile * q.u_tstride + outer * q.ostride + lane;
+        const float2* __restrict__ psrc = q.p2 + tile * q.p2_tstride + outer * q.ostride + lane;
+        if (PH == 0) {
+#ifdef __CUDA_ARCH__
+            if (tid == 0) {
+                // one thread programs the PSF tile (ceil(KZ/128) boxes of 128 rows x 64 bytes) and the L2 prefetch of a later CTA's lines
+                uint64_t* bar = reinterpret_cast<uint64_t*>(sm + BAR_ELEMS);
+                const int nbox = (q.k_src + kTmaBoxRows - 1) / kTmaBoxRows;
+                mbar_init(bar, 1);
+                mbar_expect_tx(bar, (unsigned)(nbox * kTmaBoxRows * T * sizeof(float2)));
+                for (int b = 0; b < nbox; ++b) tma_load_4d(sm + PSF_ELEMS0 + b * kTmaBoxRows * T, q.h_tmap, 0, outer, b * kTmaBoxRows, tile, bar);
+                if (q.prefetch_dist > 0) {
+                    const int lin = by * q.grid_x + bx + q.prefetch_dist;
+                    const int t2 = lin / q.grid_x, o2 = lin - t2 * q.grid_x;
+                    if (t2 < q.grid_y)
+                        for (int z = 0; z < q.n_src; z += kTmaBoxRows) tma_prefetch_4d(q.u_tmap, 0, o2, z, t2);
+                }
+            }
+#endif
+            if (active) {
+                const unsigned e = (unsigned)q.estride32;
+                // border samples of the taps j = 4 c + u of group A + c (the host guarantees EXT_MIRROR1 and KZ <= 4 NCH):
+                //   tail a'[top - j] (source top - j - left >= 0, folds at most once at the far end), head a'[KZ-1 - j] (source |..|)
+                // requested BEFORE the gather (clamped index + select), consumed after it
+                const int c = g - A, top = q.n_src + q.k_src - 1;
+                float2 tl[kPolyTaps], hd[kPolyTaps];
+                if (g >= A) {
+                    MVSIM_UNROLL
+                    for (int u = 0; u < kPolyTaps; ++u) {
+                        const int j = kPolyTaps * c + u;
+                        const int it = top - j - q.left, ih = q.k_src - 1 - j - q.left;
+                        const int mt = 2 * (q.n_src - 1) - it;
+                        const bool okt = j < q.k_src && top - j < N, okh = j < q.k_src && j >= 1;
+                        tl[u] = *at32(src, (unsigned)(okt ? (it < mt ? it : mt) : 0), e);
+                        hd[u] = *at32(src, (unsigned)(okh ? (ih < 0 ? -ih : ih) : 0), e);
+                        if (!okt) tl[u] = make_float2(0.f, 0.f);
+                        if (!okh) hd[u] = make_float2(0.f, 0.f);
+                    }
+                }
+                // image level 1: all loads of the group's items first, then the sub-transforms
+                float2 x[R1][A];
+                MVSIM_UNROLL
+                for (int r = 0; r < R1; ++r) {
+                    const int item = g + G * r;
+                    if (R1 * G == L1 || item < L1) {
+                        const int s = item / B, n2 = item - s * B;
+                        int b0 = q.crop0 - s + INC * n2;          // alpha_s[n1 B + n2] = a'[(b0 + INC B n1) mod N]
+                        b0 = b0 < 0 ? b0 + N : b0;
+                        b0 = b0 >= N ? b0 - N : b0;
+                        int idx[A];
+                        MVSIM_UNROLL
+                        for (int n1 = 0; n1 < A; ++n1) {
+                            const int nn = b0 + INC * B * n1;
+                            idx[n1] = mirror_once((nn >= N ? nn - N : nn) - q.left, q.n_src);
+                        }
+                        MVSIM_UNROLL
+                        for (int n1 = 0; n1 < A; ++n1) x[r][n1] = *at32(src, (unsigned)idx[n1], e);
+                    }
+                }
+                if (g >= A) {
+                    // DD[j] = tail - head (j >= 1; DD[0] = 0) stays in registers; chunk sums of the differences and of the tail samples
+                    float2 ts = make_float2(0.f, 0.f), ds = make_float2(0.f, 0.f);
+                    MVSIM_UNROLL
+                    for (int u = 0; u < kPolyTaps; ++u) {
+                        const bool first = kPolyTaps * c + u == 0;
+                        st.dd[u] = first ? make_float2(0.f, 0.f) : make_float2(tl[u].x - hd[u].x, tl[u].y - hd[u].y);
+                        ts.x += tl[u].x; ts.y += tl[u].y;
+                        ds.x += st.dd[u].x; ds.y += st.dd[u].y;
+                    }
+                    // padding samples beyond the last tap's reach (the planner's size is rarely exactly n_src + KZ - 1)
+                    for (int n = top + 1 + c; n < N; n += NCH) {
+                        const float2 v = *at32(src, (unsigned)mirror_once(n - q.left, q.n_src), e);
+                        ts.x += v.x; ts.y += v.y;
+                    }
+                    aux[(AUX_TS + c) * T] = ts;
+                    aux[(AUX_DS + c) * T] = ds;
+                }
+                MVSIM_UNROLL
+                for (int r = 0; r < R1; ++r) {
+                    const int item = g + G * r;
+                    if (R1 * G == L1 || item < L1) {
+                        const int s = item / B, n2 = item - s * B;
+                        RegSel<A, -1, kPackedStrided>::run(x[r]);
+                        float2* row = e1 + ((s * A) * BP + n2) * T + lane;
+                        MVSIM_UNROLL
+                        for (int k1 = 0; k1 < A; ++k1) row[k1 * BP * T] = k1 == 0 ? x[r][0] : cmul(x[r][k1], q.tw[INC * k1 * n2]);
+                    }
+                }
+            }
+        } else if (PH == 1) {
+            // image level 2: the spectrum A_s[k1 + A k2] stays in registers; its DC bins give the sum of the whole padded line
+            if (g < L2 && active) {
+                const float2* row = e1 + g * BP * T + lane;         // item g = s A + k1
+                MVSIM_UNROLL
+                for (int n2 = 0; n2 < B; ++n2) st.y[n2] = row[n2 * T];
+                RegSel<B, -1, kPackedStrided>::run(st.y);
+                if (g % A == 0) aux[(AUX_TOT + g / A) * T] = st.y[0];
+            }
+#ifdef __CUDA_ARCH__
+            mbar_wait(reinterpret_cast<uint64_t*>(sm + BAR_ELEMS), 0);       // (one barrier since the init)
+#endif
+            if (active) {
+                // PSF level 1: beta_s[q] = INC b[INC q + s], non-zero for q < ceil(KZ / INC) only
+                constexpr int K = RegSelZ<A, kPackedStrided>::K;
+                const bool pruned = (q.k_src + INC - 1) / INC <= K * B;
+                MVSIM_UNROLL
+                for (int r = 0; r < R1; ++r) {
+                    const int item = g + G * r;
+                    if (R1 * G == L1 || item < L1) {
+                        const int s = item / B, n2 = item - s * B;
+                        float2 x[A];
+                        if (pruned) {
+                            MVSIM_UNROLL
+                            for (int n1 = 0; n1 < K; ++n1) {
+                                const float2 v = psf_at(q, sm, psrc, lane, INC * (n1 * B + n2) + s);
+                                x[n1] = make_float2(v.x * (float)INC, v.y * (float)INC);
+                            }
+                            RegSelZ<A, kPackedStrided>::run(x);
+                        } else {
+                            MVSIM_UNROLL
+                            for (int n1 = 0; n1 < A; ++n1) {
+                                const float2 v = psf_at(q, sm, psrc, lane, INC * (n1 * B + n2) + s);
+                                x[n1] = make_float2(v.x * (float)INC, v.y * (float)INC);
+                            }
+                            RegSel<A, -1, kPackedStrided>::run(x);
+                        }
+                        float2* row = e2 + ((s * A) * BP + n2) * T + lane;
+                        MVSIM_UNROLL
+                        for (int k1 = 0; k1 < A; ++k1) row[k1 * BP * T] = k1 == 0 ? x[0] : cmul(x[k1], q.tw[INC * k1 * n2]);
+                    }
+                }
+                // chunk terms of the border dot product: CS_c = sum of the chunk's taps, L_c = sum_u (taps before u inside the chunk) DD[u]
+                if (g >= A) {
+                    const int c = g - A;
+                    float2 pre = make_float2(0.f, 0.f), loc = make_float2(0.f, 0.f);
+                    MVSIM_UNROLL
+                    for (int u = 0; u < kPolyTaps; ++u) {
+                        const float2 d = st.dd[u];
+                        loc.x += pre.x * d.x - pre.y * d.y;
+                        loc.y += pre.x * d.y + pre.y * d.x;
+                        const float2 b = psf_at(q, sm, psrc, lane, kPolyTaps * c + u);
+                        pre.x += b.x; pre.y += b.y;
+                    }
+                    aux[(AUX_CS + c) * T] = pre;
+                    aux[(AUX_L + c) * T] = loc;
+                }
+            }
+        } else if (PH == 2) {
+            // PSF level 2, multiply with the image spectrum, products to this item's (free) row of E1
+            if (g < L2 && active) {
+                const float2* row = e2 + g * BP * T + lane;
+                float2 y[B];
+                MVSIM_UNROLL
+                for (int n2 = 0; n2 < B; ++n2) y[n2] = row[n2 * T];
+                RegSel<B, -1, kPackedStrided>::run(y);
+                float2* prow = e1 + g * BP * T + lane;
+                MVSIM_UNROLL
+                for (int k2 = 0; k2 < B; ++k2) prow[k2 * T] = cmul(y[k2], st.y[k2]);
+            }
+        } else if (PH == 3) {
+            // C[k1 + A k2] = sum over the phases, in place in the rows of phase 0 (the only thread that touches these INC slots)
+            if (active) {
+                for (int el = g; el < M; el += G) {
+                    const int k1 = el / B, k2 = el - k1 * B;
+                    float2* p = e1 + (k1 * BP + k2) * T + lane;
+                    float2 acc = p[0];
+                    MVSIM_UNROLL
+                    for (int s = 1; s < INC; ++s) { const float2 v = p[s * A * BP * T]; acc.x += v.x; acc.y += v.y; }
+                    p[0] = acc;
+                }
+            }
+        } else if (PH == 4) {
+            if (g < A) {
+                // inverse level 1 of the ONE M-point transform: thread k1 holds C[k1 + A k2], B-point inverse, twiddle, own row in place
+                if (active) {
+                    float2* row = e1 + g * BP * T + lane;
+                    float2 y[B];
+                    MVSIM_UNROLL
+                    for (int k2 = 0; k2 < B; ++k2) y[k2] = row[k2 * T];
+                    RegSel<B, 1, kPackedStrided>::run(y);
+                    MVSIM_UNROLL
+                    for (int n2 = 0; n2 < B; ++n2) row[n2 * T] = n2 == 0 ? y[0] : cmulc(y[n2], q.tw[INC * n2 * g]);
+                }
+            } else if (g < A + NSC && active) {
+                // chunk scan, quarter i: sum_c (CS_0 + .. + CS_{c-1}) DS_c + L_c and the tail sums over the chunks [i QSC, (i + 1) QSC)
+                const int i = g - A, c0 = i * QSC, c1 = (i + 1) * QSC < NCH ? (i + 1) * QSC : NCH;
+                float2 pre = make_float2(0.f, 0.f);
+                for (int k = 0; k < c0; ++k) { const float2 v = aux[(AUX_CS + k) * T]; pre.x += v.x; pre.y += v.y; }
+                float2 dot = make_float2(0.f, 0.f), ts = make_float2(0.f, 0.f);
+                for (int c = c0; c < c1; ++c) {
+                    const float2 d = aux[(AUX_DS + c) * T], l = aux[(AUX_L + c) * T], t = aux[(AUX_TS + c) * T], b = aux[(AUX_CS + c) * T];
+                    dot.x += pre.x * d.x - pre.y * d.y + l.x;
+                    dot.y += pre.x * d.y + pre.y * d.x + l.y;
+                    ts.x += t.x; ts.y += t.y;
+                    pre.x += b.x; pre.y += b.y;
+                }
+                if (i == NSC - 1) aux[AUX_B0 * T] = pre;        // B0: the whole PSF line
+                aux[(AUX_SC + i) * T] = dot;
+                aux[(AUX_SC + NSC + i) * T] = ts;
+            }
+        } else if (PH == 5) {
+            if (g < B && active) {
+                // inverse level 2: thread n2 ends up with c[crop0 + INC (n2 + n1 B)]: the kept planes kz = n2 + n1 B, compacted
+                float2 x[A];
+                const float2* col = e1 + g * T + lane;
+                MVSIM_UNROLL
+                for (int k1 = 0; k1 < A; ++k1) x[k1] = col[k1 * BP * T];
+                RegSel<A, 1, kPackedStrided>::run(x);
+                float2* dst = q.u + tile * q.u_tstride + outer * q.ostride + lane;
+                const unsigned e = (unsigned)q.estride32;
+                float2 ks = make_float2(0.f, 0.f);
+                MVSIM_UNROLL
+                for (int n1 = 0; n1 < A; ++n1) {
+                    const int kz = g + n1 * B;
+                    if (kz < q.n_keep) { *at32(dst, (unsigned)kz, e) = x[n1]; ks.x += x[n1].x; ks.y += x[n1].y; }
+                }
+                aux[(AUX_KEPT + g) * T] = ks;
+            }
+        } else {
+            // plane n_keep: N (B0 sum_{n < n_src} a'[n] + dot) - kept planes  (the z transforms are unnormalised: factor N as in the
+            // spectral kernels; the kept planes carry it through beta's factor INC and the unnormalised M-point inverse)
+            if (g == 0 && active) {
+                float2 d = make_float2(0.f, 0.f), t = make_float2(0.f, 0.f), tot = make_float2(0.f, 0.f), kept = make_float2(0.f, 0.f);
+                MVSIM_UNROLL
+                for (int j = 0; j < NSC; ++j) {
+                    const float2 a = aux[(AUX_SC + j) * T], b = aux[(AUX_SC + NSC + j) * T];
+                    d.x += a.x; d.y += a.y; t.x += b.x; t.y += b.y;
+                }
+                MVSIM_UNROLL
+                for (int s = 0; s < INC; ++s) { const float2 v = aux[(AUX_TOT + s) * T]; tot.x += v.x; tot.y += v.y; }
+                MVSIM_UNROLL
+                for (int j = 0; j < B; ++j) { const float2 v = aux[(AUX_KEPT + j) * T]; kept.x += v.x; kept.y += v.y; }
+                const float2 b0 = aux[AUX_B0 * T];
+                const float2 sa = make_float2(tot.x - t.x, tot.y - t.y);
+                const float2 all = make_float2(b0.x * sa.x - b0.y * sa.y + d.x, b0.x * sa.y + b0.y * sa.x + d.y);
+                q.u[tile * q.u_tstride + outer * q.ostride + lane + q.n_keep * q.estride] =
+                    make_float2((float)N * all.x - kept.x, (float)N * all.y - kept.y);
+            }
+        }
+    }
+};
+
+}  // namespace mvsim

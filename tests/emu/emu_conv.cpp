@@ -10,13 +10,20 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 using namespace mvsim;
 
+// dynamic shared memory of a launch: K::SMEM_BYTES, or K::smem_bytes(params) where the kernel sizes an area at run time
+template <class K, class = void> struct EmuSmem { static size_t bytes(const typename K::Params&) { return (size_t)K::SMEM_BYTES; } };
+template <class K> struct EmuSmem<K, std::void_t<decltype(&K::smem_bytes)>> {
+    static size_t bytes(const typename K::Params& q) { return (size_t)K::smem_bytes(q); }
+};
+
 template <class K> static void emulate(const typename K::Params& q, int gx, int gy)
 {
-    std::vector<float2> sm((size_t)K::SMEM_BYTES / sizeof(float2) + 8);
+    std::vector<float2> sm(EmuSmem<K>::bytes(q) / sizeof(float2) + 8);
     std::vector<typename K::State> st(K::THREADS);
     for (int by = 0; by < gy; ++by)
         for (int bx = 0; bx < gx; ++bx) {
@@ -93,6 +100,28 @@ struct EmuLauncher {
         }
     }
     static int decimated_launches;
+    // polyphase form of the whole-view fused z pass (ZFusedPoly)
+    bool z_polyphase(const FftSize& s, int inc, int k_src) const { return getenv("MVSIM_EMU_POLY") != nullptr && k_src <= zfused_poly_max_taps(s.n, inc); }
+    int launch_zfused_poly(const FftSize& s, const ZFusedParams& q, int tiles, int n_outer, int inc)
+    {
+        ++polyphase_launches;
+        switch (s.n) {
+#define MVSIM_X(n_, a_, b_) case n_: return inc == 3 ? poly<n_, 3>(q, n_outer, tiles) : poly<n_, 5>(q, n_outer, tiles);
+            MVSIM_FFT_SIZES(MVSIM_X)
+#undef MVSIM_X
+        }
+        return 5;
+    }
+    template <int N, int INC> static int poly(const ZFusedParams& q, int n_outer, int tiles)
+    {
+        if constexpr (zfused_poly_ok(N, INC)) {
+            emulate<ZFusedPoly<N, INC, T>>(q, n_outer, tiles);
+            return 0;
+        } else {
+            return 5;
+        }
+    }
+    static int polyphase_launches;
     int launch_zfused(const FftSize& s, const ZFusedParams& q, int tiles, int n_outer)
     {
         if (q.h_mode)
@@ -112,6 +141,8 @@ struct EmuLauncher {
 
 int EmuLauncher::decimated_launches = 0;
 extern "C" int emu_decimated_launches() { return EmuLauncher::decimated_launches; }
+int EmuLauncher::polyphase_launches = 0;
+extern "C" int emu_polyphase_launches() { return EmuLauncher::polyphase_launches; }
 
 extern "C" int emu_plan(const int64_t dims[3], const int64_t kdims[3], int out[11], int max_line)
 {

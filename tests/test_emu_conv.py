@@ -198,3 +198,51 @@ def test_decimated_inverse_of_the_fused_z_pass(emu, oracle, monkeypatch, psf_spe
     dropped = ref.astype(np.float64).sum(axis=0) - kept.astype(np.float64).sum(axis=0)
     assert rel_err(out[nk], dropped.astype(np.float32)) < 3e-5
     assert s == pytest.approx(float(ref.astype(np.float64).sum()), rel=3e-6)
+
+
+@pytest.mark.parametrize("shape,kshape,inc", [
+    ((599, 2, 3), (42, 1, 2), 5),      # 640 = 5 x 128 (BASELINE config 3's z line): 5 phases of 8 x 16 points, top == N exactly
+    ((580, 1, 3), (42, 2, 1), 5),      # 640 with padding samples beyond the last tap's reach
+    ((271, 1, 2), (90, 1, 1), 3),      # 360 = 3 x 120, PSF phases longer than the pruned sub-transform reads: full level 1
+    ((261, 1, 2), (100, 1, 1), 5),     # 360 = 5 x 72, the same
+    ((513, 1, 20), (128, 1, 2), 5),    # 640 = 513 + 128 - 1, even kernel, partial last kx tile
+    ((344, 2, 3), (17, 1, 2), 3),      # 360 = 3 x 120 (config 1 / 4 z lines at inc 3): 10 x 12
+    ((344, 1, 3), (17, 2, 1), 5),      # 360 = 5 x 72: 8 x 9, 45 groups
+    ((560, 1, 3), (17, 1, 1), 3),      # 576 = 3 x 192: 12 x 16, 48 groups
+    ((330, 1, 2), (1, 1, 1), 3),       # identity kernel: crop0 = 0 < inc - 1 (negative phase offsets wrap)
+    ((350, 1, 2), (2, 1, 1), 5),       # two taps
+])
+def test_polyphase_fused_z_pass(emu, oracle, monkeypatch, psf_spectrum_mode, request, shape, kshape, inc):
+    """ZFusedPoly: inc cyclic convolutions of n / inc points for the kept planes, sum of the dropped planes from the time domain
+    (PSF prefix sums against the border samples of the image line)."""
+    monkeypatch.setenv("MVSIM_EMU_POLY", "1")
+    emu.emu_polyphase_launches.restype = C.c_int
+    before = emu.emu_polyphase_launches()
+    rng = np.random.default_rng(22)
+    vol = rng.random(shape, dtype=np.float32)
+    psf = rng.random(kshape, dtype=np.float32)
+    ref = oracle.convolve(vol, psf, "direct")
+    kept = ref[::inc]
+    nk = kept.shape[0]
+    out, s = _run(emu, vol, psf, keep_inc=inc, planes=nk + 1)
+    if "on-the-fly" in request.node.name:
+        assert emu.emu_polyphase_launches() == before + 1       # the polyphase kernel really ran
+    assert rel_err(out[:nk], kept) < 5e-6
+    dropped = ref.astype(np.float64).sum(axis=0) - kept.astype(np.float64).sum(axis=0)
+    assert rel_err(out[nk], dropped.astype(np.float32)) < 3e-5
+    assert s == pytest.approx(float(ref.astype(np.float64).sum()), rel=3e-6)
+
+
+def test_polyphase_kernel_is_vetoed_for_long_psf_lines(emu, oracle, monkeypatch):
+    """More PSF taps than the border groups hold in registers (4 per group): the launcher falls back to the spectral kernels."""
+    monkeypatch.setenv("MVSIM_EMU_POLY", "1")
+    monkeypatch.setenv("MVSIM_EMU_OTF", "1")
+    emu.emu_polyphase_launches.restype = C.c_int
+    before = emu.emu_polyphase_launches()
+    rng = np.random.default_rng(23)
+    vol = rng.random((441, 1, 2), dtype=np.float32)
+    psf = rng.random((200, 1, 1), dtype=np.float32)
+    ref = oracle.convolve(vol, psf, "direct")
+    out, _ = _run(emu, vol, psf, keep_inc=5, planes=(441 - 1) // 5 + 2)
+    assert emu.emu_polyphase_launches() == before
+    assert rel_err(out[:-1], ref[::5]) < 5e-6

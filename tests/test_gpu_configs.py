@@ -149,3 +149,25 @@ def test_view_loop_on_resident_and_wrapped_ground_truth(mv):
                         outs=[np.empty((8, 40, 40), dtype=np.float32) for _ in range(3)])
     vol.free()
     ctx.close()
+
+
+@pytest.mark.parametrize("shape,kshape,inc,distinct", [
+    ((330, 48, 40), (31, 9, 7), 3, 3),       # z line 360: polyphase (3 x 120), decimated inverse (18 | 3) and full spectral kernel
+    ((330, 40, 24), (31, 7, 5), 5, 2),       # 360 at inc 5: polyphase (5 x 72); no decimated kernel for this split -> full spectral
+    ((512, 32, 24), (128, 9, 5), 5, 3),      # BASELINE config 3's z line: 640 = 5 x 128
+])
+def test_fused_z_kernel_variants_agree(mv, shape, kshape, inc, distinct):
+    """MVSIM_OPT_Z_KERNEL: the polyphase, decimated-inverse and full spectral fused z kernels compute the same view (kept planes AND,
+    through adjustImage's mean, the sum of the dropped planes) to float32 rounding -- and are really different kernels."""
+    S = mv.SimulateMultiViewDataset
+    rng = np.random.default_rng(31)
+    gt = rng.random(shape, dtype=np.float32)
+    psf = gaussian_psf(kshape, (kshape[0] / 6.0, 1.5, 1.2), threshold=0.0) + 1e-3 * rng.random(kshape, dtype=np.float32)
+    outs = []
+    for which in (3, 1, 2):
+        ctx = mv.Context(0).z_kernel(which)
+        outs.append(S.simulateView(gt, psf.copy(), 40, inc=inc, poissonSNR=-1.0, ctx=ctx))
+    for o in outs[1:]:
+        assert rel_err(outs[0], o) < 2e-6
+        assert float(o.astype(np.float64).mean()) == pytest.approx(float(outs[0].astype(np.float64).mean()), rel=2e-6)
+    assert len({o.tobytes() for o in outs}) == distinct
