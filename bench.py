@@ -34,9 +34,11 @@ WORKLOADS = {
     # name: (shape_zyx, kshape_zyx, sigma_zyx, degrees, inc, snr)
     "cfg3": ((512, 1024, 1024), (128, 128, 128), (17.5, 5.5, 5.0), [15, 75, 135, 195, 255, 315], 5, 25.0),
     "cfg1": ((256, 512, 512), (51, 51, 51), (7.0, 2.2, 2.0), [15, 105, 195, 285], 3, 25.0),
+    "cfg4": ((512, 512, 512), (51, 51, 51), (7.0, 2.2, 2.0), [15, 105, 195, 285], 3, 25.0),      # bead-volume shape: 576-point z lines, inc 3
     "small": ((64, 128, 128), (16, 16, 16), (3.0, 1.2, 1.1), [15, 75, 135, 195, 255, 315], 5, 25.0),
 }
 CPU_SAMPLE = {"cfg3": ((128, 256, 256), (32, 32, 32), (4.4, 1.4, 1.25)), "cfg1": ((64, 128, 128), (25, 25, 25), (3.5, 1.1, 1.0)),
+              "cfg4": ((128, 128, 128), (25, 25, 25), (3.5, 1.1, 1.0)),
               "small": ((32, 64, 64), (8, 8, 8), (1.5, 0.8, 0.8))}
 
 

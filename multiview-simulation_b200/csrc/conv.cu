@@ -114,7 +114,7 @@ static int get_dec_table(mvsim_ctx* ctx, int n, int crop0, int n_src, int inc, c
 }
 
 // does MVSIM_OPT_Z_KERNEL = 0 (auto) pick the polyphase kernel where it applies?  Measured on B200 at config 3 (profiles/r02_notes.md)
-constexpr bool kPolyphaseDefault = false;
+constexpr bool kPolyphaseDefault = true;
 
 struct CudaLauncher {
     mvsim_ctx* ctx;

@@ -17,17 +17,18 @@
 //
 // (each a'[n] is weighted by the part of the PSF line whose taps land inside the cropped range), and
 // sum_{n < n_src} a'[n] = sum_s DFT(alpha_s)[0] - sum_{n >= n_src} a'[n].  The 2 (KZ - 1) border samples are loaded a second time
-// (L1 / L2 hits: the same CTA gathers them in the same phase): group A + c owns the taps j = 4 c .. 4 c + 3, keeps their differences
-// DD[j] in registers, and in the next phase (PSF tile present) forms its local share L_c = sum_u (b[4c] + .. + b[4c+u-1]) DD[4c+u]
-// and its chunk sums CS_c = sum b, DS_c = sum DD.  What is left, sum_c (CS_0 + .. + CS_{c-1}) DS_c + L_c, is a scan over the NCH
-// chunks, run by ONE warp beside the two warps of the first inverse half.
+// (L1 / L2 hits: the same CTA gathers them in the same phase): group A + c owns the taps j = 4 c .. 4 c + 3, keeps their samples in
+// registers, and in the next phase (PSF tile present) forms the differences DD[j], its local share
+// L_c = sum_u (b[4c] + .. + b[4c+u-1]) DD[4c+u] and its chunk sums CS_c = sum b, DS_c = sum DD.  What is left,
+// sum_c (CS_0 + .. + CS_{c-1}) DS_c + L_c, is a scan over the NCH chunks, run by ONE warp beside the two warps of the first
+// inverse half.
 //
 // Work items of a CTA (T neighbouring kx columns of one ky; G = THREADS / T groups, group g works on `lane` = tid % T):
 //   level 1 : (phase s, n2 < B): A-point transform over n1 of alpha_s[n1 B + n2]      -> INC B items, R1 rounds over the G groups
 //   level 2 : (phase s, k1 < A): B-point transform                                     -> INC A items <= G, one per group
 // so every warp works in the four transform phases; only the single inverse runs on A, then B groups.
-// Phases: image level 1, border differences | image level 2 (spectrum stays in registers), PSF level 1, chunk terms |
-//         PSF level 2, multiply | sum over the phases | inverse level 1, chunk scan | inverse level 2 + stores | sum plane.
+// Phases: requests (PSF tile by TMA, border samples, gather) | level 1 of the PSF and image phases (shared twiddles), chunk terms |
+//         level 2 of both, multiply | sum over the phases | inverse level 1, chunk scan | inverse level 2 + stores | sum plane.
 #pragma once
 
 namespace mvsim {
@@ -35,8 +36,9 @@ namespace mvsim {
 // groups per CTA for the split M = a * b (a <= b) with inc phases
 constexpr int poly_groups(int a, int b, int inc)
 {
+    // one level-1 item per group up to 40 groups (320 threads at T = 8: two CTAs per SM at 96 registers), else two rounds
     const int l1 = inc * b, l2 = inc * a;
-    if (l1 <= 48) return l1;
+    if (l1 <= 40) return l1;
     const int half = (l1 + 1) / 2;
     return l2 > half ? l2 : half;
 }
@@ -48,7 +50,9 @@ constexpr bool zfused_poly_ok(int n, int inc)
     const FftSize s = fft_size_lookup(n / inc);
     if (s.n < 64 || s.a > s.b) return false;
     const int g = poly_groups(s.a, s.b, inc);
-    return g >= inc * s.a && g >= s.b && g - s.a >= 8 && g * 8 <= 512;
+    // (two gathered items of more than 8 samples each do not fit the 96 registers of 2 x 320 threads per SM: such splits spill)
+    const int r1 = (inc * s.b + g - 1) / g;
+    return g >= inc * s.a && g >= s.b && g - s.a >= 8 && g <= 40 && (r1 * s.a <= 16 || g <= 32);
 }
 // PSF taps the border groups of a launch can take
 constexpr int zfused_poly_max_taps(int n, int inc)
@@ -72,7 +76,11 @@ inline bool zfused_poly_fits(int n, int inc, int t, int k_src)
     return k_src <= zfused_poly_max_taps(n, inc) && poly_smem_base(m.a, m.b, inc, t) + poly_psf_tile_bytes(k_src, t) <= kPolySmemMax;
 }
 
-template <int B> struct PolyState { float2 y[B]; float2 dd[kPolyTaps]; };
+template <int A, int B, int R1> struct PolyState {
+    float2 x[R1][A];                // gathered image samples of the group's level-1 items (requested in phase 0, used in phase 1)
+    float2 tl[kPolyTaps], hd[kPolyTaps];    // border samples of the group's taps
+    float2 y[B];                    // image spectrum A_s[k1 + A k2] of the group's level-2 item
+};
 
 template <int N_, int INC_, int T_> struct ZFusedPoly {
     static constexpr bool IS_X = false;
@@ -97,7 +105,7 @@ template <int N_, int INC_, int T_> struct ZFusedPoly {
     static constexpr int SMEM_BYTES = PSF_ELEMS0 * (int)sizeof(float2);       // without the PSF tile
     static constexpr int NPH = 7;
     using Params = ZFusedParams;
-    using State = PolyState<B>;
+    using State = PolyState<A, B, R1>;
     static_assert(SMEM_BYTES == poly_smem_base(A, B, INC_, T_), "host-side shared memory formula out of sync");
     static int smem_bytes(const Params& q) { return SMEM_BYTES + (q.use_tma ? poly_psf_tile_bytes(q.k_src, T) : 0); }
     static int smem_bytes_max() { return kPolySmemMax > SMEM_BYTES ? kPolySmemMax : SMEM_BYTES; }
@@ -130,9 +138,10 @@ template <int N_, int INC_, int T_> struct ZFusedPoly {
         const float2* __restrict__ src = q.u + tile * q.u_tstride + outer * q.ostride + lane;
         const float2* __restrict__ psrc = q.p2 + tile * q.p2_tstride + outer * q.ostride + lane;
         if (PH == 0) {
+            // requests only: PSF tile (TMA), L2 prefetch of a later CTA's lines, border samples, the gather.  Nothing is consumed
+            // before the barrier, which also publishes the mbarrier's initialisation
 #ifdef __CUDA_ARCH__
             if (tid == 0) {
-                // one thread programs the PSF tile (ceil(KZ/128) boxes of 128 rows x 64 bytes) and the L2 prefetch of a later CTA's lines
                 uint64_t* bar = reinterpret_cast<uint64_t*>(sm + BAR_ELEMS);
                 const int nbox = (q.k_src + kTmaBoxRows - 1) / kTmaBoxRows;
                 mbar_init(bar, 1);
@@ -150,24 +159,19 @@ template <int N_, int INC_, int T_> struct ZFusedPoly {
                 const unsigned e = (unsigned)q.estride32;
                 // border samples of the taps j = 4 c + u of group A + c (the host guarantees EXT_MIRROR1 and KZ <= 4 NCH):
                 //   tail a'[top - j] (source top - j - left >= 0, folds at most once at the far end), head a'[KZ-1 - j] (source |..|)
-                // requested BEFORE the gather (clamped index + select), consumed after it
-                const int c = g - A, top = q.n_src + q.k_src - 1;
-                float2 tl[kPolyTaps], hd[kPolyTaps];
+                // (clamped index + select)
                 if (g >= A) {
+                    const int c = g - A, top = q.n_src + q.k_src - 1;
                     MVSIM_UNROLL
                     for (int u = 0; u < kPolyTaps; ++u) {
                         const int j = kPolyTaps * c + u;
                         const int it = top - j - q.left, ih = q.k_src - 1 - j - q.left;
                         const int mt = 2 * (q.n_src - 1) - it;
                         const bool okt = j < q.k_src && top - j < N, okh = j < q.k_src && j >= 1;
-                        tl[u] = *at32(src, (unsigned)(okt ? (it < mt ? it : mt) : 0), e);
-                        hd[u] = *at32(src, (unsigned)(okh ? (ih < 0 ? -ih : ih) : 0), e);
-                        if (!okt) tl[u] = make_float2(0.f, 0.f);
-                        if (!okh) hd[u] = make_float2(0.f, 0.f);
+                        st.tl[u] = *at32(src, (unsigned)(okt ? (it < mt ? it : mt) : 0), e);
+                        st.hd[u] = *at32(src, (unsigned)(okh ? (ih < 0 ? -ih : ih) : 0), e);
                     }
                 }
-                // image level 1: all loads of the group's items first, then the sub-transforms
-                float2 x[R1][A];
                 MVSIM_UNROLL
                 for (int r = 0; r < R1; ++r) {
                     const int item = g + G * r;
@@ -183,53 +187,17 @@ template <int N_, int INC_, int T_> struct ZFusedPoly {
                             idx[n1] = mirror_once((nn >= N ? nn - N : nn) - q.left, q.n_src);
                         }
                         MVSIM_UNROLL
-                        for (int n1 = 0; n1 < A; ++n1) x[r][n1] = *at32(src, (unsigned)idx[n1], e);
-                    }
-                }
-                if (g >= A) {
-                    // DD[j] = tail - head (j >= 1; DD[0] = 0) stays in registers; chunk sums of the differences and of the tail samples
-                    float2 ts = make_float2(0.f, 0.f), ds = make_float2(0.f, 0.f);
-                    MVSIM_UNROLL
-                    for (int u = 0; u < kPolyTaps; ++u) {
-                        const bool first = kPolyTaps * c + u == 0;
-                        st.dd[u] = first ? make_float2(0.f, 0.f) : make_float2(tl[u].x - hd[u].x, tl[u].y - hd[u].y);
-                        ts.x += tl[u].x; ts.y += tl[u].y;
-                        ds.x += st.dd[u].x; ds.y += st.dd[u].y;
-                    }
-                    // padding samples beyond the last tap's reach (the planner's size is rarely exactly n_src + KZ - 1)
-                    for (int n = top + 1 + c; n < N; n += NCH) {
-                        const float2 v = *at32(src, (unsigned)mirror_once(n - q.left, q.n_src), e);
-                        ts.x += v.x; ts.y += v.y;
-                    }
-                    aux[(AUX_TS + c) * T] = ts;
-                    aux[(AUX_DS + c) * T] = ds;
-                }
-                MVSIM_UNROLL
-                for (int r = 0; r < R1; ++r) {
-                    const int item = g + G * r;
-                    if (R1 * G == L1 || item < L1) {
-                        const int s = item / B, n2 = item - s * B;
-                        RegSel<A, -1, kPackedStrided>::run(x[r]);
-                        float2* row = e1 + ((s * A) * BP + n2) * T + lane;
-                        MVSIM_UNROLL
-                        for (int k1 = 0; k1 < A; ++k1) row[k1 * BP * T] = k1 == 0 ? x[r][0] : cmul(x[r][k1], q.tw[INC * k1 * n2]);
+                        for (int n1 = 0; n1 < A; ++n1) st.x[r][n1] = *at32(src, (unsigned)idx[n1], e);
                     }
                 }
             }
         } else if (PH == 1) {
-            // image level 2: the spectrum A_s[k1 + A k2] stays in registers; its DC bins give the sum of the whole padded line
-            if (g < L2 && active) {
-                const float2* row = e1 + g * BP * T + lane;         // item g = s A + k1
-                MVSIM_UNROLL
-                for (int n2 = 0; n2 < B; ++n2) st.y[n2] = row[n2 * T];
-                RegSel<B, -1, kPackedStrided>::run(st.y);
-                if (g % A == 0) aux[(AUX_TOT + g / A) * T] = st.y[0];
-            }
 #ifdef __CUDA_ARCH__
-            mbar_wait(reinterpret_cast<uint64_t*>(sm + BAR_ELEMS), 0);       // (one barrier since the init)
+            mbar_wait(reinterpret_cast<uint64_t*>(sm + BAR_ELEMS), 0);       // the PSF tile (8 KB) lands before the gathered lines
 #endif
             if (active) {
-                // PSF level 1: beta_s[q] = INC b[INC q + s], non-zero for q < ceil(KZ / INC) only
+                // level 1 of the PSF phases (beta_s[q] = INC b[INC q + s], non-zero for q < ceil(KZ / INC) only) and of the image
+                // phases, item by item: both use the twiddles W_M^{k1 n2} of the item
                 constexpr int K = RegSelZ<A, kPackedStrided>::K;
                 const bool pruned = (q.k_src + INC - 1) / INC <= K * B;
                 MVSIM_UNROLL
@@ -237,6 +205,9 @@ template <int N_, int INC_, int T_> struct ZFusedPoly {
                     const int item = g + G * r;
                     if (R1 * G == L1 || item < L1) {
                         const int s = item / B, n2 = item - s * B;
+                        float2 tw[A];
+                        MVSIM_UNROLL
+                        for (int k1 = 1; k1 < A; ++k1) tw[k1] = q.tw[INC * k1 * n2];
                         float2 x[A];
                         if (pruned) {
                             MVSIM_UNROLL
@@ -253,38 +224,60 @@ template <int N_, int INC_, int T_> struct ZFusedPoly {
                             }
                             RegSel<A, -1, kPackedStrided>::run(x);
                         }
-                        float2* row = e2 + ((s * A) * BP + n2) * T + lane;
+                        float2* prow = e2 + ((s * A) * BP + n2) * T + lane;
                         MVSIM_UNROLL
-                        for (int k1 = 0; k1 < A; ++k1) row[k1 * BP * T] = k1 == 0 ? x[0] : cmul(x[k1], q.tw[INC * k1 * n2]);
+                        for (int k1 = 0; k1 < A; ++k1) prow[k1 * BP * T] = k1 == 0 ? x[0] : cmul(x[k1], tw[k1]);
+                        RegSel<A, -1, kPackedStrided>::run(st.x[r]);
+                        float2* row = e1 + ((s * A) * BP + n2) * T + lane;
+                        MVSIM_UNROLL
+                        for (int k1 = 0; k1 < A; ++k1) row[k1 * BP * T] = k1 == 0 ? st.x[r][0] : cmul(st.x[r][k1], tw[k1]);
                     }
                 }
-                // chunk terms of the border dot product: CS_c = sum of the chunk's taps, L_c = sum_u (taps before u inside the chunk) DD[u]
                 if (g >= A) {
-                    const int c = g - A;
-                    float2 pre = make_float2(0.f, 0.f), loc = make_float2(0.f, 0.f);
+                    // border terms of chunk c: DD[u] = tail - head (DD = 0 at tap 0 and beyond the PSF line), the chunk sums
+                    // TS_c (tail samples), DS_c (differences), CS_c (PSF taps) and L_c = sum_u (taps of the chunk before u) DD[u]
+                    const int c = g - A, top = q.n_src + q.k_src - 1;
+                    float2 ts = make_float2(0.f, 0.f), ds = make_float2(0.f, 0.f), pre = make_float2(0.f, 0.f), loc = make_float2(0.f, 0.f);
                     MVSIM_UNROLL
                     for (int u = 0; u < kPolyTaps; ++u) {
-                        const float2 d = st.dd[u];
+                        const int j = kPolyTaps * c + u;
+                        const bool okt = j < q.k_src && top - j < N, okh = j < q.k_src && j >= 1;
+                        const float2 t = okt ? st.tl[u] : make_float2(0.f, 0.f);
+                        const float2 d = okh ? make_float2(t.x - st.hd[u].x, t.y - st.hd[u].y) : make_float2(0.f, 0.f);
+                        ts.x += t.x; ts.y += t.y;
+                        ds.x += d.x; ds.y += d.y;
                         loc.x += pre.x * d.x - pre.y * d.y;
                         loc.y += pre.x * d.y + pre.y * d.x;
-                        const float2 b = psf_at(q, sm, psrc, lane, kPolyTaps * c + u);
+                        const float2 b = psf_at(q, sm, psrc, lane, j);
                         pre.x += b.x; pre.y += b.y;
                     }
+                    // padding samples beyond the last tap's reach (the planner's size is rarely exactly n_src + KZ - 1)
+                    for (int n = top + 1 + c; n < N; n += NCH) {
+                        const float2 v = *at32(src, (unsigned)mirror_once(n - q.left, q.n_src), (unsigned)q.estride32);
+                        ts.x += v.x; ts.y += v.y;
+                    }
+                    aux[(AUX_TS + c) * T] = ts;
+                    aux[(AUX_DS + c) * T] = ds;
                     aux[(AUX_CS + c) * T] = pre;
                     aux[(AUX_L + c) * T] = loc;
                 }
             }
         } else if (PH == 2) {
-            // PSF level 2, multiply with the image spectrum, products to this item's (free) row of E1
+            // level 2 of the image phase (spectrum A_s[k1 + A k2] in registers; the DC bins give the sum of the whole padded line) and
+            // of the PSF phase, multiply, products to this item's row of E1 (read completely by this thread before it is rewritten)
             if (g < L2 && active) {
-                const float2* row = e2 + g * BP * T + lane;
+                float2* row = e1 + g * BP * T + lane;               // item g = s A + k1
+                MVSIM_UNROLL
+                for (int n2 = 0; n2 < B; ++n2) st.y[n2] = row[n2 * T];
+                RegSel<B, -1, kPackedStrided>::run(st.y);
+                if (g % A == 0) aux[(AUX_TOT + g / A) * T] = st.y[0];
+                const float2* prow = e2 + g * BP * T + lane;
                 float2 y[B];
                 MVSIM_UNROLL
-                for (int n2 = 0; n2 < B; ++n2) y[n2] = row[n2 * T];
+                for (int n2 = 0; n2 < B; ++n2) y[n2] = prow[n2 * T];
                 RegSel<B, -1, kPackedStrided>::run(y);
-                float2* prow = e1 + g * BP * T + lane;
                 MVSIM_UNROLL
-                for (int k2 = 0; k2 < B; ++k2) prow[k2 * T] = cmul(y[k2], st.y[k2]);
+                for (int k2 = 0; k2 < B; ++k2) row[k2 * T] = cmul(y[k2], st.y[k2]);
             }
         } else if (PH == 3) {
             // C[k1 + A k2] = sum over the phases, in place in the rows of phase 0 (the only thread that touches these INC slots)

@@ -207,8 +207,8 @@ def test_decimated_inverse_of_the_fused_z_pass(emu, oracle, monkeypatch, psf_spe
     ((261, 1, 2), (100, 1, 1), 5),     # 360 = 5 x 72, the same
     ((513, 1, 20), (128, 1, 2), 5),    # 640 = 513 + 128 - 1, even kernel, partial last kx tile
     ((344, 2, 3), (17, 1, 2), 3),      # 360 = 3 x 120 (config 1 / 4 z lines at inc 3): 10 x 12
-    ((344, 1, 3), (17, 2, 1), 5),      # 360 = 5 x 72: 8 x 9, 45 groups
-    ((560, 1, 3), (17, 1, 1), 3),      # 576 = 3 x 192: 12 x 16, 48 groups
+    ((344, 1, 3), (17, 2, 1), 5),      # 360 = 5 x 72: 8 x 9, 40 groups, two rounds of level-1 items (5 in the second)
+    ((330, 2, 3), (30, 1, 2), 3),      # 360 = 3 x 120 with an even kernel (crop0 = 29), one padding sample
     ((330, 1, 2), (1, 1, 1), 3),       # identity kernel: crop0 = 0 < inc - 1 (negative phase offsets wrap)
     ((350, 1, 2), (2, 1, 1), 5),       # two taps
 ])
