@@ -120,8 +120,12 @@ inline int conv_out_planes(const ConvPlan& pl, const SlabGeom& g, int keep_inc)
 }
 
 // fused z pass on this rank's tiles, in place on buf = [S][tiles][Zl][Ny][T]
-template <class L> int conv_middle_z(L& l, const ConvPlan& pl, const SlabGeom& g, const ConvWorkspace& ws, float2* buf, int keep_inc)
+// sum_is_total (nullable): set to true when the extra plane of the pruned inverse side carries the sum of ALL cropped planes (the
+// polyphase kernel) instead of the sum of the dropped ones -- the inverse x pass must then count that plane alone
+template <class L> int conv_middle_z(L& l, const ConvPlan& pl, const SlabGeom& g, const ConvWorkspace& ws, float2* buf, int keep_inc,
+                                     bool* sum_is_total = nullptr)
 {
+    if (sum_is_total) *sum_is_total = false;
     const long long T = l.lanes, ny = pl.sy.n;
     const int planes = conv_out_planes(pl, g, keep_inc);
     const bool pruned = g.world == 1 && planes != pl.dims[2];
@@ -148,7 +152,10 @@ template <class L> int conv_middle_z(L& l, const ConvPlan& pl, const SlabGeom& g
     if (pruned && l.h_on_the_fly && zp.estride32 != 0 && zp.ext == EXT_MIRROR1 && zfused_poly_ok(pl.sz.n, keep_inc) && pl.dims[2] >= pl.kdims[2] &&
         l.z_polyphase(pl.sz, keep_inc, pl.kdims[2])) {
         const int perr = l.launch_zfused_poly(pl.sz, zp, g.tiles_own, pl.sy.n, keep_inc);
-        if (perr != -2) return perr;        // -2: the launcher could not set the kernel up (no TMA descriptor): spectral kernels below
+        if (perr != -2) {                   // -2: the launcher could not set the kernel up (no TMA descriptor): spectral kernels below
+            if (sum_is_total) *sum_is_total = true;
+            return perr;
+        }
     }
     // decimated inverse when the kept planes are whole columns of the exchange (the launcher may veto: line length, A/B knob)
     if (pruned && l.h_on_the_fly && zp.estride32 != 0 && zfused_dec_ok(pl.sz.a, pl.sz.b, keep_inc) && l.z_decimate(pl.sz))
@@ -196,10 +203,13 @@ template <class L> int conv_inverse_y(L& l, const ConvPlan& pl, const SlabGeom& 
 }
 
 // x inverse + crop: ws.u1o -> out [planes][Y][X]; partials (nullable): one double per block
-template <class L> int conv_inverse_x(L& l, const ConvPlan& pl, const ConvWorkspace& ws, float* out, double* partials, int planes)
+// sum_last_plane_only: the per-block sums count the LAST plane alone (it carries the sum of all cropped planes, see conv_middle_z)
+template <class L> int conv_inverse_x(L& l, const ConvPlan& pl, const ConvWorkspace& ws, float* out, double* partials, int planes,
+                                      bool sum_last_plane_only = false)
 {
     XParams ix = {};
     ix.cin = ws.u1o; ix.rout = out; ix.tw = ws.tw_x; ix.twist = ws.twist_x; ix.partials = partials;
+    ix.sum_row0 = sum_last_plane_only ? (long long)pl.dims[1] * (planes - 1) : 0;
     ix.X = pl.dims[0]; ix.n_rows = pl.dims[1] * planes; ix.crop0 = pl.crop0[0];
     return l.launch_x(true, pl.sx, ix);
 }
@@ -211,12 +221,13 @@ template <class L> int conv_apply(L& l, const ConvPlan& pl, const SlabGeom& g, c
 {
     const int planes = conv_out_planes(pl, g, keep_inc);
     int err = conv_forward_x(l, pl, g, ws, img);
+    bool sum_total = false;         // the same kernel serves every y block, so the last answer stands for all
     for (int b = 0; b < pl.y_blocks && !err; ++b) {
         err = conv_forward_y(l, pl, g, ws, b);
-        if (!err) err = conv_middle_z(l, pl, g, ws, ws.u2, keep_inc);
+        if (!err) err = conv_middle_z(l, pl, g, ws, ws.u2, keep_inc, &sum_total);
         if (!err) err = conv_inverse_y(l, pl, g, ws, b, planes);
     }
-    if (!err) err = conv_inverse_x(l, pl, ws, out, partials, planes);
+    if (!err) err = conv_inverse_x(l, pl, ws, out, partials, planes, sum_total);
     return err;
 }
 

@@ -367,7 +367,8 @@ struct ZFusedParams {
     unsigned keep_magic;    // div_magic(keep_inc)
     int keep_inc, n_keep;   // keep_inc > 1 (single segment only): store only z = 0, inc, 2 inc, ... compacted to planes
                             // 0..n_keep-1 and the SUM of all other cropped z in plane n_keep (enough for extractSlices + the
-                            // mean of adjustImage)
+                            // mean of adjustImage).  ZFusedPoly stores the sum of ALL cropped z there instead (conv_middle_z
+                            // reports which; the inverse x pass then counts that plane alone, XParams::sum_row0)
     long long estride;      // z stride inside a segment (= Ny*T), also the kz stride of h
     int estride32;          // != 0: one segment (single GPU) and every in-line offset z*estride fits 32 bits: the loaders and storers
                             // then spend one 32-bit multiply per element instead of the segmented 64-bit address arithmetic
@@ -986,7 +987,8 @@ struct XParams {
     float2* cout;           // forward: spectrum rows [n_rows][N]
     const float2* tw;       // exp(-2 pi i m / N)
     const float2* twist;    // exp(-i pi m / 2N)
-    double* partials;       // inverse: per-block sums of the stored voxels (may be null)
+    double* partials;       // inverse: per-block sums of the stored voxels of the rows >= sum_row0 (may be null)
+    long long sum_row0;
     int X, n_rows, left, ext, crop0;
     int prefetch_dist;      // forward: thread 0 of CTA i prefetches the rows of CTA i + prefetch_dist into the L2 (0 = off)
 };
@@ -1135,7 +1137,7 @@ template <int A_, int B_, int R_> struct XInv : LineShape<A_, B_> {
                     if ((unsigned)o2 < (unsigned)q.X) { dst[o2] = mi; acc += mi; }
                 }
             }
-            if (q.partials) psum(sm)[tid] = acc;
+            if (q.partials) psum(sm)[tid] = row >= q.sum_row0 ? acc : 0.f;
         } else if (PH == 2) {
             if (q.partials && tid < 32) {
                 double s = 0.0;

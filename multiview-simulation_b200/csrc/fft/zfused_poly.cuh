@@ -28,7 +28,13 @@
 //   level 2 : (phase s, k1 < A): B-point transform                                     -> INC A items <= G, one per group
 // so every warp works in the four transform phases; only the single inverse runs on A, then B groups.
 // Phases: requests (PSF tile by TMA, border samples, gather) | level 1 of the PSF and image phases (shared twiddles), chunk terms |
-//         level 2 of both, multiply | sum over the phases | inverse level 1, chunk scan | inverse level 2 + stores | sum plane.
+//         level 2 of both, multiply, inverse level 1 of the item's OWN products | inverse level 2 (summing the INC phases as it
+//         loads) + stores, chunk scan | sum plane.
+// The inverse is linear, so the sum over the phases may come after its first half: every level-2 thread inverts the products it
+// holds in registers (INC times the work of inverting the sum, but on all warps and without the two barriers and the two
+// low-occupancy phases -- reduce, 2-warp inverse -- that cost 16 % of the kernel's warp samples in ncu r02g).
+// The extra plane carries the sum of ALL cropped planes (ZFusedParams::sum_total): the inverse x pass then takes adjustImage's mean
+// from that plane alone (XParams::sum_row0), no bookkeeping of the kept planes here.
 #pragma once
 
 namespace mvsim {
@@ -52,7 +58,7 @@ constexpr bool zfused_poly_ok(int n, int inc)
     const int g = poly_groups(s.a, s.b, inc);
     // (two gathered items of more than 8 samples each do not fit the 96 registers of 2 x 320 threads per SM: such splits spill)
     const int r1 = (inc * s.b + g - 1) / g;
-    return g >= inc * s.a && g >= s.b && g - s.a >= 8 && g <= 40 && (r1 * s.a <= 16 || g <= 32);
+    return g >= inc * s.a && g >= s.b + 4 && g - s.a >= 8 && g <= 40 && (r1 * s.a <= 16 || g <= 32);
 }
 // PSF taps the border groups of a launch can take
 constexpr int zfused_poly_max_taps(int n, int inc)
@@ -64,7 +70,7 @@ constexpr int zfused_poly_max_taps(int n, int inc)
 // shared memory without the PSF tile (the host needs it without the template)
 constexpr int poly_smem_base(int a, int b, int inc, int t)
 {
-    const int g = poly_groups(a, b, inc), aux_rows = 4 * (g - a) + inc + 8 + b + 1;
+    const int g = poly_groups(a, b, inc), aux_rows = 4 * (g - a) + inc + 8 + 1;
     return ((2 * inc * a * (b | 1) * t + aux_rows * t + 15) / 16 * 16 + 16) * (int)sizeof(float2);
 }
 constexpr int poly_psf_tile_bytes(int k_src, int t) { return (k_src + kTmaBoxRows - 1) / kTmaBoxRows * kTmaBoxRows * t * (int)sizeof(float2); }
@@ -94,16 +100,16 @@ template <int N_, int INC_, int T_> struct ZFusedPoly {
     static constexpr int MIN_BLOCKS = 2;
     static constexpr int NCH = G - A;                     // border groups: A .. G-1 (they idle during the first inverse half)
     static constexpr int NSC = 4, QSC = (NCH + NSC - 1) / NSC;      // the chunk scan runs on NSC groups (one warp at T = 8)
-    static_assert(N_ % INC_ == 0 && A * B == M && G >= L2 && G >= B && NCH >= NSC, "unsupported split");
+    static_assert(N_ % INC_ == 0 && A * B == M && G >= L2 && G >= B + NSC && NCH >= NSC, "unsupported split");
     // shared memory (float2 elements): [E1: INC x (A x BP) x T][E2: the same][AUX rows of T][mbarrier][PSF tile (TMA)]
     static constexpr int E_ELEMS = INC * A * BP * T;
     static constexpr int AUX_CS = 0, AUX_DS = NCH, AUX_L = 2 * NCH, AUX_TS = 3 * NCH, AUX_TOT = 4 * NCH, AUX_SC = AUX_TOT + INC,
-                         AUX_KEPT = AUX_SC + 2 * NSC, AUX_B0 = AUX_KEPT + B, AUX_ROWS = AUX_B0 + 1;
+                         AUX_B0 = AUX_SC + 2 * NSC, AUX_ROWS = AUX_B0 + 1;
     static constexpr int AUX0 = 2 * E_ELEMS;
     static constexpr int BAR_ELEMS = (AUX0 + AUX_ROWS * T + 15) / 16 * 16;
     static constexpr int PSF_ELEMS0 = BAR_ELEMS + 16;
     static constexpr int SMEM_BYTES = PSF_ELEMS0 * (int)sizeof(float2);       // without the PSF tile
-    static constexpr int NPH = 7;
+    static constexpr int NPH = 5;
     using Params = ZFusedParams;
     using State = PolyState<A, B, R1>;
     static_assert(SMEM_BYTES == poly_smem_base(A, B, INC_, T_), "host-side shared memory formula out of sync");
@@ -264,7 +270,8 @@ template <int N_, int INC_, int T_> struct ZFusedPoly {
             }
         } else if (PH == 2) {
             // level 2 of the image phase (spectrum A_s[k1 + A k2] in registers; the DC bins give the sum of the whole padded line) and
-            // of the PSF phase, multiply, products to this item's row of E1 (read completely by this thread before it is rewritten)
+            // of the PSF phase, multiply; then the first half of the inverse on the item's own products: B-point inverse over k2,
+            // twiddle, into this item's row of E1 (read completely by this thread before it is rewritten)
             if (g < L2 && active) {
                 float2* row = e1 + g * BP * T + lane;               // item g = s A + k1
                 MVSIM_UNROLL
@@ -277,35 +284,38 @@ template <int N_, int INC_, int T_> struct ZFusedPoly {
                 for (int n2 = 0; n2 < B; ++n2) y[n2] = prow[n2 * T];
                 RegSel<B, -1, kPackedStrided>::run(y);
                 MVSIM_UNROLL
-                for (int k2 = 0; k2 < B; ++k2) row[k2 * T] = cmul(y[k2], st.y[k2]);
+                for (int k2 = 0; k2 < B; ++k2) y[k2] = cmul(y[k2], st.y[k2]);
+                RegSel<B, 1, kPackedStrided>::run(y);
+                const int k1 = g % A;
+                MVSIM_UNROLL
+                for (int n2 = 0; n2 < B; ++n2) row[n2 * T] = n2 == 0 ? y[0] : cmulc(y[n2], q.tw[INC * n2 * k1]);
             }
         } else if (PH == 3) {
-            // C[k1 + A k2] = sum over the phases, in place in the rows of phase 0 (the only thread that touches these INC slots)
-            if (active) {
-                for (int el = g; el < M; el += G) {
-                    const int k1 = el / B, k2 = el - k1 * B;
-                    float2* p = e1 + (k1 * BP + k2) * T + lane;
-                    float2 acc = p[0];
-                    MVSIM_UNROLL
-                    for (int s = 1; s < INC; ++s) { const float2 v = p[s * A * BP * T]; acc.x += v.x; acc.y += v.y; }
-                    p[0] = acc;
-                }
-            }
-        } else if (PH == 4) {
-            if (g < A) {
-                // inverse level 1 of the ONE M-point transform: thread k1 holds C[k1 + A k2], B-point inverse, twiddle, own row in place
+            if (g < B) {
+                // inverse level 2: thread n2 sums the INC phases as it loads, A-point inverse, and ends up with
+                // c[crop0 + INC (n2 + n1 B)]: the kept planes kz = n2 + n1 B, compacted
                 if (active) {
-                    float2* row = e1 + g * BP * T + lane;
-                    float2 y[B];
+                    float2 x[A];
+                    const float2* col = e1 + g * T + lane;
                     MVSIM_UNROLL
-                    for (int k2 = 0; k2 < B; ++k2) y[k2] = row[k2 * T];
-                    RegSel<B, 1, kPackedStrided>::run(y);
+                    for (int k1 = 0; k1 < A; ++k1) {
+                        float2 acc = col[k1 * BP * T];
+                        MVSIM_UNROLL
+                        for (int s = 1; s < INC; ++s) { const float2 v = col[(s * A + k1) * BP * T]; acc.x += v.x; acc.y += v.y; }
+                        x[k1] = acc;
+                    }
+                    RegSel<A, 1, kPackedStrided>::run(x);
+                    float2* dst = q.u + tile * q.u_tstride + outer * q.ostride + lane;
+                    const unsigned e = (unsigned)q.estride32;
                     MVSIM_UNROLL
-                    for (int n2 = 0; n2 < B; ++n2) row[n2 * T] = n2 == 0 ? y[0] : cmulc(y[n2], q.tw[INC * n2 * g]);
+                    for (int n1 = 0; n1 < A; ++n1) {
+                        const int kz = g + n1 * B;
+                        if (kz < q.n_keep) *at32(dst, (unsigned)kz, e) = x[n1];
+                    }
                 }
-            } else if (g < A + NSC && active) {
+            } else if (g >= G - NSC && active) {
                 // chunk scan, quarter i: sum_c (CS_0 + .. + CS_{c-1}) DS_c + L_c and the tail sums over the chunks [i QSC, (i + 1) QSC)
-                const int i = g - A, c0 = i * QSC, c1 = (i + 1) * QSC < NCH ? (i + 1) * QSC : NCH;
+                const int i = g - (G - NSC), c0 = i * QSC, c1 = (i + 1) * QSC < NCH ? (i + 1) * QSC : NCH;
                 float2 pre = make_float2(0.f, 0.f);
                 for (int k = 0; k < c0; ++k) { const float2 v = aux[(AUX_CS + k) * T]; pre.x += v.x; pre.y += v.y; }
                 float2 dot = make_float2(0.f, 0.f), ts = make_float2(0.f, 0.f);
@@ -320,29 +330,11 @@ template <int N_, int INC_, int T_> struct ZFusedPoly {
                 aux[(AUX_SC + i) * T] = dot;
                 aux[(AUX_SC + NSC + i) * T] = ts;
             }
-        } else if (PH == 5) {
-            if (g < B && active) {
-                // inverse level 2: thread n2 ends up with c[crop0 + INC (n2 + n1 B)]: the kept planes kz = n2 + n1 B, compacted
-                float2 x[A];
-                const float2* col = e1 + g * T + lane;
-                MVSIM_UNROLL
-                for (int k1 = 0; k1 < A; ++k1) x[k1] = col[k1 * BP * T];
-                RegSel<A, 1, kPackedStrided>::run(x);
-                float2* dst = q.u + tile * q.u_tstride + outer * q.ostride + lane;
-                const unsigned e = (unsigned)q.estride32;
-                float2 ks = make_float2(0.f, 0.f);
-                MVSIM_UNROLL
-                for (int n1 = 0; n1 < A; ++n1) {
-                    const int kz = g + n1 * B;
-                    if (kz < q.n_keep) { *at32(dst, (unsigned)kz, e) = x[n1]; ks.x += x[n1].x; ks.y += x[n1].y; }
-                }
-                aux[(AUX_KEPT + g) * T] = ks;
-            }
         } else {
-            // plane n_keep: N (B0 sum_{n < n_src} a'[n] + dot) - kept planes  (the z transforms are unnormalised: factor N as in the
-            // spectral kernels; the kept planes carry it through beta's factor INC and the unnormalised M-point inverse)
+            // plane n_keep: N (B0 sum_{n < n_src} a'[n] + dot), the sum of ALL cropped planes (the z transforms are unnormalised: factor N
+            // as in the spectral kernels; the kept planes carry it through beta's factor INC and the unnormalised M-point inverse)
             if (g == 0 && active) {
-                float2 d = make_float2(0.f, 0.f), t = make_float2(0.f, 0.f), tot = make_float2(0.f, 0.f), kept = make_float2(0.f, 0.f);
+                float2 d = make_float2(0.f, 0.f), t = make_float2(0.f, 0.f), tot = make_float2(0.f, 0.f);
                 MVSIM_UNROLL
                 for (int j = 0; j < NSC; ++j) {
                     const float2 a = aux[(AUX_SC + j) * T], b = aux[(AUX_SC + NSC + j) * T];
@@ -350,13 +342,10 @@ template <int N_, int INC_, int T_> struct ZFusedPoly {
                 }
                 MVSIM_UNROLL
                 for (int s = 0; s < INC; ++s) { const float2 v = aux[(AUX_TOT + s) * T]; tot.x += v.x; tot.y += v.y; }
-                MVSIM_UNROLL
-                for (int j = 0; j < B; ++j) { const float2 v = aux[(AUX_KEPT + j) * T]; kept.x += v.x; kept.y += v.y; }
                 const float2 b0 = aux[AUX_B0 * T];
                 const float2 sa = make_float2(tot.x - t.x, tot.y - t.y);
                 const float2 all = make_float2(b0.x * sa.x - b0.y * sa.y + d.x, b0.x * sa.y + b0.y * sa.x + d.y);
-                q.u[tile * q.u_tstride + outer * q.ostride + lane + q.n_keep * q.estride] =
-                    make_float2((float)N * all.x - kept.x, (float)N * all.y - kept.y);
+                q.u[tile * q.u_tstride + outer * q.ostride + lane + q.n_keep * q.estride] = make_float2((float)N * all.x, (float)N * all.y);
             }
         }
     }

@@ -7,6 +7,8 @@
 //   extract    S/SimulateMultiViewDataset.java:195-231 + Poisson S/Tools.java:73-86
 // All of them are HBM-bound; threads map to x (the contiguous axis) so every warp access is a
 // full 128-byte line (float4 where the row length allows).
+#include <stdlib.h>
+
 #include <type_traits>
 
 #include "ctx.h"
@@ -250,6 +252,115 @@ template <int VEC, int U, bool IDX32> __global__ void __launch_bounds__(128) rot
     for (; y >= 0; --y) *reinterpret_cast<V*>(out + (Off)(obase + sy * (Off)y)) = *reinterpret_cast<V*>(zero);
 }
 
+// The same march with the tap ADDRESSES tabulated: per output row (y, z) the table holds the four element offsets of the source rows
+// (iy, iz), (iy+1, iz), (iy+1, iz+1), (iy, iz+1) and the four weights; a tap outside the volume gets weight 0 and the offset of row
+// (0, 0), so the march issues four unconditional float4 loads per row and spends no instruction on bounds (ncu r02c: half of the
+// kernel's cycles issue, a quarter of its instructions were offsets, bound predicates and the zero fill of masked taps).  The blend
+// fmul(t, 0) = 0 of such a tap equals the blend of the zero the bounds check substituted (finite source data), so the result is
+// bit-identical to rotate_attenuate_kernel.  Volumes below 2^31 voxels, X % 4 == 0.
+struct __align__(16) RowTapsOff { unsigned o00, o10, o11, o01; float w00, w10, w11, w01; };
+
+__global__ void __launch_bounds__(256) rotate_rowtable_off_kernel(RowTapsOff* __restrict__ tab, int X, int Y, int Z, int z0, int Zl, Affine a)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)Y * Zl) return;
+    const int y = (int)(i % Y), z = z0 + (int)(i / Y);
+    const double ly = (double)y, lz = (double)z;
+    const double py = __dadd_rn(__dadd_rn(__dmul_rn(ly, a.m[5]), __dmul_rn(lz, a.m[6])), a.m[7]);
+    const double pz = __dadd_rn(__dadd_rn(__dmul_rn(ly, a.m[9]), __dmul_rn(lz, a.m[10])), a.m[11]);
+    const double fy = floor(py), fz = floor(pz);
+    const double wy = py - fy, wz = pz - fz;
+    const double wyi = 1.0 - wy, wzi = 1.0 - wz;
+    const int iy = (int)fmax(fmin(fy, 2.0e9), -2.0e9), iz = (int)fmax(fmin(fz, 2.0e9), -2.0e9);
+    const bool y0 = (unsigned)iy < (unsigned)Y, y1 = (unsigned)(iy + 1) < (unsigned)Y;
+    const bool z0b = (unsigned)iz < (unsigned)Z, z1 = (unsigned)(iz + 1) < (unsigned)Z;
+    const unsigned sy = (unsigned)X, sz = (unsigned)X * (unsigned)Y;
+    RowTapsOff t;
+    t.o00 = (y0 && z0b) ? sy * (unsigned)iy + sz * (unsigned)iz : 0u;
+    t.o10 = (y1 && z0b) ? sy * (unsigned)(iy + 1) + sz * (unsigned)iz : 0u;
+    t.o11 = (y1 && z1) ? sy * (unsigned)(iy + 1) + sz * (unsigned)(iz + 1) : 0u;
+    t.o01 = (y0 && z1) ? sy * (unsigned)iy + sz * (unsigned)(iz + 1) : 0u;
+    t.w00 = (y0 && z0b) ? (float)(wyi * wzi) : 0.f;
+    t.w10 = (y1 && z0b) ? (float)(wy * wzi) : 0.f;
+    t.w11 = (y1 && z1) ? (float)(wy * wz) : 0.f;
+    t.w01 = (y0 && z1) ? (float)(wyi * wz) : 0.f;
+    tab[i] = t;
+}
+
+template <int U> __global__ void __launch_bounds__(128) rotate_attenuate_off_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                                                    const RowTapsOff* __restrict__ tab, int X, int Y,
+                                                                                    double delta, int steps, int Zl)
+{
+    const int XV = X / 4;
+    const long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= (long long)XV * Zl) return;
+    const int x0 = (int)(col % XV) * 4, z = (int)(col / XV);      // z: local plane
+    const unsigned sy = (unsigned)X;
+    const RowTapsOff* trow = tab + (long long)Y * z;
+    const float* src = in + x0;
+    float* dst = out + (size_t)x0 + (size_t)X * Y * z;
+    double n[4] = { 1.0, 1.0, 1.0, 1.0 };
+    int y = Y - 1, s = 0;
+    RowTapsOff tp[U];
+    if (steps >= U) {
+#pragma unroll
+        for (int j = 0; j < U; ++j) tp[j] = trow[y - j];
+    }
+    for (; s + U <= steps; s += U, y -= U) {
+        float4 t00[U], t10[U], t11[U], t01[U];
+        RowTapsOff tn[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const int yn = y - U - j;
+            tn[j] = trow[yn > 0 ? yn : 0];
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            t00[j] = __ldg(reinterpret_cast<const float4*>(src + tp[j].o00));
+            t10[j] = __ldg(reinterpret_cast<const float4*>(src + tp[j].o10));
+            t11[j] = __ldg(reinterpret_cast<const float4*>(src + tp[j].o11));
+            t01[j] = __ldg(reinterpret_cast<const float4*>(src + tp[j].o01));
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const float a00[4] = { t00[j].x, t00[j].y, t00[j].z, t00[j].w }, a10[4] = { t10[j].x, t10[j].y, t10[j].z, t10[j].w };
+            const float a11[4] = { t11[j].x, t11[j].y, t11[j].z, t11[j].w }, a01[4] = { t01[j].x, t01[j].y, t01[j].z, t01[j].w };
+            float res[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a00[i], tp[j].w00), __fmul_rn(a10[i], tp[j].w10)),
+                                                    __fmul_rn(a11[i], tp[j].w11)), __fmul_rn(a01[i], tp[j].w01));
+                const double dv = (double)v;
+                const double phi = __dmul_rn(__dmul_rn(dv, delta), n[i]);
+                n[i] = fmax(__dsub_rn(n[i], phi), 0.0);
+                res[i] = (float)__dmul_rn(dv, n[i]);
+            }
+            *reinterpret_cast<float4*>(dst + sy * (unsigned)(y - j)) = make_float4(res[0], res[1], res[2], res[3]);
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) tp[j] = tn[j];
+    }
+    for (; s < steps; ++s, --y) {
+        const RowTapsOff t = trow[y];
+        const float4 b00 = __ldg(reinterpret_cast<const float4*>(src + t.o00)), b10 = __ldg(reinterpret_cast<const float4*>(src + t.o10));
+        const float4 b11 = __ldg(reinterpret_cast<const float4*>(src + t.o11)), b01 = __ldg(reinterpret_cast<const float4*>(src + t.o01));
+        const float a00[4] = { b00.x, b00.y, b00.z, b00.w }, a10[4] = { b10.x, b10.y, b10.z, b10.w };
+        const float a11[4] = { b11.x, b11.y, b11.z, b11.w }, a01[4] = { b01.x, b01.y, b01.z, b01.w };
+        float res[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float v = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a00[i], t.w00), __fmul_rn(a10[i], t.w10)), __fmul_rn(a11[i], t.w11)),
+                                      __fmul_rn(a01[i], t.w01));
+            const double dv = (double)v;
+            const double phi = __dmul_rn(__dmul_rn(dv, delta), n[i]);
+            n[i] = fmax(__dsub_rn(n[i], phi), 0.0);
+            res[i] = (float)__dmul_rn(dv, n[i]);
+        }
+        *reinterpret_cast<float4*>(dst + sy * (unsigned)y) = make_float4(res[0], res[1], res[2], res[3]);
+    }
+    for (; y >= 0; --y) *reinterpret_cast<float4*>(dst + sy * (unsigned)y) = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
 // returns MVSIM_EUNSUPPORTED when the fused path does not apply (caller falls back to the two kernels)
 int k_rotate_attenuate(mvsim_ctx* ctx, const float* in, float* out, const int64_t dims[3], int axis, const double inv[12], double delta, int steps,
                        int64_t z0, int64_t z_local)
@@ -261,11 +372,24 @@ int k_rotate_attenuate(mvsim_ctx* ctx, const float* in, float* out, const int64_
     if (!x_identity) return MVSIM_EUNSUPPORTED;
     Affine a;
     for (int i = 0; i < 12; ++i) a.m[i] = inv[i];
+    const bool aligned = (reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) % 16 == 0;
+    static const bool tab_offsets = getenv("MVSIM_ROT_OFFSETS") == nullptr || atoi(getenv("MVSIM_ROT_OFFSETS")) != 0;   // A/B knob
+    if (tab_offsets && X % 4 == 0 && aligned && (double)X * Y * Z < 2147483648.0) {
+        RowTapsOff* tabo = nullptr;
+        MVSIM_TRY(dev_alloc(ctx, (void**)&tabo, sizeof(RowTapsOff) * (size_t)Y * Zl));
+        rotate_rowtable_off_kernel<<<blocks_for((size_t)Y * Zl, 256), 256, 0, ctx->stream>>>(tabo, X, Y, Z, zfirst, Zl, a);
+        ctx->launches++;
+        rotate_attenuate_off_kernel<3><<<blocks_for((size_t)(X / 4) * Zl, 128), 128, 0, ctx->stream>>>(in, out, tabo, X, Y, delta, steps, Zl);
+        ctx->launches++;
+        cudaError_t eo = cudaGetLastError();
+        dev_free(ctx, tabo);
+        if (eo != cudaSuccess) return cuda_fail(ctx, eo, "rotate_attenuate_off_kernel");
+        return MVSIM_OK;
+    }
     RowTaps* tab = nullptr;
     MVSIM_TRY(dev_alloc(ctx, (void**)&tab, sizeof(RowTaps) * (size_t)Y * Zl));
     rotate_rowtable_kernel<<<blocks_for((size_t)Y * Zl, 256), 256, 0, ctx->stream>>>(tab, Y, zfirst, Zl, a);
     ctx->launches++;
-    const bool aligned = (reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) % 16 == 0;
     // the march along y is sequential per column, so the grid is small (X*Z/VEC threads): pick the widest
     // vector whose single wave still fits the machine (config 3: 131072 threads x float4, 2 rows in flight)
     const bool idx32 = (double)X * Y * Z < 2147483648.0;

@@ -155,6 +155,10 @@ extern "C" int emu_plan(const int64_t dims[3], const int64_t kdims[3], int out[1
     return 0;
 }
 
+static int last_sum_plane_is_total = 0;
+// 1: the extra plane of the last emu_convolve(keep_inc > 1) carries the sum of ALL cropped planes (polyphase kernel), 0: of the dropped ones
+extern "C" int emu_last_sum_plane_is_total() { return last_sum_plane_is_total; }
+
 namespace {
 
 struct RankState {
@@ -211,6 +215,7 @@ extern "C" int emu_convolve(const float* img, const int64_t dims[3], const float
         }
     const int planes = conv_out_planes(pl, rk[0].g, keep_inc);
     const size_t chunk = rk[0].u2.size() / world;
+    bool sum_total = false;
     for (int b = 0; b < pl.y_blocks; ++b) {
         if (world > 1 && p2p)
             for (int r = 0; r < world; ++r) poison(rk[r].ex);     // the y passes of ALL ranks must fill every z-pass buffer
@@ -223,7 +228,7 @@ extern "C" int emu_convolve(const float* img, const int64_t dims[3], const float
         if (world > 1)
             for (int r = 0; r < world; ++r) poison(rk[r].u2);     // everything the inverse reads must arrive again
         for (int r = 0; r < world; ++r)
-            if ((err = conv_middle_z(l, pl, rk[r].g, rk[r].ws, rk[r].ws.ex, keep_inc))) return err;
+            if ((err = conv_middle_z(l, pl, rk[r].g, rk[r].ws, rk[r].ws.ex, keep_inc, &sum_total))) return err;
         if (world > 1 && !p2p)
             for (int s = 0; s < world; ++s)
                 for (int d = 0; d < world; ++d)
@@ -235,10 +240,11 @@ extern "C" int emu_convolve(const float* img, const int64_t dims[3], const float
     for (int r = 0; r < world; ++r) {
         std::vector<double> partials(l.x_blocks(pl.sx, pl.dims[1] * planes, true), 0.0);
         float* o = out + (size_t)(world > 1 ? rk[r].g.z0 : 0) * pl.dims[1] * pl.dims[0];
-        if ((err = conv_inverse_x(l, pl, rk[r].ws, o, partials.data(), planes))) return err;
+        if ((err = conv_inverse_x(l, pl, rk[r].ws, o, partials.data(), planes, sum_total))) return err;
         for (double v : partials) total += v;
     }
     if (sum_out) *sum_out = total;
+    last_sum_plane_is_total = sum_total ? 1 : 0;
     return 0;
 }
 

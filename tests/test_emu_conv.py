@@ -225,11 +225,15 @@ def test_polyphase_fused_z_pass(emu, oracle, monkeypatch, psf_spectrum_mode, req
     kept = ref[::inc]
     nk = kept.shape[0]
     out, s = _run(emu, vol, psf, keep_inc=inc, planes=nk + 1)
+    assert rel_err(out[:nk], kept) < 5e-6
+    total = ref.astype(np.float64).sum(axis=0)
     if "on-the-fly" in request.node.name:
         assert emu.emu_polyphase_launches() == before + 1       # the polyphase kernel really ran
-    assert rel_err(out[:nk], kept) < 5e-6
-    dropped = ref.astype(np.float64).sum(axis=0) - kept.astype(np.float64).sum(axis=0)
-    assert rel_err(out[nk], dropped.astype(np.float32)) < 3e-5
+        assert emu.emu_last_sum_plane_is_total() == 1            # ... and its extra plane is the sum of ALL cropped planes
+        assert rel_err(out[nk], total.astype(np.float32)) < 3e-5
+    else:
+        assert emu.emu_last_sum_plane_is_total() == 0
+        assert rel_err(out[nk], (total - kept.astype(np.float64).sum(axis=0)).astype(np.float32)) < 3e-5
     assert s == pytest.approx(float(ref.astype(np.float64).sum()), rel=3e-6)
 
 
