@@ -554,12 +554,13 @@ def run_ours(args, rank, world, local_rank):
     b_fused_model = 8 * N + 9 * S_model + 8 * O
     b_stage_model = 32 * N + 11 * S_model + 8 * O
     view_ms = ms_step / nv
-    roofline = {"bound": "hbm", "kernel": "fft_zfused (z-forward * PSF spectrum * z-inverse of the kept planes, in place; the PSF's z transform included)",
+    roofline = {"bound": "hbm", "kernel": ("fft_zfused (ZFusedPoly at config 3: the kept planes as inc cyclic convolutions of Nz / inc points -- forward transforms of the image and "
+                           "PSF phases, multiply-add, one inverse -- plus the sum plane, in place)"),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": peak_src, "bytes_per_launch": bytes_pruned,
                 "bytes_basis": ("compulsory bytes of the pruned pass per view: 8 B x KXc x Ny x (Z planes read + KZ planes of the PSF partial spectrum read "
                                 "+ kept planes and one sum plane written); equals the ncu dram bytes. The kernel is FP32-issue bound, not HBM bound "
-                                "(three 640-point transforms per line on 4 B of traffic per point; DESIGN.md section 4.1)"),
+                                "(ten 128-point forward transforms and one inverse per line on 4 B of traffic per point; DESIGN.md section 4.1)"),
                 "bytes_per_launch_model_3S": bytes_model, "achieved_model_3S": achieved_model, "frac_model_3S": achieved_model / peak,
                 "model_3S_basis": "SURVEY 8(d): read S + PSF spectrum S + write S for an unpruned fused z pass; model-equivalent throughput, not bandwidth",
                 "ms_per_launch": per_launch_ms, "launches_timed": z_n,

@@ -16,12 +16,14 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 # MVSIM_PACKED_FFT=0 builds the butterflies on scalar FADD/FFMA instead of Blackwell's packed FP32x2 pipe (A/B measurements)
 PACKED = os.environ.get("MVSIM_PACKED_FFT", "1") != "0"
-OBJ = os.path.join(ROOT, "build" if PACKED else "build_scalar")
-LIB = os.path.join(PKG, "libmvsim.so" if PACKED else "libmvsim_scalar.so")
+# MVSIM_PACKED_X=1 builds the x passes on the packed pipe too (A/B measurements: libmvsim_px.so, loaded with MVSIM_LIB=...)
+PACKED_X = os.environ.get("MVSIM_PACKED_X", "0") == "1"
+OBJ = os.path.join(ROOT, ("build_px" if PACKED_X else "build") if PACKED else "build_scalar")
+LIB = os.path.join(PKG, ("libmvsim_px.so" if PACKED_X else "libmvsim.so") if PACKED else "libmvsim_scalar.so")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", CSRC, "-I", os.path.join(ROOT, "include"),
-         f"-DMVSIM_PACKED_FFT={1 if PACKED else 0}"]
+         f"-DMVSIM_PACKED_FFT={1 if PACKED else 0}", f"-DMVSIM_PACKED_X={1 if PACKED_X else 0}"]
 
 UNITS = [("stages", "stages.cu", []), ("phantom", "phantom.cu", []), ("conv", "conv.cu", []), ("capi", "capi.cu", [])] + \
         [(f"fft_g{g}_t{t}", os.path.join("fft", "fft_group.cu"), [f"-DMVSIM_GROUP={g}", f"-DMVSIM_LANES={t}"])

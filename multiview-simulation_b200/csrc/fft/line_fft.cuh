@@ -33,6 +33,12 @@ namespace mvsim {
 template <int N, int DIR, bool PK> struct RegSel { static MVSIM_HD void run(float2 (&x)[N]) { RegFFT<N, DIR>::run(x); } };
 template <int N, int DIR> struct RegSel<N, DIR, true> { static MVSIM_HD void run(float2 (&x)[N]) { RegFFTP<N, DIR>::run(x); } };
 constexpr bool kPackedStrided = MVSIM_PACKED_FFT != 0;
+#ifndef MVSIM_PACKED_X
+#define MVSIM_PACKED_X 0
+#endif
+// x passes on the packed pipe too (A/B builds, MVSIM_PACKED_X=1 python build.py -> libmvsim_px.so).  Measured again in round 2 with the
+// 6-row forward CTAs (96 registers): forward 0.918 -> 0.967 ms (264 bytes of spills), inverse 0.252 -> 0.249 ms: stays off
+constexpr bool kPackedX = MVSIM_PACKED_FFT != 0 && MVSIM_PACKED_X != 0;
 // forward transform of x[0..K) with x[K..N) == 0 (not read), K = RegFFTPZ<N>::K: generated with the zero terms removed
 template <int N, bool PK> struct RegSelZ {
     static constexpr int K = RegFFTPZ<N>::K;
@@ -1063,12 +1069,12 @@ template <int A_, int B_, int R_> struct XFwd : LineShape<A_, B_> {
                     const float2 t = q.twist[p + n1 * B];
                     x[n1] = make_float2(st.a[n1] * t.x + st.b[n1] * t.y, st.a[n1] * t.y - st.b[n1] * t.x);   // (a - i b) * t
                 }
-                fwd_first<A, B>(p, x, sm, r * S::ELEMS, 1, q.tw);
+                fwd_first<A, B, kPackedX>(p, x, sm, r * S::ELEMS, 1, q.tw);
             }
         } else {
             if (p < A && active) {
                 float2 y[B];
-                fwd_second<A, B>(p, y, sm, r * S::ELEMS, 1);
+                fwd_second<A, B, kPackedX>(p, y, sm, r * S::ELEMS, 1);
                 float2* dst = q.cout + row * N;
                 MVSIM_UNROLL
                 for (int k2 = 0; k2 < B; ++k2) dst[p + A * k2] = y[k2];
@@ -1117,13 +1123,13 @@ template <int A_, int B_, int R_> struct XInv : LineShape<A_, B_> {
                 const float2* src = q.cin + row * N;
                 MVSIM_UNROLL
                 for (int k2 = 0; k2 < B; ++k2) y[k2] = src[p + A * k2];
-                inv_first<A, B>(p, y, sm, r * S::ELEMS, 1, q.tw);
+                inv_first<A, B, kPackedX>(p, y, sm, r * S::ELEMS, 1, q.tw);
             }
         } else if (PH == 1) {
             float acc = 0.f;
             if (p < B && active) {
                 float2 x[A];
-                inv_second<A, B>(p, x, sm, r * S::ELEMS, 1);
+                inv_second<A, B, kPackedX>(p, x, sm, r * S::ELEMS, 1);
                 float* dst = q.rout + row * q.X;
                 MVSIM_UNROLL
                 for (int n1 = 0; n1 < A; ++n1) {
