@@ -47,7 +47,7 @@ template <class L> int conv_psf_spectrum(L& l, const ConvPlan& pl, const SlabGeo
     const long long kxc = pl.kxc(), T = l.lanes, ny = pl.sy.n;
     XParams xp = {};
     xp.rin = psf; xp.cout = ws.p1; xp.tw = ws.tw_x; xp.twist = ws.twist_x;
-    xp.X = pl.kdims[0]; xp.n_rows = pl.kdims[1] * pl.kdims[2]; xp.left = 0; xp.ext = EXT_ZERO;
+    xp.X = pl.kdims[0]; xp.n_rows = pl.kdims[1] * pl.kdims[2]; xp.left = 0; xp.ext = EXT_ZERO; xp.esz = (unsigned)sizeof(float);
     int err = l.launch_x(false, pl.sx, xp);
     if (err) return err;
 
@@ -77,7 +77,7 @@ template <class L> int conv_forward_x(L& l, const ConvPlan& pl, const SlabGeom& 
     XParams xp = {};
     xp.rin = img; xp.cout = ws.u1; xp.tw = ws.tw_x; xp.twist = ws.twist_x;
     xp.X = pl.dims[0]; xp.n_rows = pl.dims[1] * g.z_local; xp.left = pl.left[0];
-    xp.ext = mirror_mode(2 * pl.sx.n, pl.left[0], pl.dims[0]);
+    xp.ext = mirror_mode(2 * pl.sx.n, pl.left[0], pl.dims[0]); xp.esz = (unsigned)sizeof(float);
     return l.launch_x(false, pl.sx, xp);
 }
 
@@ -210,7 +210,7 @@ template <class L> int conv_inverse_x(L& l, const ConvPlan& pl, const ConvWorksp
     XParams ix = {};
     ix.cin = ws.u1o; ix.rout = out; ix.tw = ws.tw_x; ix.twist = ws.twist_x; ix.partials = partials;
     ix.sum_row0 = sum_last_plane_only ? (long long)pl.dims[1] * (planes - 1) : 0;
-    ix.X = pl.dims[0]; ix.n_rows = pl.dims[1] * planes; ix.crop0 = pl.crop0[0];
+    ix.X = pl.dims[0]; ix.n_rows = pl.dims[1] * planes; ix.crop0 = pl.crop0[0]; ix.esz = (unsigned)sizeof(float);
     return l.launch_x(true, pl.sx, ix);
 }
 

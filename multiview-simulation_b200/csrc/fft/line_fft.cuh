@@ -997,7 +997,16 @@ struct XParams {
     long long sum_row0;
     int X, n_rows, left, ext, crop0;
     int prefetch_dist;      // forward: thread 0 of CTA i prefetches the rows of CTA i + prefetch_dist into the L2 (0 = off)
+    unsigned esz;           // sizeof(float) as a RUN-TIME value: element addresses of the gather become one widening multiply-add
+                            // (IMAD.WIDE.U32) instead of the shift + add with carry pair a constant scale compiles to (144 of the
+                            // forward pass's 450 gather instructions per warp were LEA, ncu r02j)
 };
+
+// element i of a real row through the run-time element size (see XParams::esz)
+MVSIM_HD const float* rowat(const float* base, int i, unsigned esz)
+{
+    return reinterpret_cast<const float*>(reinterpret_cast<const char*>(base) + (unsigned long long)(unsigned)i * (unsigned long long)esz);
+}
 
 template <int A> struct XFwdState { float a[A], b[A]; };
 
@@ -1043,7 +1052,7 @@ template <int A_, int B_, int R_> struct XFwd : LineShape<A_, B_> {
                         ib[n1] = mirror_once(p + n1 * B + N - q.left, q.X);
                     }
                     MVSIM_UNROLL
-                    for (int n1 = 0; n1 < A; ++n1) { st.a[n1] = src[ia[n1]]; st.b[n1] = src[ib[n1]]; }
+                    for (int n1 = 0; n1 < A; ++n1) { st.a[n1] = *rowat(src, ia[n1], q.esz); st.b[n1] = *rowat(src, ib[n1], q.esz); }
                 } else if (q.ext == EXT_ZERO) {
                     MVSIM_UNROLL
                     for (int n1 = 0; n1 < A; ++n1) {
