@@ -284,7 +284,7 @@ template <int A_, int B_, int T_> struct StridedFwd : LineShape<A_, B_> {
                 if (q.out_e32) {
                     MVSIM_UNROLL
                     for (int k2 = 0; k2 < B; ++k2)
-                        dst[(unsigned)(p + A * k2) * q.out_e32] = make_float2(y[k2].x * q.scale, y[k2].y * q.scale);
+                        *at32(dst, (unsigned)(p + A * k2), q.out_e32) = make_float2(y[k2].x * q.scale, y[k2].y * q.scale);
                 } else {
                     MVSIM_UNROLL
                     for (int k2 = 0; k2 < B; ++k2)
@@ -325,7 +325,7 @@ template <int A_, int B_, int T_> struct StridedInv : LineShape<A_, B_> {
                 const float2* src = q.in + tin * q.in_tstride + outer * q.in_ostride + lane;
                 if (q.in_e32) {
                     MVSIM_UNROLL
-                    for (int k2 = 0; k2 < B; ++k2) y[k2] = src[(unsigned)(p + A * k2) * q.in_e32];
+                    for (int k2 = 0; k2 < B; ++k2) y[k2] = *at32(src, (unsigned)(p + A * k2), q.in_e32);
                 } else {
                     MVSIM_UNROLL
                     for (int k2 = 0; k2 < B; ++k2) y[k2] = src[(p + A * k2) * q.in_estride];
@@ -1139,7 +1139,9 @@ template <int A_, int B_, int R_> struct XInv : LineShape<A_, B_> {
             if (p < B && active) {
                 float2 x[A];
                 inv_second<A, B, kPackedX>(p, x, sm, r * S::ELEMS, 1);
-                float* dst = q.rout + row * q.X;
+                // one base pointer per thread (output index of n1 = 0), compile-time offsets n1 B and N + n1 B from it: the stores
+                // carry immediate offsets instead of one address computation each
+                float* d1 = q.rout + (row * q.X + (p - q.crop0));
                 MVSIM_UNROLL
                 for (int n1 = 0; n1 < A; ++n1) {
                     const int m = p + n1 * B;
@@ -1148,8 +1150,8 @@ template <int A_, int B_, int R_> struct XInv : LineShape<A_, B_> {
                     const float re = x[n1].x * t.x + x[n1].y * t.y;
                     const float mi = x[n1].x * t.y - x[n1].y * t.x;
                     const int o1 = m - q.crop0, o2 = m + N - q.crop0;
-                    if ((unsigned)o1 < (unsigned)q.X) { dst[o1] = re; acc += re; }
-                    if ((unsigned)o2 < (unsigned)q.X) { dst[o2] = mi; acc += mi; }
+                    if ((unsigned)o1 < (unsigned)q.X) { d1[n1 * B] = re; acc += re; }
+                    if ((unsigned)o2 < (unsigned)q.X) { d1[N + n1 * B] = mi; acc += mi; }
                 }
             }
             if (q.partials) psum(sm)[tid] = row >= q.sum_row0 ? acc : 0.f;

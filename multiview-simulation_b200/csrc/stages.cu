@@ -721,8 +721,14 @@ template <bool VEC4, int G> __global__ void __launch_bounds__(kWarpSamplerThread
         for (int j = 0; j < 4; ++j) v[k][j] = 0.f;
         if (valid[k]) {
             if (VEC4) {
-                const long long cz = i0 / plane, r = i0 - cz * plane;
-                const float4 t = __ldg(reinterpret_cast<const float4*>(in + (cz * inc + in_plane0) * plane + r));
+                // inc == 1 (the whole-view call hands over the kept slices compacted): output voxel i reads input voxel
+                // i + in_plane0 * plane -- no 64-bit division (a library call of ~60 instructions per group, ncu r02j)
+                long long src_i = i0 + in_plane0 * plane;
+                if (inc != 1) {
+                    const long long cz = i0 / plane, r = i0 - cz * plane;
+                    src_i = (cz * inc + in_plane0) * plane + r;
+                }
+                const float4 t = __ldg(reinterpret_cast<const float4*>(in + src_i));
                 v[k][0] = t.x; v[k][1] = t.y; v[k][2] = t.z; v[k][3] = t.w;
             } else {
 #pragma unroll
