@@ -437,7 +437,12 @@ static int ctx_create(int device, bool own, void* cuda_stream, mvsim_ctx** out)
     ctx->h_hash = nullptr;
     ctx->count_transport = 0;
     ctx->host_threads = 0;
-    ctx->z_kernel = 0;
+    {
+        // A/B runs without touching the caller: MVSIM_Z_KERNEL=<0..3> presets MVSIM_OPT_Z_KERNEL
+        const char* zk = getenv("MVSIM_Z_KERNEL");
+        const int v = zk ? atoi(zk) : 0;
+        ctx->z_kernel = (v >= 0 && v <= 3) ? v : 0;
+    }
     ctx->widen_pool = nullptr;
     ctx->profiling = false;
     memset(ctx->acc_ms, 0, sizeof(ctx->acc_ms));

@@ -170,12 +170,12 @@ struct CudaLauncher {
         const unsigned gx = q.swap_grid ? (unsigned)n_outer : tiles, gy = q.swap_grid ? tiles : (unsigned)n_outer;
         return finish(fft_launch(inverse ? FFT_SINV : FFT_SFWD, lanes, s.n, &q, gx, gy, ctx->stream), "strided pass");
     }
-    // Decimated inverse of the whole-view fused z pass (ZFusedDec in fft/line_fft.cuh): the default wherever the planner's split
-    // allows it (measured 2.49 -> 2.13 ms at config 3).  MVSIM_Z_DECIMATE=0 selects the full inverse (ZFusedOTF) for A/B runs.
+    // Decimated inverse of the whole-view fused z pass (ZFusedDec in fft/line_fft.cuh): used wherever the planner's split allows it
+    // and the polyphase kernel does not apply (measured 2.49 -> 2.13 ms at config 3 against ZFusedOTF).  MVSIM_OPT_Z_KERNEL = 2 (or
+    // MVSIM_Z_KERNEL=2 in the environment) selects the full inverse for A/B runs.
     bool z_decimate(const FftSize& s) const
     {
-        static const bool on = MVSIM_PACKED_FFT != 0 && env_int("MVSIM_Z_DECIMATE", 1) != 0;
-        return on && ctx->z_kernel != 2 && s.n >= kDecMinLine && s.n <= kDecMaxLine;
+        return MVSIM_PACKED_FFT != 0 && ctx->z_kernel != 2 && s.n >= kDecMinLine && s.n <= kDecMaxLine;
     }
     int launch_zfused_dec(const FftSize& s, const ZFusedParams& q0, int n_tiles, int n_outer, int inc)
     {
@@ -194,9 +194,8 @@ struct CudaLauncher {
     // Polyphase form of the whole-view fused z pass (ZFusedPoly in fft/zfused_poly.cuh).
     bool z_polyphase(const FftSize& s, int inc, int k_src) const
     {
-        // (auto = the measured winner at BASELINE config 3, see kPolyphaseDefault; MVSIM_Z_POLY=0/1 overrides it for A/B runs)
-        static const bool dflt = MVSIM_PACKED_FFT != 0 && env_int("MVSIM_Z_POLY", kPolyphaseDefault ? 1 : 0) != 0;
-        const bool want = ctx->z_kernel == 3 || (ctx->z_kernel == 0 && dflt);
+        // (auto = the measured winner at BASELINE config 3, see kPolyphaseDefault)
+        const bool want = ctx->z_kernel == 3 || (ctx->z_kernel == 0 && kPolyphaseDefault);
         if (!want || MVSIM_PACKED_FFT == 0 || s.n < kDecMinLine || s.n > kDecMaxLine) return false;
         return zfused_poly_fits(s.n, inc, lanes, k_src);
     }

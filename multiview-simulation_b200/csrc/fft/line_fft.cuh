@@ -720,7 +720,7 @@ template <int A_, int B_, int T_> struct ZFusedOTF : ZFused<A_, B_, T_> {
 
 // ==============================================================================================
 // Fused z pass of the whole-view call with a DECIMATED inverse (default wherever zfused_dec_ok() holds; measured on B200,
-// config 3: 2.49 -> 2.13 ms against ZFusedOTF, profiles/r02_experiments.txt; MVSIM_Z_DECIMATE=0 switches back for A/B runs).
+// config 3: 2.49 -> 2.13 ms against ZFusedOTF, profiles/r02_experiments.txt; MVSIM_Z_KERNEL=2 switches back for A/B runs).
 // extractSlices keeps z = 0, INC, 2 INC, ... (:206), i.e. the
 // padded outputs n = crop0 + INC kz.  With the split n = n1 B + n2 and INC | B these are exactly the columns
 // n2 = r (mod INC), r = crop0 mod INC, of the exchange, so

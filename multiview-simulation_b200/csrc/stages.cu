@@ -383,8 +383,8 @@ int k_rotate_attenuate(mvsim_ctx* ctx, const float* in, float* out, const int64_
     Affine a;
     for (int i = 0; i < 12; ++i) a.m[i] = inv[i];
     const bool aligned = (reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) % 16 == 0;
-    static const bool tab_offsets = getenv("MVSIM_ROT_OFFSETS") == nullptr || atoi(getenv("MVSIM_ROT_OFFSETS")) != 0;   // A/B knob
-    if (tab_offsets && X % 4 == 0 && aligned && (double)X * Y * Z < 2147483648.0) {
+    // tabulated tap offsets (measured 0.857 -> 0.810 ms at config 3, profiles/r02h_rotate_ab.txt) wherever 32-bit offsets and float4 apply
+    if (X % 4 == 0 && aligned && (double)X * Y * Z < 2147483648.0) {
         RowTapsOff* tabo = nullptr;
         MVSIM_TRY(dev_alloc(ctx, (void**)&tabo, sizeof(RowTapsOff) * (size_t)Y * Zl));
         rotate_rowtable_off_kernel<<<blocks_for((size_t)Y * Zl, 256), 256, 0, ctx->stream>>>(tabo, X, Y, Z, zfirst, Zl, a);
