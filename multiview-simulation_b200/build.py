@@ -20,10 +20,16 @@ PACKED = os.environ.get("MVSIM_PACKED_FFT", "1") != "0"
 PACKED_X = os.environ.get("MVSIM_PACKED_X", "0") == "1"
 OBJ = os.path.join(ROOT, ("build_px" if PACKED_X else "build") if PACKED else "build_scalar")
 LIB = os.path.join(PKG, ("libmvsim_px.so" if PACKED_X else "libmvsim.so") if PACKED else "libmvsim_scalar.so")
+# generic A/B builds: MVSIM_VARIANT=<name> MVSIM_EXTRA_FLAGS="-DMVSIM_EXP_FOO=1" -> build_<name>/, libmvsim_<name>.so (MVSIM_LIB=... loads it)
+VARIANT = os.environ.get("MVSIM_VARIANT", "")
+EXTRA = os.environ.get("MVSIM_EXTRA_FLAGS", "").split()
+if VARIANT:
+    OBJ = os.path.join(ROOT, "build_" + VARIANT)
+    LIB = os.path.join(PKG, f"libmvsim_{VARIANT}.so")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", CSRC, "-I", os.path.join(ROOT, "include"),
-         f"-DMVSIM_PACKED_FFT={1 if PACKED else 0}", f"-DMVSIM_PACKED_X={1 if PACKED_X else 0}"]
+         f"-DMVSIM_PACKED_FFT={1 if PACKED else 0}", f"-DMVSIM_PACKED_X={1 if PACKED_X else 0}"] + EXTRA
 
 UNITS = [("stages", "stages.cu", []), ("phantom", "phantom.cu", []), ("conv", "conv.cu", []), ("capi", "capi.cu", [])] + \
         [(f"fft_g{g}_t{t}", os.path.join("fft", "fft_group.cu"), [f"-DMVSIM_GROUP={g}", f"-DMVSIM_LANES={t}"])

@@ -10,10 +10,10 @@
 namespace mvsim {
 
 // resident CTAs per SM the register allocator must allow, so that the load, exchange and store phases of
-// different tiles overlap: x passes 4 (<= 160 threads, forward) / 3 (<= 256 threads, inverse), strided passes 2 (T=8) / 4 (T=4).
+// different tiles overlap: x passes 4 (<= 192 threads: forward 144, inverse 192) / 3 (<= 256 threads), strided passes 2 (T=8) / 4 (T=4).
 template <class K> constexpr int min_blocks()
 {
-    return K::IS_X ? (K::THREADS <= 160 ? 4 : (K::THREADS <= 256 ? 3 : 1)) : (K::THREADS <= 160 ? 4 : (K::THREADS <= 288 ? 2 : 1));
+    return K::IS_X ? (K::THREADS <= 192 ? 4 : (K::THREADS <= 256 ? 3 : 1)) : (K::THREADS <= 160 ? 4 : (K::THREADS <= 288 ? 2 : 1));
 }
 
 // a kernel may state its own residency target (K::MIN_BLOCKS)

@@ -289,6 +289,8 @@ template <int N_, int INC_, int T_> struct ZFusedPoly {
                 RegSel<B, 1, kPackedStrided>::run(y);
                 const int k1 = g % A;
                 MVSIM_UNROLL
+                // (the twiddle does not depend on the phase, so it could follow the sum in the next phase -- a quarter of the multiplies,
+                // but on 4 warps instead of 10: measured 1.813 -> 1.809 ms, not worth the longer tail)
                 for (int n2 = 0; n2 < B; ++n2) row[n2 * T] = n2 == 0 ? y[0] : cmulc(y[n2], q.tw[INC * n2 * k1]);
             }
         } else if (PH == 3) {
