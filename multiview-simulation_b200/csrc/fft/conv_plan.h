@@ -17,6 +17,7 @@ struct FftSize { int n, a, b; };
 // profiles/r02_notes.md): the forward pass wants ~120 registers and spills under the 80-register cap of 3 CTAs x 10 rows; 6 rows x
 // 4 CTAs per SM (96 registers) 0.962 -> 0.920 ms.  The inverse pass: 10 rows x 3 CTAs 0.252 ms, 6 x 4 0.277; after its stores moved to
 // immediate offsets (80 registers without the address arithmetic) 10 x 3 0.238, 8 rows x 4 CTAs 0.229 ms (fft_group.cu: min_blocks).
+// (forward geometry measured again after the address-arithmetic change: 5 rows 0.844, 6 rows 0.837, 8 rows x 4 CTAs 0.865 ms)
 constexpr int kXThreadsFwd = 144, kXThreadsInv = 192;
 constexpr int x_rows_for(int target, int a, int b) { return (target / (a > b ? a : b)) > 0 ? target / (a > b ? a : b) : 1; }
 constexpr int x_rows_per_block(int a, int b, bool inverse) { return x_rows_for(inverse ? kXThreadsInv : kXThreadsFwd, a, b); }

@@ -389,7 +389,9 @@ int k_rotate_attenuate(mvsim_ctx* ctx, const float* in, float* out, const int64_
         MVSIM_TRY(dev_alloc(ctx, (void**)&tabo, sizeof(RowTapsOff) * (size_t)Y * Zl));
         rotate_rowtable_off_kernel<<<blocks_for((size_t)Y * Zl, 256), 256, 0, ctx->stream>>>(tabo, X, Y, Z, zfirst, Zl, a);
         ctx->launches++;
-        rotate_attenuate_off_kernel<3><<<blocks_for((size_t)(X / 4) * Zl, 128), 128, 0, ctx->stream>>>(in, out, tabo, X, Y, delta, steps, Zl, (unsigned)sizeof(float));
+        // rows per batch: 3 -> 4 once the tap addresses were single instructions (62 -> 70 registers, still 7 CTAs of 128 threads per SM
+        // = one wave at config 3): 0.798 -> 0.752 ms (profiles/r02_notes.md)
+        rotate_attenuate_off_kernel<4><<<blocks_for((size_t)(X / 4) * Zl, 128), 128, 0, ctx->stream>>>(in, out, tabo, X, Y, delta, steps, Zl, (unsigned)sizeof(float));
         ctx->launches++;
         cudaError_t eo = cudaGetLastError();
         dev_free(ctx, tabo);
