@@ -391,6 +391,7 @@ int k_rotate_attenuate(mvsim_ctx* ctx, const float* in, float* out, const int64_
         ctx->launches++;
         // rows per batch: 3 -> 4 once the tap addresses were single instructions (62 -> 70 registers, still 7 CTAs of 128 threads per SM
         // = one wave at config 3): 0.798 -> 0.752 ms (profiles/r02_notes.md)
+        // (CTAs of 64 threads: 0.738 against 0.740 ms -- no difference)
         rotate_attenuate_off_kernel<4><<<blocks_for((size_t)(X / 4) * Zl, 128), 128, 0, ctx->stream>>>(in, out, tabo, X, Y, delta, steps, Zl, (unsigned)sizeof(float));
         ctx->launches++;
         cudaError_t eo = cudaGetLastError();
