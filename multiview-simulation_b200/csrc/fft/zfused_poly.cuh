@@ -11,7 +11,8 @@
 // the phases and ONE M-point inverse -- no radix-INC combine stage on either forward side and a fifth (third) of an inverse,
 // against three N-point transforms of the spectral kernels (ZFusedOTF) or two and a pruned one (ZFusedDec).
 //
-// The plane with the sum of the DROPPED slices comes from the time domain: with Bpre[i] = sum_{j < i} b[j], B0 = Bpre[KZ],
+// The extra plane -- the sum of ALL cropped planes, see the end of this comment -- comes from the time domain: with
+// Bpre[i] = sum_{j < i} b[j], B0 = Bpre[KZ],
 //
 //     sum_{o < n_src} c[crop0 + o] = B0 * sum_{n < n_src} a'[n] + sum_{i = 1}^{KZ-1} Bpre[i] (a'[n_src + KZ-1 - i] - a'[KZ-1 - i])
 //
@@ -32,8 +33,9 @@
 //         loads) + stores, chunk scan | sum plane.
 // The inverse is linear, so the sum over the phases may come after its first half: every level-2 thread inverts the products it
 // holds in registers (INC times the work of inverting the sum, but on all warps and without the two barriers and the two
-// low-occupancy phases -- reduce, 2-warp inverse -- that cost 16 % of the kernel's warp samples in ncu r02g).
-// The extra plane carries the sum of ALL cropped planes (ZFusedParams::sum_total): the inverse x pass then takes adjustImage's mean
+// low-occupancy phases -- reduce, 2-warp inverse -- that cost 16 % of the kernel's warp samples in ncu r02g; the run time is
+// the same, 1.81 ms, the tail simpler).
+// The extra plane carries the sum of ALL cropped planes (conv_middle_z reports it): the inverse x pass then takes adjustImage's mean
 // from that plane alone (XParams::sum_row0), no bookkeeping of the kept planes here.
 #pragma once
 
@@ -48,7 +50,7 @@ constexpr int poly_groups(int a, int b, int inc)
     const int half = (l1 + 1) / 2;
     return l2 > half ? l2 : half;
 }
-constexpr int kPolyTaps = 4;        // PSF taps per border group (their differences live in registers)
+constexpr int kPolyTaps = 4;        // PSF taps per border group (their border samples live in registers between two phases)
 // may a z line of n points run ZFusedPoly<n, inc, T>?  (inc phases of a supported length n / inc, enough groups for the border terms)
 constexpr bool zfused_poly_ok(int n, int inc)
 {
