@@ -184,6 +184,9 @@ struct Activate {
     {
         if (cudaGetDevice(&prev) != cudaSuccess) return;
         ok = cudaSetDevice(ctx->device) == cudaSuccess;
+        // drop a stale, non-sticky error an earlier call of this host thread left behind (ours or the caller's): the launch
+        // checks of this entry point read cudaGetLastError() and must report their own failures only
+        if (ok) cudaGetLastError();
     }
     ~Activate() { if (prev >= 0) cudaSetDevice(prev); }
 };
