@@ -141,6 +141,8 @@ struct EmuLauncher {
 
 int EmuLauncher::decimated_launches = 0;
 extern "C" int emu_decimated_launches() { return EmuLauncher::decimated_launches; }
+// which (line length, inc) pairs the polyphase fused z kernel is built for, and how many PSF taps its border groups take
+extern "C" int emu_poly_ok(int n, int inc) { return (n % inc == 0 && fft_size_lookup(n).n == n && zfused_poly_ok(n, inc)) ? zfused_poly_max_taps(n, inc) : 0; }
 int EmuLauncher::polyphase_launches = 0;
 extern "C" int emu_polyphase_launches() { return EmuLauncher::polyphase_launches; }
 

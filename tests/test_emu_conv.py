@@ -250,3 +250,17 @@ def test_polyphase_kernel_is_vetoed_for_long_psf_lines(emu, oracle, monkeypatch)
     out, _ = _run(emu, vol, psf, keep_inc=5, planes=(441 - 1) // 5 + 2)
     assert emu.emu_polyphase_launches() == before
     assert rel_err(out[:-1], ref[::5]) < 5e-6
+
+
+def test_polyphase_kernel_applicability_table(emu):
+    """zfused_poly_ok: inc in {3, 5} divides the line, n / inc is a table size of >= 64 points, at most 40 groups of 8 lanes, no
+    split whose two gathered items per group would spill (measured slower than the decimated kernel at 576 points, inc 3)."""
+    emu.emu_poly_ok.restype = C.c_int
+    emu.emu_poly_ok.argtypes = [C.c_int, C.c_int]
+    ok = {(n, inc): emu.emu_poly_ok(n, inc) for n in (320, 324, 360, 384, 400, 432, 480, 512, 540, 576, 600, 625, 640, 648) for inc in (2, 3, 5)}
+    # BASELINE config 3: 640-point z lines at inc 5 -> 5 phases of 128 = 8 x 16 points, 40 groups, 4 taps x 32 border groups >= 128
+    assert ok[(640, 5)] == 128
+    assert ok[(360, 3)] > 0 and ok[(360, 5)] > 0 and ok[(320, 5)] > 0 and ok[(400, 5)] > 0
+    assert ok[(576, 3)] == 0 and ok[(648, 3)] == 0 and ok[(540, 3)] == 0      # two 12-sample items per group: spills, excluded
+    assert ok[(512, 5)] == 0 and ok[(625, 5)] == 0                            # 5 does not divide 512; 125 points is not a table size
+    assert all(v == 0 for (n, inc), v in ok.items() if inc == 2)
