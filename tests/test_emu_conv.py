@@ -264,3 +264,28 @@ def test_polyphase_kernel_applicability_table(emu):
     assert ok[(576, 3)] == 0 and ok[(648, 3)] == 0 and ok[(540, 3)] == 0      # two 12-sample items per group: spills, excluded
     assert ok[(512, 5)] == 0 and ok[(625, 5)] == 0                            # 5 does not divide 512; 125 points is not a table size
     assert all(v == 0 for (n, inc), v in ok.items() if inc == 2)
+
+
+def test_polyphase_pass_with_overlap_save_blocks_along_y(emu, oracle, monkeypatch):
+    """Every y block runs its own fused z pass; with the polyphase kernel each block's extra plane is the sum of ALL cropped planes
+    of its rows, and the inverse x pass counts that plane alone: the total must still be the sum of the whole convolved volume."""
+    monkeypatch.setenv("MVSIM_EMU_POLY", "1")
+    monkeypatch.setenv("MVSIM_EMU_OTF", "1")
+    emu.emu_polyphase_launches.restype = C.c_int
+    out = (C.c_int * 11)()
+    shape, kshape, inc, max_line = (344, 33, 3), (17, 4, 2), 3, 16
+    z, y, x = shape
+    kz, ky, kx = kshape
+    assert emu.emu_plan((C.c_int64 * 3)(x, y, z), (C.c_int64 * 3)(kx, ky, kz), out, max_line) == 0 and out[9] >= 2 and out[2] == 360
+    before = emu.emu_polyphase_launches()
+    rng = np.random.default_rng(24)
+    vol = rng.random(shape, dtype=np.float32)
+    psf = rng.random(kshape, dtype=np.float32)
+    ref = oracle.convolve(vol, psf, "direct")
+    nk = (z - 1) // inc + 1
+    got, s = _run(emu, vol, psf, keep_inc=inc, planes=nk + 1, max_line=max_line)
+    assert emu.emu_polyphase_launches() == before + out[9]          # one launch per y block
+    assert emu.emu_last_sum_plane_is_total() == 1
+    assert rel_err(got[:nk], ref[::inc]) < 5e-6
+    assert rel_err(got[nk], ref.astype(np.float64).sum(axis=0).astype(np.float32)) < 3e-5
+    assert s == pytest.approx(float(ref.astype(np.float64).sum()), rel=3e-6)
